@@ -1,0 +1,920 @@
+/*
+ * deplex_oracle.cpp -- CPU oracle for the deplex plane-extraction hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see deplex_oracle.h).  This file restates, in plain C++17 without
+ * Eigen, what `deplex::PlaneExtractor::process` computes.  Citations are file:line under the
+ * reference tree (prime-slam/deplex).  It is not a port of the reference's code structure: the
+ * reference's classes are flattened into per-cell arrays, and every floating-point expression
+ * is written out in the evaluation order the reference's build produces.
+ *
+ * PARITY STATUS -- "parity unpinned at the Eigen boundary".
+ *   The reference delegates three reductions to Eigen 3.4 (un-vendored: external/eigen3/
+ *   CMakeLists.txt:1-16 fetches tag 3.4; no copy exists in this image), so the reference cannot
+ *   be compiled here.  Their summation orders are restated from Eigen 3.4's published kernels:
+ *     - colwise().sum()        -> redux_impl<LinearVectorizedTraversal, NoUnrolling>  (Redux.h)
+ *     - X^T * X (3 x N x 3)    -> GEBP scalar remainder path, one sequential chain per entry
+ *                                 (GeneralBlockPanelKernel.h, cols < nr and rows < LhsProgress)
+ *     - fixed-size 3 dot/norm  -> redux_novec_unroller<0,3>: a0 + (a1 + a2)
+ *   for the reference's default x86-64 build (SSE2 packets of 4 floats, no FMA).  What IS pinned:
+ *     - the 3x3 eigensolver restatement is checked bit-for-bit against the reference's own
+ *       libs/dsyev sources compiled into oracle/_ref/ (tests/test_oracle_cpu.py);
+ *     - the reference's only numeric golden value for this path, max(labels)==34 on the TUM
+ *       frame (cpp/tests/test_plane_extractor.cpp:27-33), plus its zero/throw cases.
+ */
+#include "deplex_oracle.h"
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <limits>
+#include <queue>
+#include <random>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+// ----------------------------------------------------------------------------------------------
+// 3x3 symmetric eigensolver (Kopp 2006, "hybrid" variant).  Follows libs/dsyev/src/dsyevh3.c:31-134,
+// dsyevc3.c:31-80, dsyevq3.c:29-134 and dsytrd3.h:27-102 operation by operation (fp64, no FMA).
+// Only the upper triangle of A is read.  Matrices are row-major double[9].
+// ----------------------------------------------------------------------------------------------
+struct Sym3 {
+  double a00, a01, a02, a11, a12, a22;
+};
+
+inline double sq(double x) { return x * x; }
+
+// Cardano eigenvalues (dsyevc3.c:46-77).  Output order is the reference's: w[0] >= w[2] >= w[1]
+// in exact arithmetic.
+void eig3_cardano(const Sym3& A, double w[3]) {
+  const double de = A.a01 * A.a12;
+  const double dd = sq(A.a01);
+  const double ee = sq(A.a12);
+  const double ff = sq(A.a02);
+  const double m = A.a00 + A.a11 + A.a22;
+  const double c1 = (A.a00 * A.a11 + A.a00 * A.a22 + A.a11 * A.a22) - (dd + ee + ff);
+  const double c0 = A.a22 * dd + A.a00 * ee + A.a11 * ff - A.a00 * A.a11 * A.a22 - 2.0 * A.a02 * de;
+
+  const double p = sq(m) - 3.0 * c1;
+  const double q = m * (p - (3.0 / 2.0) * c1) - (27.0 / 2.0) * c0;
+  const double sqrt_p = std::sqrt(std::fabs(p));
+
+  double phi = 27.0 * (0.25 * sq(c1) * (p - c1) + c0 * (q + 27.0 / 4.0 * c0));
+  phi = (1.0 / 3.0) * std::atan2(std::sqrt(std::fabs(phi)), q);
+
+  const double kInvSqrt3 = 1.0 / 1.73205080756887729352744634151;
+  const double c = sqrt_p * std::cos(phi);
+  const double s = kInvSqrt3 * sqrt_p * std::sin(phi);
+
+  w[1] = (1.0 / 3.0) * (m - c);
+  w[2] = w[1] + s;
+  w[0] = w[1] + c;
+  w[1] -= s;
+}
+
+// Householder tridiagonalisation (dsytrd3.h:27-102): A = Q diag/offdiag Q^T.
+void eig3_tridiag(const Sym3& A, double Q[9], double d[3], double e[3]) {
+  for (int i = 0; i < 9; ++i) Q[i] = 0.0;
+  Q[0] = Q[4] = Q[8] = 1.0;
+
+  const double h = sq(A.a01) + sq(A.a02);
+  const double g = (A.a01 > 0) ? -std::sqrt(h) : std::sqrt(h);
+  e[0] = g;
+  double f = g * A.a01;
+  const double u1 = A.a01 - g;
+  const double u2 = A.a02;
+
+  double omega = h - f;
+  if (omega > 0.0) {
+    omega = 1.0 / omega;
+    double K = 0.0;
+    f = A.a11 * u1 + A.a12 * u2;
+    double q1 = omega * f;
+    K += u1 * f;
+    f = A.a12 * u1 + A.a22 * u2;
+    double q2 = omega * f;
+    K += u2 * f;
+    K *= 0.5 * sq(omega);
+
+    q1 = q1 - K * u1;
+    q2 = q2 - K * u2;
+
+    d[0] = A.a00;
+    d[1] = A.a11 - 2.0 * q1 * u1;
+    d[2] = A.a22 - 2.0 * q2 * u2;
+
+    // inverse Householder transformation, columns 1 and 2
+    f = omega * u1;
+    Q[4] = Q[4] - f * u1;
+    Q[7] = Q[7] - f * u2;
+    f = omega * u2;
+    Q[5] = Q[5] - f * u1;
+    Q[8] = Q[8] - f * u2;
+
+    e[1] = A.a12 - q1 * u2 - u1 * q2;
+  } else {
+    d[0] = A.a00;
+    d[1] = A.a11;
+    d[2] = A.a22;
+    e[1] = A.a12;
+  }
+}
+
+// QL with implicit shifts (dsyevq3.c:52-132).  On non-convergence the reference returns -1 and the
+// caller ignores it; the partially-updated Q/w are kept, as here.
+void eig3_ql(const Sym3& A, double Q[9], double w[3]) {
+  double e[3];
+  eig3_tridiag(A, Q, w, e);
+  e[2] = 0.0;
+  for (int l = 0; l < 2; ++l) {
+    int n_iter = 0;
+    for (;;) {
+      int m;
+      for (m = l; m <= 1; ++m) {
+        const double g = std::fabs(w[m]) + std::fabs(w[m + 1]);
+        if (std::fabs(e[m]) + g == g) break;
+      }
+      if (m == l) break;
+      if (n_iter++ >= 30) return;
+
+      double g = (w[l + 1] - w[l]) / (e[l] + e[l]);
+      double r = std::sqrt(sq(g) + 1.0);
+      if (g > 0)
+        g = w[m] - w[l] + e[l] / (g + r);
+      else
+        g = w[m] - w[l] + e[l] / (g - r);
+
+      double s = 1.0, c = 1.0, p = 0.0;
+      for (int i = m - 1; i >= l; --i) {
+        const double f = s * e[i];
+        const double b = c * e[i];
+        if (std::fabs(f) > std::fabs(g)) {
+          c = g / f;
+          r = std::sqrt(sq(c) + 1.0);
+          e[i + 1] = f * r;
+          s = 1.0 / r;
+          c *= s;
+        } else {
+          s = f / g;
+          r = std::sqrt(sq(s) + 1.0);
+          e[i + 1] = g * r;
+          c = 1.0 / r;
+          s *= c;
+        }
+        g = w[i + 1] - p;
+        r = (w[i] - g) * s + 2.0 * c * b;
+        p = s * r;
+        w[i + 1] = g + p;
+        g = c * r - b;
+        for (int k = 0; k < 3; ++k) {
+          const double t = Q[3 * k + i + 1];
+          Q[3 * k + i + 1] = s * Q[3 * k + i] + c * t;
+          Q[3 * k + i] = c * Q[3 * k + i] - s * t;
+        }
+      }
+      w[l] -= p;
+      e[l] = g;
+      e[m] = 0.0;
+    }
+  }
+}
+
+// Hybrid driver (dsyevh3.c:64-133).  Returns true when the QL branch was taken.
+bool eig3_hybrid(const Sym3& A, double Q[9], double w[3]) {
+  eig3_cardano(A, w);
+
+  double t = std::fabs(w[0]);
+  double u;
+  if ((u = std::fabs(w[1])) > t) t = u;
+  if ((u = std::fabs(w[2])) > t) t = u;
+  u = (t < 1.0) ? t : sq(t);
+  const double error = 256.0 * std::numeric_limits<double>::epsilon() * sq(u);
+
+  double q01 = A.a01 * A.a12 - A.a02 * A.a11;
+  double q11 = A.a02 * A.a01 - A.a12 * A.a00;
+  double q21 = sq(A.a01);
+
+  // first eigenvector: (A - w0 I) e1 x (A - w0 I) e2
+  double q00 = q01 + A.a02 * w[0];
+  double q10 = q11 + A.a12 * w[0];
+  double q20 = (A.a00 - w[0]) * (A.a11 - w[0]) - q21;
+  double norm = sq(q00) + sq(q10) + sq(q20);
+  if (norm <= error) {
+    eig3_ql(A, Q, w);
+    return true;
+  }
+  norm = std::sqrt(1.0 / norm);
+  q00 *= norm;
+  q10 *= norm;
+  q20 *= norm;
+
+  // second eigenvector
+  q01 = q01 + A.a02 * w[1];
+  q11 = q11 + A.a12 * w[1];
+  q21 = (A.a00 - w[1]) * (A.a11 - w[1]) - q21;
+  norm = sq(q01) + sq(q11) + sq(q21);
+  if (norm <= error) {
+    eig3_ql(A, Q, w);
+    return true;
+  }
+  norm = std::sqrt(1.0 / norm);
+  q01 *= norm;
+  q11 *= norm;
+  q21 *= norm;
+
+  Q[0] = q00; Q[3] = q10; Q[6] = q20;
+  Q[1] = q01; Q[4] = q11; Q[7] = q21;
+  // third = first x second
+  Q[2] = q10 * q21 - q20 * q11;
+  Q[5] = q20 * q01 - q00 * q21;
+  Q[8] = q00 * q11 - q10 * q01;
+  return false;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Eigen 3.4 reduction orders (un-vendored dependency; restated from its published algorithm).
+// ----------------------------------------------------------------------------------------------
+
+// DenseBase::sum() over a contiguous float column of length n whose first 16-byte-aligned element
+// is index `s` -- Eigen/src/Core/Redux.h, redux_impl<..., LinearVectorizedTraversal, NoUnrolling>,
+// SSE2 Packet4f, predux = (a0+a2)+(a1+a3).  Call site: cell_segment_stat.cpp:31.
+float eigen_sum_f32(const float* p, long n, long s) {
+  const long ps = 4;
+  if (s > n) s = n;
+  const long aligned_size2 = ((n - s) / (2 * ps)) * (2 * ps);
+  const long aligned_size = ((n - s) / ps) * ps;
+  const long end2 = s + aligned_size2;
+  const long end1 = s + aligned_size;
+  float res;
+  if (aligned_size) {
+    float a0[4] = {p[s], p[s + 1], p[s + 2], p[s + 3]};
+    if (aligned_size > ps) {
+      float a1[4] = {p[s + 4], p[s + 5], p[s + 6], p[s + 7]};
+      for (long i = s + 2 * ps; i < end2; i += 2 * ps) {
+        for (int l = 0; l < 4; ++l) a0[l] = a0[l] + p[i + l];
+        for (int l = 0; l < 4; ++l) a1[l] = a1[l] + p[i + 4 + l];
+      }
+      for (int l = 0; l < 4; ++l) a0[l] = a0[l] + a1[l];
+      if (end1 > end2)
+        for (int l = 0; l < 4; ++l) a0[l] = a0[l] + p[end2 + l];
+    }
+    res = (a0[0] + a0[2]) + (a0[1] + a0[3]);
+    for (long i = 0; i < s; ++i) res = res + p[i];
+    for (long i = end1; i < n; ++i) res = res + p[i];
+  } else {
+    res = p[0];
+    for (long i = 1; i < n; ++i) res = res + p[i];
+  }
+  return res;
+}
+
+// Fixed-size-3 dot product: a0*b0 + (a1*b1 + a2*b2)  (redux_novec_unroller<0,3>).
+inline float dot3(const float* a, const float* b) {
+  const float p0 = a[0] * b[0];
+  const float p1 = a[1] * b[1];
+  const float p2 = a[2] * b[2];
+  return p0 + (p1 + p2);
+}
+
+// ----------------------------------------------------------------------------------------------
+// CellSegmentStat (cell_segment_stat.h:25-70) flattened.
+// ----------------------------------------------------------------------------------------------
+struct Stat {
+  float d = 0.f;
+  float score = 0.f;
+  float mse = std::numeric_limits<float>::max();
+  int32_t n = 0;
+  float S[3] = {0, 0, 0};
+  float V[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // V[3*i+j] = (X^T X)(i,j)
+  float mean[3] = {0, 0, 0};
+  float normal[3] = {0, 0, 0};
+  double evals[3] = {0, 0, 0};
+  bool ql = false;
+};
+
+// CellSegmentStat::fitPlane (cell_segment_stat.cpp:55-81).
+void fit_plane(Stat& st) {
+  const float fn = static_cast<float>(st.n);
+  Sym3 A;
+  double cov[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      const float outer = st.S[i] * st.S[j];
+      const float c = st.V[3 * i + j] - outer / fn;
+      cov[3 * i + j] = c;
+    }
+  A.a00 = cov[0]; A.a01 = cov[1]; A.a02 = cov[2];
+  A.a11 = cov[4]; A.a12 = cov[5]; A.a22 = cov[8];
+
+  double Q[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double w[3];
+  st.ql = eig3_hybrid(A, Q, w);
+  for (int i = 0; i < 3; ++i) st.evals[i] = w[i];
+
+  int imin = 0, imax = 0;  // std::min_element / std::max_element: first of equals
+  for (int i = 1; i < 3; ++i) {
+    if (w[i] < w[imin]) imin = i;
+    if (w[imax] < w[i]) imax = i;
+  }
+  float v[3];
+  for (int i = 0; i < 3; ++i) v[i] = static_cast<float>(Q[3 * i + imin]);
+
+  float d = -dot3(st.mean, v);
+  if (d > 0) {
+    for (int i = 0; i < 3; ++i) st.normal[i] = v[i];
+  } else {
+    for (int i = 0; i < 3; ++i) st.normal[i] = -v[i];
+    d = -d;
+  }
+  st.d = d;
+  st.mse = static_cast<float>(w[imin] / st.n);
+  st.score = static_cast<float>(w[imax] / ((w[0] + w[1]) + w[2]));
+}
+
+// CellSegmentStat::operator+= (cell_segment_stat.cpp:37-43).
+void stat_add(Stat& a, const Stat& b) {
+  a.n += b.n;
+  for (int i = 0; i < 3; ++i) a.S[i] = a.S[i] + b.S[i];
+  for (int i = 0; i < 9; ++i) a.V[i] = a.V[i] + b.V[i];
+  const float fn = static_cast<float>(a.n);
+  for (int i = 0; i < 3; ++i) a.mean[i] = a.S[i] / fn;
+}
+
+struct Cell {
+  Stat st;
+  bool valid = false;
+  bool planar = false;
+  float tol = 0.f;
+};
+
+// CellSegment::CellSegment (cell_segment.cpp:21-35) on one cell whose points are given as the
+// column-major N x 3 temporary the reference materialises (x[N], y[N], z[N]).
+void build_cell(const float* x, const float* y, const float* z, long N, const dpxo_config& cfg, Cell& cell) {
+  const long p = cfg.patch_size;
+  // hasValidPoints (cell_segment.cpp:23,57-60): threshold uses size() == 3N, signed division.
+  const long thr_signed = (3 * N) / static_cast<long>(cfg.min_pts_per_cell);
+  const size_t thr = static_cast<size_t>(thr_signed);
+  long valid = 0;
+  for (long k = 0; k < N; ++k) valid += (z[k] > 0);
+  if (!(static_cast<size_t>(valid) >= thr)) return;
+
+  // isHorizontalContinuous (cell_segment.cpp:62-76)
+  {
+    const long middle = (p * p) / 2;
+    float prev = z[middle];
+    int32_t cnt = 0;
+    for (long i = middle; i < middle + p; ++i) {
+      const float cur = z[i];
+      if (cur > 0 && std::fabs(cur - prev) < cfg.depth_discontinuity_threshold)
+        prev = cur;
+      else if (cur > 0)
+        ++cnt;
+    }
+    if (!(cnt < cfg.max_number_depth_discontinuity)) return;
+  }
+  // isVerticalContinuous (cell_segment.cpp:78-91)
+  {
+    float prev = z[p / 2];
+    int32_t cnt = 0;
+    for (long i = p / 2; i < N; i += p) {
+      const float cur = z[i];
+      if (cur > 0 && std::fabs(cur - prev) < cfg.depth_discontinuity_threshold)
+        prev = cur;
+      else if (cur > 0)
+        ++cnt;
+    }
+    if (!(cnt < cfg.max_number_depth_discontinuity)) return;
+  }
+  cell.valid = true;
+
+  // CellSegmentStat(cell_points) (cell_segment_stat.cpp:29-35)
+  Stat& st = cell.st;
+  st.n = static_cast<int32_t>(N);
+  const float* col[3] = {x, y, z};
+  for (int j = 0; j < 3; ++j) {
+    const long s = (4 - ((j * N) % 4)) % 4;  // the temporary is 16-byte aligned; column j starts at j*N
+    st.S[j] = eigen_sum_f32(col[j], N, s);
+  }
+  // X^T X: GEMM path for N + 6 >= 20 -> one sequential chain per entry.
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      float c = 0.f;
+      const float* a = col[i];
+      const float* b = col[j];
+      for (long k = 0; k < N; ++k) c = a[k] * b[k] + c;
+      st.V[3 * i + j] = c;
+    }
+  const float fn = static_cast<float>(st.n);
+  for (int j = 0; j < 3; ++j) st.mean[j] = st.S[j] / fn;
+  fit_plane(st);
+
+  // hasSmallPlaneError (cell_segment.cpp:99-102)
+  const float thr_pl = cfg.depth_sigma_coeff * (st.mean[2] * st.mean[2]) + cfg.depth_sigma_margin;
+  cell.planar = static_cast<double>(st.mse) <= static_cast<double>(thr_pl) * static_cast<double>(thr_pl);
+
+  // calculateMergeTolerance (cell_segment.cpp:104-110), min distance 20.0 hard-coded at :34
+  const float sin_merge = std::sqrt(1.0f - cfg.min_cos_angle_merge * cfg.min_cos_angle_merge);
+  const float dx = x[0] - x[N - 1], dy = y[0] - y[N - 1], dz = z[0] - z[N - 1];
+  const float diam = std::sqrt(dx * dx + (dy * dy + dz * dz));
+  const float a = diam * sin_merge;
+  const float lo = 20.0f;
+  const float mx = (a < lo) ? lo : a;                               // std::max(a, lo)
+  const float trunc = (cfg.max_merge_dist < mx) ? cfg.max_merge_dist : mx;  // std::min(mx, hi)
+  cell.tol = trunc * trunc;
+}
+
+struct Extractor {
+  dpxo_config cfg;
+  int32_t h, w, nh, nv;
+  std::vector<std::vector<long>> neighbours;
+
+  // PlaneExtractor::Impl::Impl (plane_extractor.cpp:153-176)
+  Extractor(int32_t height, int32_t width, const dpxo_config& c) : cfg(c), h(height), w(width) {
+    nh = width / std::max(c.patch_size, 1);
+    nv = height / std::max(c.patch_size, 1);
+    cfg.patch_size = std::min(cfg.patch_size, std::min(height, width));
+    if (c.patch_size == 0)
+      throw std::runtime_error("Error! Invalid config parameter: patchSize(" + std::to_string(c.patch_size) +
+                               "). patchSize has to be positive.");
+    const long nc = static_cast<long>(nh) * nv;
+    neighbours.resize(nc > 0 ? nc : 0);
+    for (long i = 0; i < nc; ++i) {
+      const long r = i / nh, q = i % nh;
+      if (r >= 1) neighbours[i].push_back(i - nh);
+      if (r + 1 < nv) neighbours[i].push_back(i + nh);
+      if (q >= 1) neighbours[i].push_back(i - 1);
+      if (q + 1 < nh) neighbours[i].push_back(i + 1);
+    }
+  }
+
+  void process(const float* xyz, int64_t n_points, int layout, int32_t* labels, dpxo_debug* dbg);
+};
+
+void Extractor::process(const float* xyz, int64_t n_points, int layout, int32_t* labels, dpxo_debug* dbg) {
+  // size check (plane_extractor.cpp:188-194)
+  if (n_points != static_cast<int64_t>(w) * h)
+    throw std::runtime_error("Error! Number of points doesn't match image shape: " + std::to_string(n_points) +
+                             " != " + std::to_string(h) + " x " + std::to_string(w));
+  const long NP = n_points;
+  const long p = cfg.patch_size;
+  const long N = p * p;
+  const long nc = static_cast<long>(nh) * nv;
+  if (nc > 0) {
+    if (p < 4 || N > 676)
+      throw std::domain_error("oracle: patchSize outside the restated Eigen GEMM domain [4, 26]");
+    if (w % p != 0 || h % p != 0)
+      throw std::domain_error("oracle: image size not divisible by patchSize (undefined behaviour in the reference)");
+    if (cfg.min_pts_per_cell == 0) throw std::domain_error("oracle: minPtsPerCell == 0 (SIGFPE in the reference)");
+  }
+
+  // (copy A) column-major argument -> row-major temporary (cell_grid.h:36 takes a RowMajor const&).
+  std::vector<float> rowmajor;
+  const float* rm = xyz;
+  if (layout == DPXO_LAYOUT_COLMAJOR) {
+    rowmajor.resize(3 * NP);
+    for (long i = 0; i < NP; ++i) {
+      rowmajor[3 * i + 0] = xyz[i];
+      rowmajor[3 * i + 1] = xyz[NP + i];
+      rowmajor[3 * i + 2] = xyz[2 * NP + i];
+    }
+    rm = rowmajor.data();
+  }
+
+  // (copy B) cellContinuousOrganize (cell_grid.cpp:69-83)
+  std::vector<float> organized(3 * NP);
+  {
+    const long image_width = static_cast<long>(nh) * p;
+    for (long c = 0; c < nc; ++c) {
+      const long outer = N * c;
+      for (long i = 0; i < p; ++i) {
+        const long src = i * image_width + (c / nh) * image_width * p + (c * p) % image_width;
+        std::memcpy(&organized[3 * (outer + i * p)], &rm[3 * src], sizeof(float) * 3 * p);
+      }
+    }
+  }
+
+  // per-cell construction (cell_grid.cpp:37-43); (copy C) row-major map -> column-major temporary
+  std::vector<Cell> cells(nc);
+  {
+    std::vector<float> tmp(3 * N);
+    for (long c = 0; c < nc; ++c) {
+      const float* src = &organized[3 * N * c];
+      float* x = tmp.data();
+      float* y = x + N;
+      float* z = y + N;
+      for (long k = 0; k < N; ++k) {
+        x[k] = src[3 * k];
+        y[k] = src[3 * k + 1];
+        z[k] = src[3 * k + 2];
+      }
+      build_cell(x, y, z, N, cfg, cells[c]);
+    }
+  }
+
+  // NormalsHistogram (plane_extractor.cpp:285-295, normals_histogram.cpp:21-49)
+  const int32_t B = cfg.histogram_bins_per_coord;
+  std::vector<int32_t> hist(static_cast<size_t>(std::max(B, 0)) * std::max(B, 0), 0);
+  std::vector<int32_t> bins(nc, -1);
+  for (long c = 0; c < nc; ++c) {
+    if (!cells[c].planar) continue;
+    const float* n = cells[c].st.normal;
+    const float prec = 1e-5f;  // Eigen isZero() default precision for float
+    if (std::fabs(n[0]) <= prec && std::fabs(n[1]) <= prec && std::fabs(n[2]) <= prec) continue;
+    const double nx = n[0], ny = n[1];
+    const double proj = std::sqrt(nx * nx + ny * ny);
+    const double polar = ::acos(static_cast<double>(-n[2]));
+    const double azimuth = ::atan2(nx / proj, ny / proj);
+    const double min_x = 0, max_x = M_PI, min_y = -M_PI, max_y = M_PI;
+    const int32_t xq = static_cast<int32_t>((B - 1) * (polar - min_x) / (max_x - min_x));
+    int32_t yq = 0;
+    if (xq > 0) yq = static_cast<int32_t>((B - 1) * (azimuth - min_y) / (max_y - min_y));
+    const int32_t bin = yq * B + xq;
+    if (bin < 0 || bin >= static_cast<int32_t>(hist.size()))
+      throw std::domain_error("oracle: histogram bin out of range (out-of-bounds write in the reference)");
+    bins[c] = bin;
+    ++hist[bin];
+  }
+  if (dbg && dbg->cell_bin)
+    for (long c = 0; c < nc; ++c) dbg->cell_bin[c] = bins[c];
+
+  // createPlaneSegments (plane_extractor.cpp:297-347)
+  std::vector<Stat> segs;
+  std::vector<int32_t> labels_map(nc, 0);
+  std::vector<char> unassigned(nc);
+  int32_t remaining = 0;
+  for (long c = 0; c < nc; ++c) {
+    unassigned[c] = cells[c].planar;
+    remaining += cells[c].planar;
+  }
+  int32_t n_seeds = 0;
+  std::vector<char> activated(nc);
+  std::vector<long> order;
+  order.reserve(nc);
+  while (remaining > 0) {
+    // getPointsFromMostFrequentBin (normals_histogram.cpp:51-67): first maximum, ascending ids
+    std::vector<int32_t> cand;
+    {
+      const auto it = std::max_element(hist.begin(), hist.end());
+      const int32_t occ = *it;
+      const long bin_id = it - hist.begin();
+      if (occ > 0)
+        for (long c = 0; c < nc; ++c)
+          if (bins[c] == bin_id) cand.push_back(static_cast<int32_t>(c));
+    }
+    if (cand.size() < static_cast<size_t>(cfg.min_region_growing_candidate_size)) break;
+    // seed = first strict minimum of MSE (plane_extractor.cpp:309-316)
+    long seed = -1;
+    double min_mse = INT_MAX;
+    for (int32_t c : cand)
+      if (cells[c].st.mse < min_mse) {
+        seed = c;
+        min_mse = cells[c].st.mse;
+      }
+    if (seed < 0) throw std::domain_error("oracle: no seed below INT_MAX (uninitialised read in the reference)");
+    ++n_seeds;
+
+    // growSeed (plane_extractor.cpp:349-392): FIFO BFS, frontier-relative test
+    order.clear();
+    if (unassigned[seed]) {
+      std::fill(activated.begin(), activated.end(), 0);
+      std::queue<long> fifo;
+      fifo.push(seed);
+      activated[seed] = 1;
+      order.push_back(seed);
+      while (!fifo.empty()) {
+        const long cur = fifo.front();
+        fifo.pop();
+        const double d_cur = cells[cur].st.d;
+        const float* n_cur = cells[cur].st.normal;
+        for (long nb : neighbours[cur]) {
+          if (!unassigned[nb] || activated[nb]) continue;
+          const double cos_angle = dot3(n_cur, cells[nb].st.normal);
+          const double t = dot3(n_cur, cells[nb].st.mean) + d_cur;  // float + double
+          const double merge_dist = t * t;
+          if (cos_angle >= cfg.min_cos_angle_merge && merge_dist <= cells[nb].tol) {
+            activated[nb] = 1;
+            order.push_back(nb);
+            fifo.push(nb);
+          }
+        }
+      }
+    }
+
+    // accumulate (the seed is counted twice: copy-constructed, then += itself) (:318-327)
+    Stat cand_stat = cells[seed].st;
+    for (long v : order) {
+      stat_add(cand_stat, cells[v].st);
+      --hist[bins[v]];
+      bins[v] = -1;
+      unassigned[v] = 0;
+      --remaining;
+    }
+    if (order.size() < static_cast<size_t>(cfg.min_region_growing_cells_activated)) continue;
+    fit_plane(cand_stat);
+    if (cand_stat.score > cfg.min_region_planarity_score) {
+      segs.push_back(cand_stat);
+      const int32_t id = static_cast<int32_t>(segs.size());
+      for (long v : order) labels_map[v] = id;
+    }
+  }
+
+  if (dbg) {
+    for (long c = 0; c < nc; ++c) {
+      const Cell& ce = cells[c];
+      if (dbg->cell_valid) dbg->cell_valid[c] = ce.valid;
+      if (dbg->cell_planar) dbg->cell_planar[c] = ce.planar;
+      if (dbg->cell_sum) std::memcpy(dbg->cell_sum + 3 * c, ce.st.S, 12);
+      if (dbg->cell_var) std::memcpy(dbg->cell_var + 9 * c, ce.st.V, 36);
+      if (dbg->cell_mean) std::memcpy(dbg->cell_mean + 3 * c, ce.st.mean, 12);
+      if (dbg->cell_normal) std::memcpy(dbg->cell_normal + 3 * c, ce.st.normal, 12);
+      if (dbg->cell_d) dbg->cell_d[c] = ce.st.d;
+      if (dbg->cell_mse) dbg->cell_mse[c] = ce.st.mse;
+      if (dbg->cell_score) dbg->cell_score[c] = ce.st.score;
+      if (dbg->cell_tol) dbg->cell_tol[c] = ce.tol;
+      if (dbg->cell_eval) std::memcpy(dbg->cell_eval + 3 * c, ce.st.evals, 24);
+      if (dbg->cell_seglabel) dbg->cell_seglabel[c] = labels_map[c];
+    }
+    if (dbg->n_seeds) *dbg->n_seeds = n_seeds;
+    if (dbg->n_ql_fallback) {
+      int32_t q = 0;
+      for (long c = 0; c < nc; ++c) q += (cells[c].valid && cells[c].st.ql);
+      *dbg->n_ql_fallback = q;
+    }
+    if (dbg->n_planes) *dbg->n_planes = static_cast<int32_t>(segs.size());
+  }
+
+  // early exit (plane_extractor.cpp:230-232)
+  std::fill(labels, labels + NP, 0);
+  if (segs.empty()) return;
+
+  // getConnectedComponents (plane_extractor.cpp:430-453): last cell row / column skipped
+  const size_t P = segs.size();
+  std::vector<std::vector<char>> assoc(P, std::vector<char>(P, 0));
+  for (long r = 0; r < nv - 1; ++r)
+    for (long q = 0; q < nh - 1; ++q) {
+      const int32_t id = labels_map[r * nh + q];
+      if (id > 0) {
+        const int32_t right = labels_map[r * nh + q + 1];
+        const int32_t down = labels_map[(r + 1) * nh + q];
+        if (right > 0 && id != right) assoc[id - 1][right - 1] = 1;
+        if (down > 0 && id != down) assoc[id - 1][down - 1] = 1;
+      }
+    }
+  for (size_t r = 0; r < P; ++r)
+    for (size_t q = 0; q < P; ++q) assoc[r][q] = assoc[r][q] || assoc[q][r];
+
+  // findMergedLabels (plane_extractor.cpp:394-426)
+  std::vector<int32_t> ml(P);
+  for (size_t i = 0; i < P; ++i) ml[i] = static_cast<int32_t>(i);
+  for (size_t r = 0; r < P; ++r) {
+    const int32_t a = ml[r];
+    bool expanded = false;
+    for (size_t t = r + 1; t < P; ++t) {
+      if (!assoc[r][t]) continue;
+      const double cos_angle = dot3(segs[a].normal, segs[t].normal);
+      const float dist_f = dot3(segs[a].normal, segs[t].mean) + segs[a].d;  // float + float
+      const double distance = static_cast<double>(dist_f) * static_cast<double>(dist_f);
+      if (cos_angle > cfg.min_cos_angle_merge && distance < cfg.max_merge_dist) {
+        stat_add(segs[a], segs[t]);
+        ml[t] = a;
+        expanded = true;
+      }
+    }
+    if (expanded) fit_plane(segs[a]);
+  }
+
+  if (dbg) {
+    const size_t cap = static_cast<size_t>(std::max(dbg->plane_capacity, 0));
+    for (size_t i = 0; i < P && i < cap; ++i) {
+      if (dbg->plane_normal) std::memcpy(dbg->plane_normal + 3 * i, segs[i].normal, 12);
+      if (dbg->plane_mean) std::memcpy(dbg->plane_mean + 3 * i, segs[i].mean, 12);
+      if (dbg->plane_d) dbg->plane_d[i] = segs[i].d;
+      if (dbg->plane_mse) dbg->plane_mse[i] = segs[i].mse;
+      if (dbg->plane_score) dbg->plane_score[i] = segs[i].score;
+      if (dbg->plane_npts) dbg->plane_npts[i] = segs[i].n;
+      if (dbg->merge_labels) dbg->merge_labels[i] = ml[i];
+    }
+  }
+
+  // toImageLabels (plane_extractor.cpp:455-470)
+  for (long row = 0; row < h; ++row)
+    for (long col = 0; col < w; ++col) {
+      const int32_t l = labels_map[(row / p) * nh + col / p];
+      labels[row * w + col] = (l == 0 ? 0 : ml[l - 1] + 1);
+    }
+
+  // refineLabels (plane_extractor.cpp:472-509) + RTL::PlaneRANSAC (libs/rtl/include/rtl/RANSAC.hpp:25-111)
+  // + PlaneEstimator (Plane.hpp:13-49).  Uses this host's libstdc++ <random>, as the reference does.
+  if (cfg.ransac_refinement) {
+    auto px = [&](long i, int a) -> float {
+      return layout == DPXO_LAYOUT_COLMAJOR ? xyz[a * NP + i] : xyz[3 * i + a];
+    };
+    int32_t max_label = 0;
+    for (long i = 0; i < NP; ++i) max_label = std::max(max_label, labels[i]);
+    std::vector<std::vector<int32_t>> idx(max_label);
+    for (long i = 0; i < NP; ++i)
+      if (labels[i] != 0) idx[labels[i] - 1].push_back(static_cast<int32_t>(i));
+
+    std::mt19937 gen;  // one generator per refineLabels call, shared across labels
+    const int max_iter = cfg.ransac_max_iterations;
+    const double thr = cfg.ransac_threshold;
+    const double ratio = cfg.ransac_inliers_ratio;
+    for (auto& pts : idx) {
+      if (pts.empty()) continue;
+      const int n = static_cast<int>(pts.size());
+      float best[4] = {0, 0, 0, 0};
+      std::uniform_int_distribution<int> uni(0, n - 1);
+      double bestloss = HUGE_VAL;
+      int iteration = 0;
+      for (;;) {
+        // IsContinued(iteration, N - bestloss, N): int(N - inf) is INT_MIN on x86-64
+        const int inl = std::isinf(bestloss) ? INT_MIN : static_cast<int>(n - bestloss);
+        if (!(iteration < max_iter && inl < ratio * n)) break;
+        ++iteration;
+        std::set<int> smp;
+        while (static_cast<int>(smp.size()) < 3) smp.insert(uni(gen));
+        auto it = smp.begin();
+        const long i0 = pts[*it++], i1 = pts[*it++], i2 = pts[*it++];
+        const float x0 = px(i0, 0), x1 = px(i1, 0), x2 = px(i2, 0);
+        const float y0 = px(i0, 1), y1 = px(i1, 1), y2 = px(i2, 1);
+        const float z0 = px(i0, 2), z1 = px(i1, 2), z2 = px(i2, 2);
+        const float D = x0 * y1 - x1 * y0 - x0 * y2 + x2 * y0 + x1 * y2 - x2 * y1;
+        const float a = (z0 * (y1 - y2)) / D - (z1 * (y0 - y2)) / D + (z2 * (y0 - y1)) / D;
+        const float b = (z1 * (x0 - x2)) / D - (z0 * (x1 - x2)) / D - (z2 * (x0 - x1)) / D;
+        const float d = (z2 * (x0 * y1 - x1 * y0)) / D - (z1 * (x0 * y2 - x2 * y0)) / D + (z0 * (x1 * y2 - x2 * y1)) / D;
+        const float c = -1.0f;
+        const float l = static_cast<float>(std::sqrt(static_cast<double>(a * a + b * b + c * c)));
+        const float model[4] = {a / l, b / l, c / l, d / l};
+        double loss = 0;
+        for (int i = 0; i < n; ++i) {
+          const long pi = pts[i];
+          const double e = model[0] * px(pi, 0) + model[1] * px(pi, 1) + model[2] * px(pi, 2) + model[3];
+          loss += (std::fabs(e) >= thr);
+        }
+        if (loss < bestloss) {
+          std::memcpy(best, model, sizeof(best));
+          bestloss = loss;
+        }
+      }
+      // FindInliers + relabel (plane_extractor.cpp:498-507)
+      std::vector<int> inliers;
+      for (int i = 0; i < n; ++i) {
+        const long pi = pts[i];
+        const double e = best[0] * px(pi, 0) + best[1] * px(pi, 1) + best[2] * px(pi, 2) + best[3];
+        if (std::fabs(e) < thr) inliers.push_back(i);
+      }
+      size_t cur = 0;
+      for (int i = 0; i < n && cur < inliers.size(); ++i) {
+        if (inliers[cur] != i)
+          labels[pts[i]] = 0;
+        else
+          ++cur;
+      }
+    }
+  }
+}
+
+void set_err(char* err, int errlen, const char* msg) {
+  if (err && errlen > 0) {
+    std::strncpy(err, msg, errlen - 1);
+    err[errlen - 1] = 0;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+void dpxo_config_default(dpxo_config* c) {
+  // config.h:51-81
+  c->patch_size = 10;
+  c->histogram_bins_per_coord = 20;
+  c->min_cos_angle_merge = 0.90;
+  c->max_merge_dist = 500;
+  c->min_region_growing_candidate_size = 5;
+  c->min_region_growing_cells_activated = 4;
+  c->min_region_planarity_score = 0.55;
+  c->depth_sigma_coeff = 1.425e-6;
+  c->depth_sigma_margin = 10.;
+  c->min_pts_per_cell = 3;
+  c->depth_discontinuity_threshold = 160;
+  c->max_number_depth_discontinuity = 1;
+  c->ransac_refinement = 0;
+  c->ransac_max_iterations = 1000;
+  c->ransac_threshold = 1.;
+  c->ransac_inliers_ratio = 0.9;
+}
+
+// Config(std::string const&) (config.cpp:28-80)
+int dpxo_config_load_ini(const char* path, dpxo_config* c, char* err, int errlen) {
+  dpxo_config_default(c);
+  std::ifstream f(path);
+  if (!f.is_open()) {
+    set_err(err, errlen, (std::string("Couldn't open ini file: ") + path).c_str());
+    return 1;
+  }
+  try {
+    while (f) {
+      std::string line;
+      std::getline(f, line);
+      if (line.empty() || line[0] == '#') continue;
+      const size_t eq = line.find_first_of('=');
+      if (eq == std::string::npos || eq == 0) continue;
+      const std::string key = line.substr(0, eq), value = line.substr(eq + 1);
+      if (key == "patchSize") c->patch_size = std::stoi(value);
+      else if (key == "histogramBinsPerCoord") c->histogram_bins_per_coord = std::stoi(value);
+      else if (key == "minCosAngleForMerge") c->min_cos_angle_merge = std::stof(value);
+      else if (key == "maxMergeDist") c->max_merge_dist = std::stof(value);
+      else if (key == "minRegionGrowingCandidateSize") c->min_region_growing_candidate_size = std::stoi(value);
+      else if (key == "minRegionGrowingCellsActivated") c->min_region_growing_cells_activated = std::stoi(value);
+      else if (key == "minRegionPlanarityScore") c->min_region_planarity_score = std::stof(value);
+      else if (key == "depthSigmaCoeff") c->depth_sigma_coeff = std::stof(value);
+      else if (key == "depthSigmaMargin") c->depth_sigma_margin = std::stof(value);
+      else if (key == "minPtsPerCell") c->min_pts_per_cell = std::stoi(value);
+      else if (key == "depthDiscontinuityThreshold") c->depth_discontinuity_threshold = std::stof(value);
+      else if (key == "maxNumberDepthDiscontinuity") c->max_number_depth_discontinuity = std::stoi(value);
+      else if (key == "ransacRefinement") c->ransac_refinement = static_cast<bool>(std::stoi(value));
+      else if (key == "ransacMaxIterations") c->ransac_max_iterations = std::stoi(value);
+      else if (key == "ransacThreshold") c->ransac_threshold = std::stof(value);
+      else if (key == "ransacInliersRatio") c->ransac_inliers_ratio = std::stof(value);
+      else std::cerr << "Unknown parameter name: " << key << '\n';
+    }
+  } catch (const std::exception& e) {
+    set_err(err, errlen, e.what());
+    return 1;
+  }
+  return 0;
+}
+
+int dpxo_process(int32_t h, int32_t w, const dpxo_config* cfg, const float* xyz, int64_t n_points, int layout,
+                 int32_t* labels, dpxo_debug* dbg, char* err, int errlen) {
+  try {
+    Extractor ex(h, w, *cfg);
+    ex.process(xyz, n_points, layout, labels, dbg);
+  } catch (const std::domain_error& e) {
+    set_err(err, errlen, e.what());
+    return 2;
+  } catch (const std::exception& e) {
+    set_err(err, errlen, e.what());
+    return 1;
+  }
+  return 0;
+}
+
+int dpxo_process_batch(int32_t h, int32_t w, const dpxo_config* cfg, const float* xyz, int32_t n_frames, int layout,
+                       int32_t* labels, int32_t n_threads, char* err, int errlen) {
+  if (n_threads < 1) n_threads = 1;
+  const int64_t NP = static_cast<int64_t>(h) * w;
+  std::vector<int> rc(n_threads, 0);
+  std::vector<std::string> msgs(n_threads);
+  auto work = [&](int t) {
+    try {
+      Extractor ex(h, w, *cfg);
+      for (int32_t f = t; f < n_frames; f += n_threads) ex.process(xyz + 3 * NP * f, NP, layout, labels + NP * f, nullptr);
+    } catch (const std::exception& e) {
+      rc[t] = 1;
+      msgs[t] = e.what();
+    }
+  };
+  if (n_threads == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(work, t);
+    for (auto& t : th) t.join();
+  }
+  for (int t = 0; t < n_threads; ++t)
+    if (rc[t]) {
+      set_err(err, errlen, msgs[t].c_str());
+      return 1;
+    }
+  return 0;
+}
+
+int dpxo_eig3(const double* A, double* Q, double* w) {
+  Sym3 S{A[0], A[1], A[2], A[4], A[5], A[8]};
+  return eig3_hybrid(S, Q, w) ? 1 : 0;
+}
+
+void dpxo_depth_to_cloud(const uint16_t* depth, int32_t h, int32_t w, float fx, float fy, float cx, float cy,
+                         float* out) {
+  // depth_image.cpp:64-73: z = float(raw); x = (col - cx) * z / fx; y = (row - cy) * z / fy  (fp32, left to right)
+  for (int32_t r = 0; r < h; ++r)
+    for (int32_t c = 0; c < w; ++c) {
+      const long i = static_cast<long>(r) * w + c;
+      const float z = static_cast<float>(depth[i]);
+      out[3 * i + 0] = (static_cast<float>(c) - cx) * z / fx;
+      out[3 * i + 1] = (static_cast<float>(r) - cy) * z / fy;
+      out[3 * i + 2] = z;
+    }
+}
+
+}  // extern "C"
