@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of the plane-extraction hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference CPU path (oracle port), host cores
+
+A "step" is one pass of the hot path over one batch of 256 synthetic 640x480 organized clouds
+(BASELINE.json configs[2]).  `value` is device-resident throughput (inputs already in HBM); `e2e` is the
+same metric through the host-pointer C-ABI call with pinned host buffers, H2D and D2H inside the timed
+region.  One process per GPU; frames are independent, so ranks shard frames with no data-path collective
+(weak scaling: every rank processes its own 256-frame batch per step).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "frames/sec @640x480 (batched, 256 frames/batch)"
+UNIT = "frames/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=256, help="frames per batch (per GPU)")
+    ap.add_argument("--unique", type=int, default=64, help="distinct synthetic frames generated per rank, tiled to --frames")
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--patch", type=int, default=10)
+    ap.add_argument("--layout", default="rowmajor", choices=["rowmajor", "colmajor"])
+    ap.add_argument("--cpu-sample-frames", type=int, default=0, help="frames in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, extra=None):
+    cfg = {
+        "workload": f"configs[2]: batched synthetic piecewise-planar {a.width}x{a.height} organized clouds, "
+                    f"{a.frames} frames/batch, default Config (patchSize={a.patch}), noise + holes",
+        "frames_per_batch": a.frames, "height": a.height, "width": a.width, "patch_size": a.patch,
+        "layout": a.layout, "unique_frames": min(a.unique, a.frames),
+        "l2": "inputs larger than L2 (batch input %.0f MB vs 126 MB L2)" % (a.frames * a.height * a.width * 12 / 1e6),
+        "parallelism": "frame-sharded, one process per GPU, no data-path collective",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def make_host_batch(a, rank):
+    from deplex_b200 import synth
+    uniq = min(a.unique, a.frames)
+    base = synth.make_batch(a.height, a.width, rank * 100000, uniq, a.layout)
+    reps = (a.frames + uniq - 1) // uniq
+    return np.concatenate([base] * reps, axis=0)[: a.frames]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(a, host_batch, threads, sample_frames):
+    """The oracle (a port of the reference's CPU algorithm) timed on this box's host cores."""
+    import oracle
+    from deplex_b200 import Config
+    cfg = oracle.OracleConfig(**Config(patch_size=a.patch).as_dict())
+    layout = 1 if a.layout == "rowmajor" else 0
+    sample = host_batch[:sample_frames]
+    oracle.process_batch(a.height, a.width, cfg, sample[: max(1, threads)], layout, threads)  # warm
+    t0 = time.perf_counter()
+    oracle.process_batch(a.height, a.width, cfg, sample, layout, threads)
+    dt = time.perf_counter() - t0
+    return sample.shape[0] / dt, dt
+
+
+def run_reference(a):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference cannot be compiled here
+    (Eigen 3.4 is fetched from the network by its build), so this times the oracle port on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    host_batch = make_host_batch(a, 0)
+    per_step = min(a.frames, max(threads, 16 * threads))
+    per_step = min(per_step, host_batch.shape[0])
+    import oracle
+    from deplex_b200 import Config
+    cfg = oracle.OracleConfig(**Config(patch_size=a.patch).as_dict())
+    layout = 1 if a.layout == "rowmajor" else 0
+    sample = host_batch[:per_step]
+    for _ in range(a.warmup):
+        oracle.process_batch(a.height, a.width, cfg, sample, layout, threads)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        oracle.process_batch(a.height, a.width, cfg, sample, layout, threads)
+    dt = time.perf_counter() - t0
+    value = a.steps * per_step / dt
+    sample_desc = f"{per_step} frames/step of the same batch, {threads} threads, frame-parallel"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import deplex_b200
+    from deplex_b200 import Config, PlaneExtractor, LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lay = LAYOUT_ROWMAJOR if a.layout == "rowmajor" else LAYOUT_COLMAJOR
+    host_np = make_host_batch(a, rank)
+    n_px = a.height * a.width
+    pin_in = torch.empty(host_np.shape, dtype=torch.float32).pin_memory()
+    pin_in.copy_(torch.from_numpy(host_np))
+    pin_out = torch.empty((a.frames, n_px), dtype=torch.int32).pin_memory()
+    d_xyz = pin_in.to(dev, non_blocking=False)
+    d_lab = torch.empty((a.frames, n_px), dtype=torch.int32, device=dev)
+
+    cfg = Config(patch_size=a.patch)
+    ex = PlaneExtractor(a.height, a.width, cfg, max_batch=a.frames, device=local)
+    stream = torch.cuda.current_stream(dev)
+
+    # ---- device-resident throughput ---------------------------------------------------------------
+    for _ in range(max(a.warmup, 3)):
+        ex.process_batch_device(d_xyz, lay, d_lab, stream)
+    torch.cuda.synchronize()
+    ex.set_profiling(True)
+    stage_acc = {}
+    sampler = ClockSampler(local)
+    launches0 = ex.kernel_launches()
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(a.steps):
+        ex.process_batch_device(d_xyz, lay, d_lab, stream)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = ex.kernel_launches() - launches0
+    elapsed_ms = e0.elapsed_time(e1)
+    ex.set_profiling(False)
+    # per-stage CUDA-event times (on the launching stream), averaged over a separate short run so the
+    # event records do not sit inside the timed region above
+    ex.set_profiling(True)
+    n_prof = min(a.steps, 10)
+    for _ in range(n_prof):
+        ex.process_batch_device(d_xyz, lay, d_lab, stream)
+        torch.cuda.synchronize()
+        for k, v in ex.stage_ms().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v / n_prof
+    ex.set_profiling(False)
+
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+    value = world * a.steps * a.frames / (max_ms / 1e3)
+
+    # ---- end to end: host pointers, pinned memory, H2D + D2H inside the timed region ------------------
+    e2e = None
+    if not a.no_e2e:
+        for _ in range(2):
+            ex.process_batch_host_ptr(pin_in.data_ptr(), a.frames, lay, pin_out.data_ptr())
+        k_e2e = max(3, min(a.steps, 10))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            ex.process_batch_host_ptr(pin_in.data_ptr(), a.frames, lay, pin_out.data_ptr())
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * k_e2e * a.frames / float(t.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(a.frames * n_px * 12), "d2h_bytes_per_step": int(a.frames * n_px * 4),
+               "steps": k_e2e, "api": "dpx_process_batch_host (pinned host buffers, chunked copy/compute overlap)",
+               "labels_checksum": int(pin_out.view(-1)[:: 997].to(torch.int64).sum().item())}
+        same = bool(torch.equal(pin_out, d_lab.cpu()))
+        e2e["matches_device_path"] = same
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+    n_cells = ex.info.n_cells
+    alg_bytes = {  # algorithmic bytes per launch
+        "cell_stats": a.frames * n_px * 12,
+        "region_grow": a.frames * n_cells * 82,
+        "labeling": a.frames * n_px * 4,
+    }
+    stages = {}
+    for k in ("cell_stats", "region_grow", "labeling"):
+        ms = stage_acc.get(k, 0.0)
+        gbs = alg_bytes[k] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        stages[k] = {"ms": ms, "algorithmic_bytes": alg_bytes[k], "gbs": gbs, "frac": gbs / peak}
+    dominant = max(stages, key=lambda k: stages[k]["ms"])
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": stages[dominant]["gbs"], "peak": peak,
+                "unit": "GB/s", "frac": stages[dominant]["frac"], "traffic": None, "peak_source": peak_src,
+                "stages": stages}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": max_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(a), "clocks": clocks, "gpu_launches": launches,
+        "roofline": roofline, "latency_ms_per_frame_in_batch": max_ms / a.steps / a.frames,
+    }
+    if e2e:
+        out["e2e"] = e2e
+    if world == 1 and not a.no_cpu_baseline:
+        n = a.cpu_sample_frames or a.frames
+        reps = 4
+        sample = np.concatenate([host_np[:n]] * reps, axis=0)
+        v, dt = cpu_baseline(a, sample, 1, sample.shape[0])
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                               "sample": f"{sample.shape[0]} frames ({n} of this batch x{reps}), 1 thread (the reference is "
+                                         f"single-threaded by default), {dt:.1f} s; host has {os.cpu_count()} cores"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

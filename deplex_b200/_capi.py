@@ -1,0 +1,93 @@
+"""ctypes declarations for libdeplex_b200.so (include/deplex_b200.h).  No arithmetic happens in Python."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdeplex_b200.so")
+
+DPX_OK, DPX_ERR_RUNTIME, DPX_ERR_UNSUPPORTED, DPX_ERR_CUDA, DPX_ERR_ARGUMENT = range(5)
+LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR = 0, 1
+N_STAGES = 4
+STAGE_NAMES = ("cell_stats", "region_grow", "labeling", "refine")
+
+# every symbol include/deplex_b200.h declares (checked by tests/test_capi_cpu.py)
+EXPORTS = (
+    "dpx_config_default", "dpx_config_load_ini", "dpx_create", "dpx_destroy", "dpx_last_error", "dpx_get_info",
+    "dpx_process_host", "dpx_process_batch_host", "dpx_process_batch_device", "dpx_get_cells", "dpx_get_planes",
+    "dpx_set_profiling", "dpx_get_stage_ms", "dpx_kernel_launches", "dpx_host_alloc", "dpx_host_free", "dpx_version",
+)
+
+
+class dpx_config(C.Structure):
+    _fields_ = [
+        ("patch_size", C.c_int32), ("histogram_bins_per_coord", C.c_int32),
+        ("min_cos_angle_merge", C.c_float), ("max_merge_dist", C.c_float),
+        ("min_region_growing_candidate_size", C.c_int32), ("min_region_growing_cells_activated", C.c_int32),
+        ("min_region_planarity_score", C.c_float), ("depth_sigma_coeff", C.c_float),
+        ("depth_sigma_margin", C.c_float), ("min_pts_per_cell", C.c_int32),
+        ("depth_discontinuity_threshold", C.c_float), ("max_number_depth_discontinuity", C.c_int32),
+        ("ransac_refinement", C.c_int32), ("ransac_max_iterations", C.c_int32),
+        ("ransac_threshold", C.c_float), ("ransac_inliers_ratio", C.c_float),
+    ]
+
+
+class dpx_info(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("height", "width", "patch_size", "cells_x", "cells_y", "n_cells",
+                                          "plane_capacity", "max_batch", "device", "sm_count")]
+
+
+class dpx_cell(C.Structure):
+    _fields_ = [
+        ("sum", C.c_float * 3), ("var", C.c_float * 6), ("mean", C.c_float * 3), ("normal", C.c_float * 3),
+        ("d", C.c_float), ("mse", C.c_float), ("score", C.c_float), ("merge_tolerance", C.c_float),
+        ("bin", C.c_int32), ("valid", C.c_int32), ("planar", C.c_int32), ("seg_label", C.c_int32),
+        ("final_label", C.c_int32),
+    ]
+
+
+class dpx_plane(C.Structure):
+    _fields_ = [
+        ("normal", C.c_float * 3), ("d", C.c_float), ("mean", C.c_float * 3), ("mse", C.c_float),
+        ("score", C.c_float), ("n_points", C.c_int32), ("merge_label", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library.  There is no fallback: a missing library is an error."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C deplex_b200/csrc`).  deplex_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    sig = {
+        "dpx_config_default": (None, [C.POINTER(dpx_config)]),
+        "dpx_config_load_ini": (C.c_int, [C.c_char_p, C.POINTER(dpx_config)]),
+        "dpx_create": (C.c_int, [i32, i32, C.POINTER(dpx_config), i32, i32, C.POINTER(vp)]),
+        "dpx_destroy": (None, [vp]),
+        "dpx_last_error": (C.c_char_p, [vp]),
+        "dpx_get_info": (C.c_int, [vp, C.POINTER(dpx_info)]),
+        "dpx_process_host": (C.c_int, [vp, vp, i64, C.c_int, vp]),
+        "dpx_process_batch_host": (C.c_int, [vp, vp, i32, C.c_int, vp]),
+        "dpx_process_batch_device": (C.c_int, [vp, vp, i32, C.c_int, vp, vp]),
+        "dpx_get_cells": (C.c_int, [vp, i32, C.POINTER(dpx_cell), i32]),
+        "dpx_get_planes": (C.c_int, [vp, i32, C.POINTER(dpx_plane), i32, C.POINTER(i32)]),
+        "dpx_set_profiling": (C.c_int, [vp, i32]),
+        "dpx_get_stage_ms": (C.c_int, [vp, C.POINTER(C.c_float * N_STAGES)]),
+        "dpx_kernel_launches": (i64, [vp]),
+        "dpx_host_alloc": (C.c_int, [C.POINTER(vp), C.c_size_t]),
+        "dpx_host_free": (None, [vp]),
+        "dpx_version": (i32, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

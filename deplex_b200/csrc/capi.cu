@@ -1,0 +1,485 @@
+// capi.cu -- the C-ABI of libdeplex_b200.so (include/deplex_b200.h): handle management, device scratch,
+// stream plumbing and the three-stage launch sequence.  No arithmetic on labels happens here.
+//
+// Reference behaviour mirrored (file:line under the reference tree):
+//   constructor geometry, patch clamp, patchSize==0 error      plane_extractor.cpp:153-176
+//   size check and its message                                  plane_extractor.cpp:188-194
+//   stage order cell grid -> histogram -> growing -> merging -> labels   plane_extractor.cpp:195-283
+#include "deplex_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cell_stats.cuh"
+#include "error_state.h"
+#include "labeling.cuh"
+#include "region_grow.cuh"
+
+namespace dpx {
+namespace {
+thread_local std::string g_thread_error;
+}
+void set_thread_error(const std::string& msg) { g_thread_error = msg; }
+const char* thread_error() { return g_thread_error.c_str(); }
+}  // namespace dpx
+
+using namespace dpx;
+
+struct dpx_extractor {
+  dpx_config cfg;
+  Geometry geom;
+  Thresholds thr;
+  Tables tb;
+  int device = 0, max_batch = 0, sm_count = 0;
+  int tile_cells = 0;
+  bool bins_in_smem = false;
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  // host-pointer path: double-buffered staging + three streams
+  int host_chunk = 0;
+  float* d_xyz[2] = {nullptr, nullptr};
+  int32_t* d_lab[2] = {nullptr, nullptr};
+  cudaStream_t s_h2d = nullptr, s_run = nullptr, s_d2h = nullptr;
+  cudaEvent_t e_h2d[2] = {nullptr, nullptr}, e_run[2] = {nullptr, nullptr}, e_d2h[2] = {nullptr, nullptr};
+  // measurement
+  bool profiling = false;
+  cudaEvent_t e_stage[DPX_N_STAGES + 1] = {};
+  bool stage_valid = false;
+  int64_t launches = 0;
+  int last_frames = 0;
+  std::string err;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+dpx_status fail(dpx_extractor* ex, dpx_status st, const std::string& msg) {
+  if (ex) ex->err = msg;
+  else set_thread_error(msg);
+  return st;
+}
+
+dpx_status cuda_fail(dpx_extractor* ex, cudaError_t e, const char* what) {
+  return fail(ex, DPX_ERR_CUDA, std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
+}
+
+#define DPX_CUDA(ex, call)                                        \
+  do {                                                            \
+    cudaError_t e__ = (call);                                     \
+    if (e__ != cudaSuccess) return cuda_fail((ex), e__, #call);   \
+  } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Carve the frame-major tables out of one allocation.
+size_t carve_tables(const Geometry& g, int max_batch, bool bins_in_smem, char* base, Tables* tb) {
+  size_t off = 0;
+  const size_t F = static_cast<size_t>(max_batch), C = static_cast<size_t>(g.n_cells), P = static_cast<size_t>(g.plane_cap);
+  auto take = [&](size_t bytes) {
+    char* p = base ? base + off : nullptr;
+    off = align_up(off + bytes, 256);
+    return p;
+  };
+  tb->rec_a = reinterpret_cast<float4*>(take(F * C * 2 * sizeof(float4)));
+  tb->rec_b = reinterpret_cast<float4*>(take(F * C * 3 * sizeof(float4)));
+  tb->bin = reinterpret_cast<int16_t*>(take(F * C * sizeof(int16_t)));
+  tb->flags = reinterpret_cast<uint8_t*>(take(F * C));
+  tb->seg_label = reinterpret_cast<int32_t*>(take(F * C * sizeof(int32_t)));
+  tb->cell_label = reinterpret_cast<int32_t*>(take(F * C * sizeof(int32_t)));
+  tb->queue = reinterpret_cast<int32_t*>(take(F * C * sizeof(int32_t)));
+  tb->pairs = reinterpret_cast<uint32_t*>(take(F * C * 2 * sizeof(uint32_t)));
+  tb->bin_work = reinterpret_cast<int16_t*>(take(bins_in_smem ? 0 : F * C * sizeof(int16_t)));
+  tb->segs = reinterpret_cast<float*>(take(F * P * kSegFloats * sizeof(float)));
+  tb->merge = reinterpret_cast<int32_t*>(take(F * P * sizeof(int32_t)));
+  tb->n_planes = reinterpret_cast<int32_t*>(take(F * sizeof(int32_t)));
+  return off;
+}
+
+// The three stages on one stream (plane_extractor.cpp:195-283).
+dpx_status run_stages(dpx_extractor* ex, const float* d_xyz, int n_frames, int layout, int32_t* d_labels, cudaStream_t st) {
+  const bool prof = ex->profiling;
+  if (prof) DPX_CUDA(ex, cudaEventRecord(ex->e_stage[0], st));
+  if (ex->geom.n_cells > 0) {
+    CellStatsArgs ca{};
+    ca.xyz = d_xyz;
+    ca.n_frames = n_frames;
+    ca.layout = layout;
+    ca.tile_cells = ex->tile_cells;
+    ca.vec_ok = (reinterpret_cast<uintptr_t>(d_xyz) % 16 == 0) && (ex->geom.n_points % 4 == 0) && (ex->geom.width % 4 == 0);
+    ca.geom = ex->geom;
+    ca.thr = ex->thr;
+    ca.tables = ex->tb;
+    DPX_CUDA(ex, launch_cell_stats(ca, st));
+    ++ex->launches;
+  }
+  if (prof) DPX_CUDA(ex, cudaEventRecord(ex->e_stage[1], st));
+  if (ex->geom.n_cells > 0) {
+    RegionArgs ra{};
+    ra.n_frames = n_frames;
+    ra.bins_in_smem = ex->bins_in_smem;
+    ra.geom = ex->geom;
+    ra.thr = ex->thr;
+    ra.tables = ex->tb;
+    DPX_CUDA(ex, launch_region_grow(ra, st));
+    ++ex->launches;
+  }
+  if (prof) DPX_CUDA(ex, cudaEventRecord(ex->e_stage[2], st));
+  {
+    LabelArgs la{};
+    la.n_frames = n_frames;
+    la.geom = ex->geom;
+    la.cell_label = ex->tb.cell_label;
+    la.labels = d_labels;
+    DPX_CUDA(ex, launch_labeling(la, st));
+    if (ex->geom.n_cells > 0) ++ex->launches;
+  }
+  if (prof) {
+    DPX_CUDA(ex, cudaEventRecord(ex->e_stage[3], st));
+    DPX_CUDA(ex, cudaEventRecord(ex->e_stage[4], st));  // refinement stage placeholder (not enabled)
+    ex->stage_valid = true;
+  }
+  ex->last_frames = n_frames;
+  return DPX_OK;
+}
+
+dpx_status ensure_host_path(dpx_extractor* ex) {
+  if (ex->s_run) return DPX_OK;
+  ex->host_chunk = std::max(1, std::min(ex->max_batch, 32));
+  const size_t np = static_cast<size_t>(ex->geom.n_points);
+  for (int i = 0; i < 2; ++i) {
+    DPX_CUDA(ex, cudaMalloc(&ex->d_xyz[i], std::max<size_t>(16, np * 3 * sizeof(float) * ex->host_chunk)));
+    DPX_CUDA(ex, cudaMalloc(&ex->d_lab[i], std::max<size_t>(16, np * sizeof(int32_t) * ex->host_chunk)));
+    DPX_CUDA(ex, cudaEventCreateWithFlags(&ex->e_h2d[i], cudaEventDisableTiming));
+    DPX_CUDA(ex, cudaEventCreateWithFlags(&ex->e_run[i], cudaEventDisableTiming));
+    DPX_CUDA(ex, cudaEventCreateWithFlags(&ex->e_d2h[i], cudaEventDisableTiming));
+  }
+  DPX_CUDA(ex, cudaStreamCreateWithFlags(&ex->s_h2d, cudaStreamNonBlocking));
+  DPX_CUDA(ex, cudaStreamCreateWithFlags(&ex->s_d2h, cudaStreamNonBlocking));
+  DPX_CUDA(ex, cudaStreamCreateWithFlags(&ex->s_run, cudaStreamNonBlocking));
+  return DPX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t dpx_version(void) { return DPX_VERSION; }
+
+const char* dpx_last_error(const dpx_extractor* ex) { return ex ? ex->err.c_str() : thread_error(); }
+
+dpx_status dpx_create(int32_t height, int32_t width, const dpx_config* cfg_in, int32_t device, int32_t max_batch,
+                      dpx_extractor** out) {
+  if (!out) return fail(nullptr, DPX_ERR_ARGUMENT, "dpx_create: out is NULL");
+  *out = nullptr;
+  dpx_config cfg;
+  if (cfg_in) cfg = *cfg_in;
+  else dpx_config_default(&cfg);
+
+  // plane_extractor.cpp:155-164 -- cell counts come from the UNclamped patch size, then the clamp, then the check
+  if (cfg.patch_size == 0)
+    return fail(nullptr, DPX_ERR_RUNTIME,
+                "Error! Invalid config parameter: patchSize(" + std::to_string(cfg.patch_size) +
+                    "). patchSize has to be positive.");
+  if (cfg.patch_size < 0) return fail(nullptr, DPX_ERR_UNSUPPORTED, "negative patchSize is undefined behaviour in the reference");
+  if (height < 0 || width < 0) return fail(nullptr, DPX_ERR_UNSUPPORTED, "negative image size");
+  if (max_batch < 1) return fail(nullptr, DPX_ERR_ARGUMENT, "dpx_create: max_batch must be >= 1");
+
+  Geometry g{};
+  g.height = height;
+  g.width = width;
+  g.nh = width / std::max(cfg.patch_size, 1);
+  g.nv = height / std::max(cfg.patch_size, 1);
+  g.patch = std::min(cfg.patch_size, std::min(height, width));
+  g.n_cells = g.nh * g.nv;
+  g.n_points = static_cast<long long>(height) * width;
+
+  Thresholds th{};
+  if (g.n_cells > 0) {
+    const int p = g.patch;
+    if (p < 4 || p > 26)
+      return fail(nullptr, DPX_ERR_UNSUPPORTED,
+                  "patchSize " + std::to_string(p) + " is outside the supported range [4, 26] (Eigen's product kernels switch "
+                  "summation order outside it; see DESIGN.md)");
+    if (width % p != 0 || height % p != 0)
+      return fail(nullptr, DPX_ERR_UNSUPPORTED,
+                  "image size " + std::to_string(height) + " x " + std::to_string(width) + " is not divisible by patchSize " +
+                      std::to_string(p) + " (out-of-bounds reads in the reference, cell_grid.cpp:71)");
+    if (cfg.min_pts_per_cell == 0)
+      return fail(nullptr, DPX_ERR_UNSUPPORTED, "minPtsPerCell == 0 divides by zero in the reference (cell_segment.cpp:23)");
+    if (cfg.histogram_bins_per_coord < 1 || cfg.histogram_bins_per_coord > 181)
+      return fail(nullptr, DPX_ERR_UNSUPPORTED, "histogramBinsPerCoord must be in [1, 181]");
+    const long long mca = cfg.min_region_growing_cells_activated;
+    g.plane_cap = static_cast<int>(mca >= 1 ? g.n_cells / mca : g.n_cells) + 1;
+    if (g.plane_cap > 65535) return fail(nullptr, DPX_ERR_UNSUPPORTED, "more than 65535 possible plane segments per frame");
+    // size_t valid_pts_threshold = cell_points.size() / config.min_pts_per_cell  (signed division, then cast)
+    th.valid_pts_threshold = static_cast<unsigned long long>(static_cast<long long>(3LL * p * p) / static_cast<long long>(cfg.min_pts_per_cell));
+  } else {
+    g.plane_cap = 1;
+  }
+  th.min_cos_angle_merge = cfg.min_cos_angle_merge;
+  th.max_merge_dist = cfg.max_merge_dist;
+  th.min_region_planarity_score = cfg.min_region_planarity_score;
+  th.depth_sigma_coeff = cfg.depth_sigma_coeff;
+  th.depth_sigma_margin = cfg.depth_sigma_margin;
+  th.depth_discontinuity_threshold = cfg.depth_discontinuity_threshold;
+  th.max_number_depth_discontinuity = cfg.max_number_depth_discontinuity;
+  th.histogram_bins_per_coord = cfg.histogram_bins_per_coord;
+  th.min_candidate_size = static_cast<unsigned long long>(static_cast<long long>(cfg.min_region_growing_candidate_size));
+  th.min_cells_activated = static_cast<unsigned long long>(static_cast<long long>(cfg.min_region_growing_cells_activated));
+
+  if (device < 0) {
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDevice (no usable CUDA device: this library has no CPU path)");
+  }
+  int n_dev = 0;
+  {
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+      return fail(nullptr, DPX_ERR_CUDA,
+                  std::string("no usable CUDA device (this library has no CPU path): ") + cudaGetErrorString(e));
+    if (device >= n_dev) return fail(nullptr, DPX_ERR_ARGUMENT, "dpx_create: device index out of range");
+  }
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(nullptr, DPX_ERR_CUDA, "cudaSetDevice failed");
+
+  dpx_extractor* ex = new dpx_extractor();
+  ex->cfg = cfg;
+  ex->geom = g;
+  ex->thr = th;
+  ex->device = device;
+  ex->max_batch = max_batch;
+  cudaDeviceProp prop;
+  {
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { delete ex; return cuda_fail(nullptr, e, "cudaGetDeviceProperties"); }
+  }
+  ex->sm_count = prop.multiProcessorCount;
+  if (g.n_cells > 0) {
+    ex->tile_cells = cell_stats_tile_cells(g.patch, g.nh);
+    ex->bins_in_smem = region_grow_smem_bytes(g, th, true) <= 64 * 1024;
+    Tables probe{};
+    ex->scratch_bytes = carve_tables(g, max_batch, ex->bins_in_smem, nullptr, &probe);
+    cudaError_t e = cudaMalloc(&ex->scratch, ex->scratch_bytes);
+    if (e != cudaSuccess) { delete ex; return cuda_fail(nullptr, e, "cudaMalloc(scratch tables)"); }
+    carve_tables(g, max_batch, ex->bins_in_smem, static_cast<char*>(ex->scratch), &ex->tb);
+  }
+  for (int i = 0; i <= DPX_N_STAGES; ++i) {
+    cudaError_t e = cudaEventCreate(&ex->e_stage[i]);
+    if (e != cudaSuccess) { dpx_destroy(ex); return cuda_fail(nullptr, e, "cudaEventCreate"); }
+  }
+  *out = ex;
+  return DPX_OK;
+}
+
+void dpx_destroy(dpx_extractor* ex) {
+  if (!ex) return;
+  DeviceGuard guard(ex->device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < 2; ++i) {
+    if (ex->d_xyz[i]) cudaFree(ex->d_xyz[i]);
+    if (ex->d_lab[i]) cudaFree(ex->d_lab[i]);
+    if (ex->e_h2d[i]) cudaEventDestroy(ex->e_h2d[i]);
+    if (ex->e_run[i]) cudaEventDestroy(ex->e_run[i]);
+    if (ex->e_d2h[i]) cudaEventDestroy(ex->e_d2h[i]);
+  }
+  if (ex->s_h2d) cudaStreamDestroy(ex->s_h2d);
+  if (ex->s_d2h) cudaStreamDestroy(ex->s_d2h);
+  if (ex->s_run) cudaStreamDestroy(ex->s_run);
+  for (int i = 0; i <= DPX_N_STAGES; ++i)
+    if (ex->e_stage[i]) cudaEventDestroy(ex->e_stage[i]);
+  if (ex->scratch) cudaFree(ex->scratch);
+  delete ex;
+}
+
+dpx_status dpx_get_info(const dpx_extractor* ex, dpx_info* info) {
+  if (!ex || !info) return DPX_ERR_ARGUMENT;
+  info->height = ex->geom.height;
+  info->width = ex->geom.width;
+  info->patch_size = ex->geom.patch;
+  info->cells_x = ex->geom.nh;
+  info->cells_y = ex->geom.nv;
+  info->n_cells = ex->geom.n_cells;
+  info->plane_capacity = ex->geom.plane_cap;
+  info->max_batch = ex->max_batch;
+  info->device = ex->device;
+  info->sm_count = ex->sm_count;
+  return DPX_OK;
+}
+
+dpx_status dpx_process_batch_device(dpx_extractor* ex, const float* d_xyz, int32_t n_frames, dpx_layout layout,
+                                    int32_t* d_labels, void* cuda_stream) {
+  if (!ex) return DPX_ERR_ARGUMENT;
+  if (n_frames < 0 || n_frames > ex->max_batch)
+    return fail(ex, DPX_ERR_ARGUMENT, "n_frames " + std::to_string(n_frames) + " exceeds max_batch " + std::to_string(ex->max_batch));
+  if (layout != DPX_LAYOUT_COLMAJOR && layout != DPX_LAYOUT_ROWMAJOR) return fail(ex, DPX_ERR_ARGUMENT, "unknown layout");
+  if (n_frames == 0 || ex->geom.n_points == 0) return DPX_OK;
+  if (!d_xyz || !d_labels) return fail(ex, DPX_ERR_ARGUMENT, "null device pointer");
+  DeviceGuard guard(ex->device);
+  if (!guard.ok) return fail(ex, DPX_ERR_CUDA, "cudaSetDevice failed");
+  return run_stages(ex, d_xyz, n_frames, layout, d_labels, static_cast<cudaStream_t>(cuda_stream));
+}
+
+dpx_status dpx_process_batch_host(dpx_extractor* ex, const float* xyz, int32_t n_frames, dpx_layout layout, int32_t* labels) {
+  if (!ex) return DPX_ERR_ARGUMENT;
+  if (n_frames < 0) return fail(ex, DPX_ERR_ARGUMENT, "negative n_frames");
+  if (layout != DPX_LAYOUT_COLMAJOR && layout != DPX_LAYOUT_ROWMAJOR) return fail(ex, DPX_ERR_ARGUMENT, "unknown layout");
+  if (n_frames == 0 || ex->geom.n_points == 0) return DPX_OK;
+  if (!xyz || !labels) return fail(ex, DPX_ERR_ARGUMENT, "null host pointer");
+  DeviceGuard guard(ex->device);
+  if (!guard.ok) return fail(ex, DPX_ERR_CUDA, "cudaSetDevice failed");
+  dpx_status st = ensure_host_path(ex);
+  if (st != DPX_OK) return st;
+
+  const size_t np = static_cast<size_t>(ex->geom.n_points);
+  const int chunk = ex->host_chunk;
+  int n_chunks = 0;
+  for (int f0 = 0; f0 < n_frames; f0 += chunk, ++n_chunks) {
+    const int slot = n_chunks & 1;
+    const int nf = std::min(chunk, n_frames - f0);
+    // H2D into slot: the kernels of the chunk that used this slot two rounds ago must be done reading it
+    if (n_chunks >= 2) DPX_CUDA(ex, cudaStreamWaitEvent(ex->s_h2d, ex->e_run[slot], 0));
+    DPX_CUDA(ex, cudaMemcpyAsync(ex->d_xyz[slot], xyz + static_cast<size_t>(f0) * np * 3, np * 3 * sizeof(float) * nf,
+                                 cudaMemcpyHostToDevice, ex->s_h2d));
+    DPX_CUDA(ex, cudaEventRecord(ex->e_h2d[slot], ex->s_h2d));
+    // kernels: need the input, and the label slot must have been drained
+    DPX_CUDA(ex, cudaStreamWaitEvent(ex->s_run, ex->e_h2d[slot], 0));
+    if (n_chunks >= 2) DPX_CUDA(ex, cudaStreamWaitEvent(ex->s_run, ex->e_d2h[slot], 0));
+    st = run_stages(ex, ex->d_xyz[slot], nf, layout, ex->d_lab[slot], ex->s_run);
+    if (st != DPX_OK) return st;
+    DPX_CUDA(ex, cudaEventRecord(ex->e_run[slot], ex->s_run));
+    // D2H
+    DPX_CUDA(ex, cudaStreamWaitEvent(ex->s_d2h, ex->e_run[slot], 0));
+    DPX_CUDA(ex, cudaMemcpyAsync(labels + static_cast<size_t>(f0) * np, ex->d_lab[slot], np * sizeof(int32_t) * nf,
+                                 cudaMemcpyDeviceToHost, ex->s_d2h));
+    DPX_CUDA(ex, cudaEventRecord(ex->e_d2h[slot], ex->s_d2h));
+  }
+  DPX_CUDA(ex, cudaStreamSynchronize(ex->s_d2h));
+  DPX_CUDA(ex, cudaStreamSynchronize(ex->s_run));
+  DPX_CUDA(ex, cudaStreamSynchronize(ex->s_h2d));
+  return DPX_OK;
+}
+
+dpx_status dpx_process_host(dpx_extractor* ex, const float* xyz, int64_t n_points, dpx_layout layout, int32_t* labels) {
+  if (!ex) return DPX_ERR_ARGUMENT;
+  // plane_extractor.cpp:188-194
+  if (n_points != ex->geom.n_points)
+    return fail(ex, DPX_ERR_RUNTIME,
+                "Error! Number of points doesn't match image shape: " + std::to_string(n_points) + " != " +
+                    std::to_string(ex->geom.height) + " x " + std::to_string(ex->geom.width));
+  return dpx_process_batch_host(ex, xyz, 1, layout, labels);
+}
+
+dpx_status dpx_get_cells(dpx_extractor* ex, int32_t frame, dpx_cell* out, int32_t capacity) {
+  if (!ex || !out) return DPX_ERR_ARGUMENT;
+  const int C = ex->geom.n_cells;
+  if (frame < 0 || frame >= ex->last_frames) return fail(ex, DPX_ERR_ARGUMENT, "frame index outside the last batch");
+  if (capacity < C) return fail(ex, DPX_ERR_ARGUMENT, "dpx_get_cells: capacity < n_cells");
+  if (C == 0) return DPX_OK;
+  DeviceGuard guard(ex->device);
+  DPX_CUDA(ex, cudaDeviceSynchronize());
+  std::vector<float4> ra(2 * static_cast<size_t>(C)), rb(3 * static_cast<size_t>(C));
+  std::vector<int16_t> bin(C);
+  std::vector<uint8_t> flags(C);
+  std::vector<int32_t> seg(C), lab(C);
+  const size_t f = static_cast<size_t>(frame);
+  DPX_CUDA(ex, cudaMemcpy(ra.data(), ex->tb.rec_a + f * C * 2, ra.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+  DPX_CUDA(ex, cudaMemcpy(rb.data(), ex->tb.rec_b + f * C * 3, rb.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+  DPX_CUDA(ex, cudaMemcpy(bin.data(), ex->tb.bin + f * C, C * sizeof(int16_t), cudaMemcpyDeviceToHost));
+  DPX_CUDA(ex, cudaMemcpy(flags.data(), ex->tb.flags + f * C, C, cudaMemcpyDeviceToHost));
+  DPX_CUDA(ex, cudaMemcpy(seg.data(), ex->tb.seg_label + f * C, C * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  DPX_CUDA(ex, cudaMemcpy(lab.data(), ex->tb.cell_label + f * C, C * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  for (int c = 0; c < C; ++c) {
+    dpx_cell& o = out[c];
+    std::memset(&o, 0, sizeof(o));
+    o.valid = (flags[c] & kFlagValid) != 0;
+    o.planar = (flags[c] & kFlagPlanar) != 0;
+    o.bin = bin[c];
+    o.seg_label = seg[c];
+    o.final_label = lab[c];
+    if (!o.valid) continue;
+    const float4 a0 = ra[2 * c], a1 = ra[2 * c + 1], b0 = rb[3 * c], b1 = rb[3 * c + 1], b2 = rb[3 * c + 2];
+    o.normal[0] = a0.x; o.normal[1] = a0.y; o.normal[2] = a0.z; o.d = a0.w;
+    o.mean[0] = a1.x; o.mean[1] = a1.y; o.mean[2] = a1.z; o.merge_tolerance = a1.w;
+    o.sum[0] = b0.x; o.sum[1] = b0.y; o.sum[2] = b0.z;
+    o.var[0] = b0.w; o.var[1] = b1.x; o.var[2] = b1.y; o.var[3] = b1.z; o.var[4] = b1.w; o.var[5] = b2.x;
+    o.mse = b2.y; o.score = b2.z;
+  }
+  return DPX_OK;
+}
+
+dpx_status dpx_get_planes(dpx_extractor* ex, int32_t frame, dpx_plane* out, int32_t capacity, int32_t* n_planes) {
+  if (!ex || !n_planes) return DPX_ERR_ARGUMENT;
+  *n_planes = 0;
+  if (frame < 0 || frame >= ex->last_frames) return fail(ex, DPX_ERR_ARGUMENT, "frame index outside the last batch");
+  if (ex->geom.n_cells == 0) return DPX_OK;
+  DeviceGuard guard(ex->device);
+  DPX_CUDA(ex, cudaDeviceSynchronize());
+  int32_t P = 0;
+  DPX_CUDA(ex, cudaMemcpy(&P, ex->tb.n_planes + frame, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  *n_planes = P;
+  if (!out || P == 0) return DPX_OK;
+  const int n = std::min(P, capacity);
+  std::vector<float> segs(static_cast<size_t>(n) * kSegFloats);
+  std::vector<int32_t> merge(n);
+  const size_t f = static_cast<size_t>(frame);
+  DPX_CUDA(ex, cudaMemcpy(segs.data(), ex->tb.segs + f * ex->geom.plane_cap * kSegFloats, segs.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  DPX_CUDA(ex, cudaMemcpy(merge.data(), ex->tb.merge + f * ex->geom.plane_cap, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; ++i) {
+    const float* r = &segs[static_cast<size_t>(i) * kSegFloats];
+    dpx_plane& o = out[i];
+    std::memcpy(o.normal, r + kSegNormal, 12);
+    std::memcpy(o.mean, r + kSegMean, 12);
+    o.d = r[kSegD];
+    o.mse = r[kSegMse];
+    o.score = r[kSegScore];
+    std::memcpy(&o.n_points, r + kSegN, 4);
+    o.merge_label = merge[i];
+  }
+  return DPX_OK;
+}
+
+dpx_status dpx_set_profiling(dpx_extractor* ex, int32_t enabled) {
+  if (!ex) return DPX_ERR_ARGUMENT;
+  ex->profiling = enabled != 0;
+  ex->stage_valid = false;
+  return DPX_OK;
+}
+
+dpx_status dpx_get_stage_ms(dpx_extractor* ex, float ms[DPX_N_STAGES]) {
+  if (!ex || !ms) return DPX_ERR_ARGUMENT;
+  if (!ex->stage_valid) return fail(ex, DPX_ERR_ARGUMENT, "no profiled batch: call dpx_set_profiling(ex, 1) first");
+  DeviceGuard guard(ex->device);
+  DPX_CUDA(ex, cudaEventSynchronize(ex->e_stage[DPX_N_STAGES]));
+  for (int i = 0; i < DPX_N_STAGES; ++i) DPX_CUDA(ex, cudaEventElapsedTime(&ms[i], ex->e_stage[i], ex->e_stage[i + 1]));
+  return DPX_OK;
+}
+
+int64_t dpx_kernel_launches(const dpx_extractor* ex) { return ex ? ex->launches : 0; }
+
+dpx_status dpx_host_alloc(void** ptr, size_t bytes) {
+  if (!ptr) return DPX_ERR_ARGUMENT;
+  cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaHostAlloc");
+  return DPX_OK;
+}
+
+void dpx_host_free(void* ptr) {
+  if (ptr) cudaFreeHost(ptr);
+}
+
+}  // extern "C"

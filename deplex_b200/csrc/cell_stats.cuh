@@ -1,0 +1,24 @@
+// cell_stats.cuh -- launcher interface of stage 1 (cell statistics).
+#pragma once
+#include "common.cuh"
+
+namespace dpx {
+
+constexpr int kCellStatsThreads = 128;
+
+struct CellStatsArgs {
+  const float* xyz;  // device, n_frames organized clouds
+  int n_frames;
+  int layout;
+  int tile_cells;       // cells staged per CTA (from cell_stats_tile_cells)
+  int tiles_per_strip;  // filled by the launcher
+  int vec_ok;           // base pointer and plane strides allow 16-byte loads
+  Geometry geom;
+  Thresholds thr;
+  Tables tables;
+};
+
+int cell_stats_tile_cells(int patch, int nh);
+cudaError_t launch_cell_stats(const CellStatsArgs& args, cudaStream_t stream);
+
+}  // namespace dpx

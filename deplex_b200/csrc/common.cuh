@@ -1,0 +1,62 @@
+// common.cuh -- device-side data layout shared by the three stages of the hot path.
+//
+// HBM layout (all arrays are frame-major, sized for max_batch frames at dpx_create):
+//   rec_a   float4[F][C][2]  {nx,ny,nz,d} {mean_x,mean_y,mean_z,merge_tolerance}   32 B/cell  (read by the BFS)
+//   rec_b   float4[F][C][3]  {Sx,Sy,Sz,Vxx} {Vxy,Vxz,Vyy,Vyz} {Vzz,mse,score,0}    48 B/cell  (read by the accumulation)
+//   bin     int16 [F][C]     initial NormalsHistogram bin, -1 when the cell is not planar
+//   flags   uint8 [F][C]     bit0 = valid (stats exist), bit1 = planar
+//   seg_label / cell_label int32[F][C], queue int32[F][C], pairs uint32[F][2C], segs float[F][Pcap][24],
+//   merge int32[F][Pcap], n_planes int32[F]
+// rec_a / rec_b are only written for valid cells; nothing reads them for the others.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace dpx {
+
+constexpr int kLayoutColMajor = 0;
+constexpr int kLayoutRowMajor = 1;
+
+constexpr uint8_t kFlagValid = 1;
+constexpr uint8_t kFlagPlanar = 2;
+
+constexpr int kSegFloats = 24;  // n(int) S3 V6 mean3 normal3 d mse score + pad
+// offsets inside one segment record
+constexpr int kSegN = 0, kSegS = 1, kSegV = 4, kSegMean = 10, kSegNormal = 13, kSegD = 16, kSegMse = 17, kSegScore = 18;
+
+struct Geometry {
+  int height, width;
+  int patch;        // clamped patch size
+  int nh, nv;       // cells per row / column
+  int n_cells;
+  int plane_cap;
+  long long n_points;
+};
+
+struct Thresholds {
+  // config values exactly as the reference holds them (fp32 / int32)
+  float min_cos_angle_merge, max_merge_dist, min_region_planarity_score;
+  float depth_sigma_coeff, depth_sigma_margin, depth_discontinuity_threshold;
+  int max_number_depth_discontinuity;
+  int histogram_bins_per_coord;
+  unsigned long long valid_pts_threshold;       // size_t(cell_points.size() / minPtsPerCell)
+  unsigned long long min_candidate_size;        // size_t(int32) conversions of the reference's comparisons
+  unsigned long long min_cells_activated;
+};
+
+struct Tables {
+  float4* rec_a;
+  float4* rec_b;
+  int16_t* bin;
+  uint8_t* flags;
+  int32_t* seg_label;
+  int32_t* cell_label;
+  int32_t* queue;
+  uint32_t* pairs;     // [F][2C] packed (min<<16 | max) adjacent plane pairs
+  int16_t* bin_work;   // used by region growing when the bins do not fit in shared memory
+  float* segs;
+  int32_t* merge;
+  int32_t* n_planes;
+};
+
+}  // namespace dpx

@@ -1,0 +1,206 @@
+"""Host-side mirror of the reference's Python interface, over the C-ABI.
+
+Reference surface (cpp/pybind/plane_extraction/plane_extraction.cpp:28-37, python/deplex/__init__.py:1-2):
+    deplex.Config(path)
+    deplex.PlaneExtractor(image_height, image_width, config=Config()).process(pcd_array) -> int32 (N,)
+std::runtime_error surfaces as RuntimeError, with the reference's texts.  Additions beyond the reference:
+keyword construction of Config, batched / device-resident processing, and the per-cell / per-plane tables.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR
+
+
+class UnsupportedError(RuntimeError):
+    """Input that is undefined behaviour in the reference or outside the parity domain (DPX_ERR_UNSUPPORTED)."""
+
+
+class CudaError(RuntimeError):
+    """CUDA failure, including 'no device': there is no CPU path."""
+
+
+def _raise(status, msg):
+    msg = msg.decode() if isinstance(msg, bytes) else msg
+    if status == _capi.DPX_ERR_RUNTIME:
+        raise RuntimeError(msg)
+    if status == _capi.DPX_ERR_UNSUPPORTED:
+        raise UnsupportedError(msg)
+    if status == _capi.DPX_ERR_CUDA:
+        raise CudaError(msg)
+    raise ValueError(msg or f"dpx status {status}")
+
+
+class Config:
+    """deplex.Config: parameters of the plane extraction algorithm (config.h:29-82).
+
+    Config(path) reads an .ini exactly like the reference; Config() holds the defaults; keyword arguments
+    (e.g. Config(patch_size=4)) override single fields."""
+
+    def __init__(self, path=None, **fields):
+        lib = _capi.load()
+        self._c = _capi.dpx_config()
+        if path is None:
+            lib.dpx_config_default(C.byref(self._c))
+        else:
+            st = lib.dpx_config_load_ini(str(path).encode(), C.byref(self._c))
+            if st != _capi.DPX_OK:
+                _raise(st, lib.dpx_last_error(None))
+        for k, v in fields.items():
+            setattr(self, k, v)
+
+    def copy(self):
+        c = Config()
+        C.memmove(C.byref(c._c), C.byref(self._c), C.sizeof(self._c))
+        return c
+
+    def as_dict(self):
+        return {n: getattr(self._c, n) for n, _ in self._c._fields_}
+
+    def __repr__(self):
+        return "Config(" + ", ".join(f"{k}={v!r}" for k, v in self.as_dict().items()) + ")"
+
+
+def _cfg_property(name):
+    def get(self):
+        return getattr(self._c, name)
+
+    def set_(self, v):
+        setattr(self._c, name, v)
+
+    return property(get, set_)
+
+
+for _n, _ in _capi.dpx_config._fields_:
+    setattr(Config, _n, _cfg_property(_n))
+
+
+def _host_layout(a):
+    if a.ndim == 2 and a.shape[1] == 3 and a.flags.c_contiguous:
+        return LAYOUT_ROWMAJOR
+    if a.ndim == 2 and a.shape[1] == 3 and a.flags.f_contiguous:
+        return LAYOUT_COLMAJOR
+    return None
+
+
+class PlaneExtractor:
+    """deplex.PlaneExtractor (plane_extractor.h:28-56) running on one B200.
+
+    PlaneExtractor(image_height, image_width, config=Config()).process(pcd_array) is the reference call;
+    `max_batch` / `device` size the device scratch for the batched entry points."""
+
+    def __init__(self, image_height, image_width, config=None, *, max_batch=1, device=-1):
+        lib = _capi.load()
+        self._lib = lib
+        self._h = C.c_void_p()
+        cfg = config if config is not None else Config()
+        st = lib.dpx_create(int(image_height), int(image_width), C.byref(cfg._c), int(device), int(max_batch),
+                            C.byref(self._h))
+        if st != _capi.DPX_OK:
+            self._h = C.c_void_p()
+            _raise(st, lib.dpx_last_error(None))
+        info = _capi.dpx_info()
+        lib.dpx_get_info(self._h, C.byref(info))
+        self.info = info
+        self.height, self.width = int(image_height), int(image_width)
+        self.n_points = self.height * self.width
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.dpx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st != _capi.DPX_OK:
+            _raise(st, self._lib.dpx_last_error(self._h))
+
+    # ---- the reference call -------------------------------------------------------------------------
+    def process(self, pcd_array):
+        """One organized cloud, any numeric (N,3) array (converted to float32 like the pybind Eigen caster).
+        Returns int32 labels of shape (N,): 0 = non-planar, k > 0 = plane id (not compacted)."""
+        a = np.asarray(pcd_array)
+        if a.dtype != np.float32:
+            a = a.astype(np.float32)
+        if a.ndim != 2 or (a.size and a.shape[1] != 3):
+            a = a.reshape(-1, 3) if a.size % 3 == 0 else a
+        n = a.shape[0] if a.ndim == 2 else -1
+        layout = _host_layout(a) if a.size else LAYOUT_ROWMAJOR
+        if layout is None:
+            a = np.ascontiguousarray(a)
+            layout = LAYOUT_ROWMAJOR
+        labels = np.empty(max(n, 0), dtype=np.int32)
+        self._check(self._lib.dpx_process_host(self._h, a.ctypes.data if a.size else None, n, layout,
+                                               labels.ctypes.data if labels.size else None))
+        return labels
+
+    # ---- batched entry points (additions) -----------------------------------------------------------
+    def process_batch_host(self, xyz, layout, labels=None):
+        """xyz: host float32 array holding F frames back to back ((F,N,3) row-major or (F,3,N) column-major).
+        Copies are chunked and overlapped with the kernels.  Returns (F,N) int32."""
+        a = np.ascontiguousarray(xyz, dtype=np.float32)
+        f = a.size // (3 * self.n_points) if self.n_points else 0
+        assert a.size == f * 3 * self.n_points, "batch does not hold a whole number of frames"
+        if labels is None:
+            labels = np.empty((f, self.n_points), dtype=np.int32)
+        self._check(self._lib.dpx_process_batch_host(self._h, a.ctypes.data, f, layout, labels.ctypes.data))
+        return labels
+
+    def process_batch_host_ptr(self, xyz_ptr, n_frames, layout, labels_ptr):
+        """Raw host pointers (e.g. pinned torch tensors' data_ptr())."""
+        self._check(self._lib.dpx_process_batch_host(self._h, xyz_ptr, n_frames, layout, labels_ptr))
+
+    def process_batch_device(self, xyz, layout, labels=None, stream=None):
+        """xyz: CUDA torch.float32 tensor with F frames ((F,N,3) or (F,3,N)); asynchronous on `stream`
+        (default: torch's current stream).  Returns a CUDA int32 tensor (F,N)."""
+        import torch
+        assert xyz.is_cuda and xyz.dtype == torch.float32 and xyz.is_contiguous()
+        f = xyz.numel() // (3 * self.n_points)
+        assert xyz.numel() == f * 3 * self.n_points
+        if labels is None:
+            labels = torch.empty((f, self.n_points), dtype=torch.int32, device=xyz.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(xyz.device)
+        self._check(self._lib.dpx_process_batch_device(self._h, xyz.data_ptr(), f, layout, labels.data_ptr(),
+                                                       stream.cuda_stream))
+        return labels
+
+    # ---- tables the reference computes and discards --------------------------------------------------
+    def cells(self, frame=0):
+        n = self.info.n_cells
+        buf = (_capi.dpx_cell * max(n, 1))()
+        self._check(self._lib.dpx_get_cells(self._h, frame, buf, n))
+        rec = np.frombuffer(buf, dtype=np.dtype([
+            ("sum", "f4", 3), ("var", "f4", 6), ("mean", "f4", 3), ("normal", "f4", 3), ("d", "f4"), ("mse", "f4"),
+            ("score", "f4"), ("merge_tolerance", "f4"), ("bin", "i4"), ("valid", "i4"), ("planar", "i4"),
+            ("seg_label", "i4"), ("final_label", "i4")]))[:n]
+        return rec.copy()
+
+    def planes(self, frame=0):
+        cap = self.info.plane_capacity
+        buf = (_capi.dpx_plane * max(cap, 1))()
+        n = C.c_int32(0)
+        self._check(self._lib.dpx_get_planes(self._h, frame, buf, cap, C.byref(n)))
+        rec = np.frombuffer(buf, dtype=np.dtype([
+            ("normal", "f4", 3), ("d", "f4"), ("mean", "f4", 3), ("mse", "f4"), ("score", "f4"), ("n_points", "i4"),
+            ("merge_label", "i4")]))[:n.value]
+        return rec.copy()
+
+    # ---- measurement ----------------------------------------------------------------------------------
+    def set_profiling(self, enabled):
+        self._check(self._lib.dpx_set_profiling(self._h, 1 if enabled else 0))
+
+    def stage_ms(self):
+        ms = (C.c_float * _capi.N_STAGES)()
+        self._check(self._lib.dpx_get_stage_ms(self._h, C.byref(ms)))
+        return dict(zip(_capi.STAGE_NAMES, [float(x) for x in ms]))
+
+    def kernel_launches(self):
+        return int(self._lib.dpx_kernel_launches(self._h))

@@ -1,0 +1,156 @@
+/*
+ * deplex_b200.h -- C-ABI of libdeplex_b200.so: the B200 (sm_100a) plane-extraction hot path.
+ *
+ * This is the drop-in boundary for prime-slam/deplex's
+ *     deplex::PlaneExtractor(height, width, config).process(organized_pcd) -> labels
+ * (reference: cpp/deplex/include/deplex/plane_extractor.h:28-56, implemented by
+ * cpp/deplex/src/deplex/plane_extractor.cpp:153-283).  Plain pointers and sizes only: no C++,
+ * Eigen, torch or CUDA types cross this boundary.  The C++ class shim
+ * (deplex_b200/cpp/deplex/plane_extractor.h) and the pybind module `deplex.pybind`
+ * (deplex_b200/pybind/) are both written against exactly these entry points.
+ *
+ * There is NO CPU fallback: every process call runs CUDA kernels and fails with DPX_ERR_CUDA
+ * when no usable device is present.
+ */
+#ifndef DEPLEX_B200_H
+#define DEPLEX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPX_VERSION 100
+
+#if defined(__GNUC__)
+#define DPX_API __attribute__((visibility("default")))
+#else
+#define DPX_API
+#endif
+
+typedef enum dpx_status {
+  DPX_OK = 0,
+  DPX_ERR_RUNTIME = 1,     /* the reference throws std::runtime_error here; dpx_last_error() has its exact text */
+  DPX_ERR_UNSUPPORTED = 2, /* input is undefined behaviour in the reference or outside the parity domain */
+  DPX_ERR_CUDA = 3,        /* CUDA runtime / driver failure (including "no device") */
+  DPX_ERR_ARGUMENT = 4     /* NULL handle, batch larger than max_batch, ... */
+} dpx_status;
+
+/* Memory layout of one organized cloud of N = height*width points. */
+typedef enum dpx_layout {
+  DPX_LAYOUT_COLMAJOR = 0, /* X[N] Y[N] Z[N]: Eigen::MatrixX3f (plane_extractor.h:48) */
+  DPX_LAYOUT_ROWMAJOR = 1  /* x0 y0 z0 x1 ...: numpy C-order (N,3); DepthImage::toPointCloud's native order */
+} dpx_layout;
+
+/* Field-for-field mirror of deplex::config::Config (cpp/deplex/include/deplex/config.h:51-81). */
+typedef struct dpx_config {
+  int32_t patch_size;                         /* patchSize */
+  int32_t histogram_bins_per_coord;           /* histogramBinsPerCoord */
+  float min_cos_angle_merge;                  /* minCosAngleForMerge */
+  float max_merge_dist;                       /* maxMergeDist */
+  int32_t min_region_growing_candidate_size;  /* minRegionGrowingCandidateSize */
+  int32_t min_region_growing_cells_activated; /* minRegionGrowingCellsActivated */
+  float min_region_planarity_score;           /* minRegionPlanarityScore */
+  float depth_sigma_coeff;                    /* depthSigmaCoeff */
+  float depth_sigma_margin;                   /* depthSigmaMargin */
+  int32_t min_pts_per_cell;                   /* minPtsPerCell */
+  float depth_discontinuity_threshold;        /* depthDiscontinuityThreshold */
+  int32_t max_number_depth_discontinuity;     /* maxNumberDepthDiscontinuity */
+  int32_t ransac_refinement;                  /* ransacRefinement (bool) */
+  int32_t ransac_max_iterations;              /* ransacMaxIterations */
+  float ransac_threshold;                     /* ransacThreshold */
+  float ransac_inliers_ratio;                 /* ransacInliersRatio */
+} dpx_config;
+
+typedef struct dpx_extractor dpx_extractor; /* opaque: PlaneExtractor::Impl's replacement */
+
+/* Geometry and capacities fixed at creation. */
+typedef struct dpx_info {
+  int32_t height, width;
+  int32_t patch_size;      /* after the reference's clamp min(patch, min(h, w)) (plane_extractor.cpp:160) */
+  int32_t cells_x, cells_y;/* nr_horizontal_cells_, nr_vertical_cells_ (plane_extractor.cpp:155-156) */
+  int32_t n_cells;
+  int32_t plane_capacity;  /* upper bound on plane segments per frame */
+  int32_t max_batch;
+  int32_t device;
+  int32_t sm_count;
+} dpx_info;
+
+/* Per-cell record returned by dpx_get_cells (one per cell of one frame of the last batch). */
+typedef struct dpx_cell {
+  float sum[3];     /* CellSegmentStat::coord_sum_ */
+  float var[6];     /* upper triangle of variance_ (X^T X): xx xy xz yy yz zz */
+  float mean[3];
+  float normal[3];
+  float d, mse, score;
+  float merge_tolerance;
+  int32_t bin;      /* initial NormalsHistogram bin, -1 if the cell is not planar */
+  int32_t valid;    /* passed hasValidPoints && isDepthContinuous (cell_segment.cpp:27-30) */
+  int32_t planar;   /* CellSegment::isPlanar */
+  int32_t seg_label;/* labels_map_ entry after region growing (1-based segment id, 0 = none) */
+  int32_t final_label; /* label painted by toImageLabels for this cell */
+} dpx_cell;
+
+/* Per-plane-segment record returned by dpx_get_planes (post-merge statistics, like the reference's
+ * plane_segments vector at the end of findMergedLabels). */
+typedef struct dpx_plane {
+  float normal[3];
+  float d;
+  float mean[3];
+  float mse, score;
+  int32_t n_points;
+  int32_t merge_label; /* plane_merge_labels[i] (plane_extractor.cpp:398-425) */
+} dpx_plane;
+
+/* Stage indices for dpx_get_stage_ms. */
+enum { DPX_STAGE_CELL_STATS = 0, DPX_STAGE_REGION_GROW = 1, DPX_STAGE_LABELING = 2, DPX_STAGE_REFINE = 3, DPX_N_STAGES = 4 };
+
+/* ---- Config: replaces Config::Config() and Config::Config(std::string const&) (config.cpp:23-80) ---- */
+DPX_API void dpx_config_default(dpx_config* cfg);
+/* Same parsing rules as config.cpp:33-79.  DPX_ERR_RUNTIME + "Couldn't open ini file: <path>" when unreadable. */
+DPX_API dpx_status dpx_config_load_ini(const char* path, dpx_config* cfg);
+
+/* ---- Extractor: replaces PlaneExtractor::PlaneExtractor / ~PlaneExtractor (plane_extractor.cpp:153-183) ---- */
+/* device < 0 selects the current CUDA device.  max_batch >= 1 frames of device scratch are allocated. */
+DPX_API dpx_status dpx_create(int32_t height, int32_t width, const dpx_config* cfg, int32_t device, int32_t max_batch,
+                      dpx_extractor** out);
+DPX_API void dpx_destroy(dpx_extractor* ex);
+/* Message of the last failure on this handle; ex == NULL returns the calling thread's last handle-less failure
+ * (dpx_create, dpx_config_load_ini). */
+DPX_API const char* dpx_last_error(const dpx_extractor* ex);
+DPX_API dpx_status dpx_get_info(const dpx_extractor* ex, dpx_info* info);
+
+/* ---- process: replaces PlaneExtractor::process (plane_extractor.cpp:185-283) ---- */
+/* One frame, host pointers (pageable or pinned).  n_points is pcd_array.rows(); a mismatch with height*width
+ * returns DPX_ERR_RUNTIME with the reference's message (plane_extractor.cpp:188-194).  labels: n_points int32. */
+DPX_API dpx_status dpx_process_host(dpx_extractor* ex, const float* xyz, int64_t n_points, dpx_layout layout, int32_t* labels);
+/* n_frames independent frames, host pointers, frame-major; copies are pipelined with the kernels in chunks. */
+DPX_API dpx_status dpx_process_batch_host(dpx_extractor* ex, const float* xyz, int32_t n_frames, dpx_layout layout,
+                                  int32_t* labels);
+/* n_frames <= max_batch frames already resident in device memory; asynchronous on `cuda_stream` (a cudaStream_t,
+ * NULL = the legacy default stream).  d_labels: n_frames * height * width int32 in device memory. */
+DPX_API dpx_status dpx_process_batch_device(dpx_extractor* ex, const float* d_xyz, int32_t n_frames, dpx_layout layout,
+                                    int32_t* d_labels, void* cuda_stream);
+
+/* ---- introspection of the last batch (the reference computes these and discards them) ---- */
+DPX_API dpx_status dpx_get_cells(dpx_extractor* ex, int32_t frame, dpx_cell* out, int32_t capacity);
+DPX_API dpx_status dpx_get_planes(dpx_extractor* ex, int32_t frame, dpx_plane* out, int32_t capacity, int32_t* n_planes);
+
+/* ---- measurement: CUDA-event time of each stage of the last dpx_process_batch_device call ---- */
+DPX_API dpx_status dpx_set_profiling(dpx_extractor* ex, int32_t enabled);
+DPX_API dpx_status dpx_get_stage_ms(dpx_extractor* ex, float ms[DPX_N_STAGES]);
+/* Number of kernels launched by this handle since creation. */
+DPX_API int64_t dpx_kernel_launches(const dpx_extractor* ex);
+
+/* ---- pinned host memory helpers (cudaHostAlloc / cudaFreeHost) ---- */
+DPX_API dpx_status dpx_host_alloc(void** ptr, size_t bytes);
+DPX_API void dpx_host_free(void* ptr);
+
+DPX_API int32_t dpx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEPLEX_B200_H */
