@@ -70,7 +70,8 @@ def make_host_batch(a, rank):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled while the GPU runs the benchmark's steps
+    (B200_PROFILING.md recipe).  Samples are time-stamped on arrival and selected by window."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -78,12 +79,12 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.samples = []  # (arrival time, line)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -92,9 +93,12 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.samples.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def count(self, t0, t1):
+        return sum(1 for t, _ in self.samples if t0 <= t <= t1)
+
+    def stop(self, t0, t1, window):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -104,7 +108,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for t, ln in self.samples:
+            if not (t0 <= t <= t1):
+                continue
             p = [x.strip() for x in ln.split(",")]
             if len(p) < 9:
                 continue
@@ -117,7 +123,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "window": window}
 
 
 def cpu_baseline(a, host_batch, threads, sample_frames):
@@ -203,21 +209,36 @@ def run_ours(a):
     for _ in range(max(a.warmup, 3)):
         ex.process_batch_device(d_xyz, lay, d_lab, stream)
     torch.cuda.synchronize()
-    ex.set_profiling(True)
     stage_acc = {}
     sampler = ClockSampler(local)
+    sampler.start()
+    for _ in range(3):  # give nvidia-smi time to come up while the GPU is already under this load
+        ex.process_batch_device(d_xyz, lay, d_lab, stream)
+    torch.cuda.synchronize()
     launches0 = ex.kernel_launches()
     barrier()
-    sampler.start()
+    t_start = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(a.steps):
         ex.process_batch_device(d_xyz, lay, d_lab, stream)
     e1.record(stream)
     barrier()
-    clocks = sampler.stop()
+    t_end = time.perf_counter()
     launches = ex.kernel_launches() - launches0
     elapsed_ms = e0.elapsed_time(e1)
+    window = "timed region"
+    if sampler.count(t_start, t_end) < 3:
+        # the timed region is shorter than a few sampler periods: keep the same step running for ~1.5 s
+        # right after it (untimed) and read the clocks under that load
+        t_start = time.perf_counter()
+        while time.perf_counter() - t_start < 1.5:
+            for _ in range(5):
+                ex.process_batch_device(d_xyz, lay, d_lab, stream)
+            torch.cuda.synchronize()
+        t_end = time.perf_counter()
+        window = "1.5 s of the same step run back to back right after the timed region (the timed region is shorter than the sampler period)"
+    clocks = sampler.stop(t_start, t_end, window)
     ex.set_profiling(False)
     # per-stage CUDA-event times (on the launching stream), averaged over a separate short run so the
     # event records do not sit inside the timed region above

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -35,7 +36,9 @@ struct dpx_extractor {
   Tables tb;
   int device = 0, max_batch = 0, sm_count = 0;
   int tile_cells = 0;
-  bool bins_in_smem = false;
+  int stream_warps = 8;       // env DPX_STREAM_WARPS=8|12
+  int force_tile_kernel = 0;  // env DPX_CELL_KERNEL=tile (A/B measurement of the two stage-1 kernels)
+  RegionPlan plan{};
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
   // host-pointer path: double-buffered staging + three streams
@@ -99,6 +102,7 @@ size_t carve_tables(const Geometry& g, int max_batch, bool bins_in_smem, char* b
   tb->rec_b = reinterpret_cast<float4*>(take(F * C * 3 * sizeof(float4)));
   tb->bin = reinterpret_cast<int16_t*>(take(F * C * sizeof(int16_t)));
   tb->flags = reinterpret_cast<uint8_t*>(take(F * C));
+  tb->mse = reinterpret_cast<float*>(take(F * C * sizeof(float)));
   tb->seg_label = reinterpret_cast<int32_t*>(take(F * C * sizeof(int32_t)));
   tb->cell_label = reinterpret_cast<int32_t*>(take(F * C * sizeof(int32_t)));
   tb->queue = reinterpret_cast<int32_t*>(take(F * C * sizeof(int32_t)));
@@ -121,6 +125,9 @@ dpx_status run_stages(dpx_extractor* ex, const float* d_xyz, int n_frames, int l
     ca.layout = layout;
     ca.tile_cells = ex->tile_cells;
     ca.vec_ok = (reinterpret_cast<uintptr_t>(d_xyz) % 16 == 0) && (ex->geom.n_points % 4 == 0) && (ex->geom.width % 4 == 0);
+    ca.sm_count = ex->sm_count;
+    ca.force_tile_kernel = ex->force_tile_kernel;
+    ca.stream_warps = ex->stream_warps;
     ca.geom = ex->geom;
     ca.thr = ex->thr;
     ca.tables = ex->tb;
@@ -131,7 +138,7 @@ dpx_status run_stages(dpx_extractor* ex, const float* d_xyz, int n_frames, int l
   if (ex->geom.n_cells > 0) {
     RegionArgs ra{};
     ra.n_frames = n_frames;
-    ra.bins_in_smem = ex->bins_in_smem;
+    ra.plan = ex->plan;
     ra.geom = ex->geom;
     ra.thr = ex->thr;
     ra.tables = ex->tb;
@@ -271,12 +278,14 @@ dpx_status dpx_create(int32_t height, int32_t width, const dpx_config* cfg_in, i
   ex->sm_count = prop.multiProcessorCount;
   if (g.n_cells > 0) {
     ex->tile_cells = cell_stats_tile_cells(g.patch, g.nh);
-    ex->bins_in_smem = region_grow_smem_bytes(g, th, true) <= 64 * 1024;
+    if (const char* e = std::getenv("DPX_STREAM_WARPS")) ex->stream_warps = std::atoi(e) == 12 ? 12 : 8;
+    if (const char* e = std::getenv("DPX_CELL_KERNEL")) ex->force_tile_kernel = std::strcmp(e, "tile") == 0;
+    ex->plan = region_grow_plan(g, th);
     Tables probe{};
-    ex->scratch_bytes = carve_tables(g, max_batch, ex->bins_in_smem, nullptr, &probe);
+    ex->scratch_bytes = carve_tables(g, max_batch, ex->plan.bins_smem != 0, nullptr, &probe);
     cudaError_t e = cudaMalloc(&ex->scratch, ex->scratch_bytes);
     if (e != cudaSuccess) { delete ex; return cuda_fail(nullptr, e, "cudaMalloc(scratch tables)"); }
-    carve_tables(g, max_batch, ex->bins_in_smem, static_cast<char*>(ex->scratch), &ex->tb);
+    carve_tables(g, max_batch, ex->plan.bins_smem != 0, static_cast<char*>(ex->scratch), &ex->tb);
   }
   for (int i = 0; i <= DPX_N_STAGES; ++i) {
     cudaError_t e = cudaEventCreate(&ex->e_stage[i]);

@@ -3,337 +3,37 @@
 //
 // Replaces, per frame (reference file:line):
 //   CellGrid::CellGrid / cellContinuousOrganize      cell_grid.cpp:21-44,69-83   (no re-tiled copy is made:
-//                                                     a tile of cells is staged in shared memory instead)
+//                                                     rows of a tile of cells are staged in shared memory)
 //   CellSegment::CellSegment and its predicates      cell_segment.cpp:21-35,57-110
 //   CellSegmentStat::CellSegmentStat / fitPlane      cell_segment_stat.cpp:29-35,55-81 (+ libs/dsyev)
 //   NormalsHistogram's per-cell bin                  normals_histogram.cpp:31-45
 //
-// Work decomposition: one CTA stages `tile_cells` horizontally adjacent cells (patch rows x
-// tile_cells*patch columns) in shared memory with coalesced 16-byte loads, then one thread per cell
-// walks its patch*patch points in cell-contiguous order.  The walk is sequential on purpose: the
-// reference's X^T X entries are sequential fp32 chains and its column sums are an 8-lane strided
-// tree (Eigen 3.4), and labels only match if those orders are reproduced exactly.
-// A thread carries 6 + 24 independent accumulators, so the chains overlap in the FMA pipe.
+// Two kernels share the per-cell arithmetic in cell_walk.cuh:
 //
-// Algorithmic bytes: 12 B/pixel read once; <= 83 B/cell written.
+//  * cell_stats_stream_kernel (the fast path; compile-time patch size, 16-byte aligned input):
+//    persistent CTAs, one per SM, 8 warps each.  A warp owns a tile of 32 horizontally adjacent cells
+//    (one cell per lane) and streams the tile's image rows through a private ring of shared-memory
+//    slots filled by cp.async.bulk (TMA bulk copies, one per contiguous row segment) that complete on
+//    per-slot mbarriers.  The warp is its own producer: after the lanes have consumed a slot, lane 0
+//    re-arms its mbarrier and issues the copy of the row RING slots ahead, so RING-1 slots of loads are
+//    always in flight per warp while the lanes run the order-exact walk on the current one.  No
+//    __syncthreads on the data path.
+//
+//  * cell_stats_tile_kernel (fallback: any supported patch size, unaligned input): one CTA stages a whole
+//    tile of cells with plain loads, then one thread per cell walks it.
+//
+// The walk is sequential per cell on purpose: the reference's X^T X entries are sequential fp32 chains
+// and its column sums an 8-lane strided tree (Eigen 3.4); labels only match if those orders are
+// reproduced exactly.  A lane carries 6 + 24 independent accumulators, so the chains
+// overlap in the FMA pipe and the kernel is bound by HBM, not by the dependency chains.
+//
+// Algorithmic bytes: 12 B/pixel read once; <= 87 B/cell written.
 #include "cell_stats.cuh"
 
-#include "plane_fit.cuh"
+#include "cell_walk.cuh"
 
 namespace dpx {
 namespace {
-
-// ---- shared-memory tile addressing -------------------------------------------------------------
-// Row-major input (x y z interleaved): tile[(i * tw + col) * 3 + a]
-// Col-major input (three planes):      tile[(a * p + i) * tw + col]
-template <int LAYOUT>
-__device__ __forceinline__ int tile_index(int tw, int p, int i, int col, int a) {
-  return LAYOUT == kLayoutRowMajor ? (i * tw + col) * 3 + a : (a * p + i) * tw + col;
-}
-
-// Eigen 3.4 DenseBase::sum() over one contiguous fp32 column of N entries whose first 16-byte aligned
-// entry is S (Redux.h, LinearVectorizedTraversal/NoUnrolling, SSE2 Packet4f): two packet accumulators
-// over [S, S + 8*floor((N-S)/8)), an optional remainder packet, predux (a0+a2)+(a1+a3), then the
-// leading and trailing scalars.  `add(k, v)` is called with k = 0..N-1 in order; after full
-// unrolling every index below is a compile-time constant, so all state lives in registers.
-template <int N, int S0>
-struct ColumnSum {
-  static constexpr int kS = S0 > N ? N : S0;
-  static constexpr int kAligned = ((N - kS) / 4) * 4;
-  static constexpr int kAligned2 = ((N - kS) / 8) * 8;
-  static constexpr int kTrail = N - kS - kAligned;
-  float a0[4], a1[4], rem[4], lead[3], trail[3], seq;
-
-  __device__ __forceinline__ void add(int k, float v) {
-    if (kAligned == 0) {
-      seq = (k == 0) ? v : __fadd_rn(seq, v);
-      return;
-    }
-    if (k < kS) {
-      lead[k] = v;
-      return;
-    }
-    const int m = k - kS;
-    if (m < kAligned2) {
-      const int pi = m >> 2, l = m & 3;
-      if (pi == 0) a0[l] = v;
-      else if (pi == 1) a1[l] = v;
-      else if ((pi & 1) == 0) a0[l] = __fadd_rn(a0[l], v);
-      else a1[l] = __fadd_rn(a1[l], v);
-    } else if (m < kAligned) {
-      rem[m - kAligned2] = v;
-    } else {
-      trail[m - kAligned] = v;
-    }
-  }
-
-  __device__ __forceinline__ float result() const {
-    if (kAligned == 0) return seq;
-    float r[4];
-#pragma unroll
-    for (int l = 0; l < 4; ++l) {
-      if (kAligned2 == 0) {
-        r[l] = rem[l];
-      } else {
-        r[l] = __fadd_rn(a0[l], a1[l]);
-        if (kAligned > kAligned2) r[l] = __fadd_rn(r[l], rem[l]);
-      }
-    }
-    float res = __fadd_rn(__fadd_rn(r[0], r[2]), __fadd_rn(r[1], r[3]));
-#pragma unroll
-    for (int i = 0; i < kS; ++i) res = __fadd_rn(res, lead[i]);
-#pragma unroll
-    for (int i = 0; i < kTrail; ++i) res = __fadd_rn(res, trail[i]);
-    return res;
-  }
-};
-
-struct CellRaw {
-  Moments m;
-  int valid_cnt, hcnt, vcnt;
-  float first[3], last[3];
-};
-
-__device__ __forceinline__ void scan_step(float cur, float& prev, int& cnt, float thr) {
-  // cell_segment.cpp:68-73 / :84-88
-  if (cur > 0.f && fabsf(__fsub_rn(cur, prev)) < thr)
-    prev = cur;
-  else if (cur > 0.f)
-    ++cnt;
-}
-
-// Load the P points of row i of cell t with the widest shared-memory vector the alignment allows.
-template <int LAYOUT, int P>
-__device__ __forceinline__ void load_cell_row(const float* tile, int tw, int i, int t, float (&x)[P], float (&y)[P],
-                                              float (&z)[P]) {
-  constexpr int VW = (P % 4 == 0) ? 4 : ((P % 2 == 0) ? 2 : 1);
-  if (LAYOUT == kLayoutRowMajor) {
-    const float* src = tile + (i * tw + t * P) * 3;
-    float buf[3 * P];
-    if (VW == 4) {
-#pragma unroll
-      for (int q = 0; q < 3 * P / 4; ++q) {
-        const float4 v = reinterpret_cast<const float4*>(src)[q];
-        buf[4 * q] = v.x; buf[4 * q + 1] = v.y; buf[4 * q + 2] = v.z; buf[4 * q + 3] = v.w;
-      }
-    } else if (VW == 2) {
-#pragma unroll
-      for (int q = 0; q < 3 * P / 2; ++q) {
-        const float2 v = reinterpret_cast<const float2*>(src)[q];
-        buf[2 * q] = v.x; buf[2 * q + 1] = v.y;
-      }
-    } else {
-#pragma unroll
-      for (int q = 0; q < 3 * P; ++q) buf[q] = src[q];
-    }
-#pragma unroll
-    for (int j = 0; j < P; ++j) {
-      x[j] = buf[3 * j]; y[j] = buf[3 * j + 1]; z[j] = buf[3 * j + 2];
-    }
-  } else {
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const float* src = tile + (a * P + i) * tw + t * P;
-      float(&dst)[P] = (a == 0) ? x : (a == 1 ? y : z);
-      if (VW == 4) {
-#pragma unroll
-        for (int q = 0; q < P / 4; ++q) {
-          const float4 v = reinterpret_cast<const float4*>(src)[q];
-          dst[4 * q] = v.x; dst[4 * q + 1] = v.y; dst[4 * q + 2] = v.z; dst[4 * q + 3] = v.w;
-        }
-      } else if (VW == 2) {
-#pragma unroll
-        for (int q = 0; q < P / 2; ++q) {
-          const float2 v = reinterpret_cast<const float2*>(src)[q];
-          dst[2 * q] = v.x; dst[2 * q + 1] = v.y;
-        }
-      } else {
-#pragma unroll
-        for (int q = 0; q < P; ++q) dst[q] = src[q];
-      }
-    }
-  }
-}
-
-// Fully unrolled walk over one cell (compile-time patch size).
-template <int LAYOUT, int P>
-__device__ __forceinline__ void walk_cell_static(const float* tile, int tw, int t, float disc_thr, CellRaw& out) {
-  constexpr int N = P * P;
-  ColumnSum<N, (4 - (0 * N) % 4) % 4> sx;
-  ColumnSum<N, (4 - (1 * N) % 4) % 4> sy;
-  ColumnSum<N, (4 - (2 * N) % 4) % 4> sz;
-  float vxx = 0.f, vxy = 0.f, vxz = 0.f, vyy = 0.f, vyz = 0.f, vzz = 0.f;
-  int valid = 0, hcnt = 0, vcnt = 0;
-  float hprev = 0.f, vprev = 0.f;
-#pragma unroll
-  for (int i = 0; i < P; ++i) {
-    float x[P], y[P], z[P];
-    load_cell_row<LAYOUT, P>(tile, tw, i, t, x, y, z);
-#pragma unroll
-    for (int j = 0; j < P; ++j) {
-      const int k = i * P + j;
-      const float px = x[j], py = y[j], pz = z[j];
-      if (k == 0) { out.first[0] = px; out.first[1] = py; out.first[2] = pz; }
-      if (k == N - 1) { out.last[0] = px; out.last[1] = py; out.last[2] = pz; }
-      // X^T X: one sequential chain per entry (Eigen GEBP scalar path; cell_segment_stat.cpp:32)
-      vxx = __fadd_rn(__fmul_rn(px, px), vxx);
-      vxy = __fadd_rn(__fmul_rn(px, py), vxy);
-      vxz = __fadd_rn(__fmul_rn(px, pz), vxz);
-      vyy = __fadd_rn(__fmul_rn(py, py), vyy);
-      vyz = __fadd_rn(__fmul_rn(py, pz), vyz);
-      vzz = __fadd_rn(__fmul_rn(pz, pz), vzz);
-      // column sums (cell_segment_stat.cpp:31)
-      sx.add(k, px);
-      sy.add(k, py);
-      sz.add(k, pz);
-      // hasValidPoints (cell_segment.cpp:57-60)
-      valid += (pz > 0.f) ? 1 : 0;
-      // isHorizontalContinuous: indices [N/2, N/2 + P) (cell_segment.cpp:62-76)
-      if (k == N / 2) hprev = pz;
-      if (k >= N / 2 && k < N / 2 + P) scan_step(pz, hprev, hcnt, disc_thr);
-      // isVerticalContinuous: indices P/2, P/2 + P, ... (cell_segment.cpp:78-91)
-      if (j == P / 2) {
-        if (i == 0) vprev = pz;
-        scan_step(pz, vprev, vcnt, disc_thr);
-      }
-    }
-  }
-  out.m.n = N;
-  out.m.s[0] = sx.result(); out.m.s[1] = sy.result(); out.m.s[2] = sz.result();
-  out.m.v[0] = vxx; out.m.v[1] = vxy; out.m.v[2] = vxz; out.m.v[3] = vyy; out.m.v[4] = vyz; out.m.v[5] = vzz;
-  out.valid_cnt = valid; out.hcnt = hcnt; out.vcnt = vcnt;
-}
-
-// Runtime-patch fallback (any 4 <= patch <= 26): same orders, loops not unrolled.
-template <int LAYOUT>
-__device__ float column_sum_runtime(const float* tile, int tw, int p, int t, int a, int n, int s) {
-  auto at = [&](int k) { return tile[tile_index<LAYOUT>(tw, p, k / p, t * p + k % p, a)]; };
-  if (s > n) s = n;
-  const int aligned2 = ((n - s) / 8) * 8, aligned = ((n - s) / 4) * 4;
-  const int end2 = s + aligned2, end1 = s + aligned;
-  float res;
-  if (aligned) {
-    float a0[4], a1[4];
-#pragma unroll
-    for (int l = 0; l < 4; ++l) a0[l] = at(s + l);
-    if (aligned > 4) {
-#pragma unroll
-      for (int l = 0; l < 4; ++l) a1[l] = at(s + 4 + l);
-      for (int i = s + 8; i < end2; i += 8) {
-#pragma unroll
-        for (int l = 0; l < 4; ++l) a0[l] = __fadd_rn(a0[l], at(i + l));
-#pragma unroll
-        for (int l = 0; l < 4; ++l) a1[l] = __fadd_rn(a1[l], at(i + 4 + l));
-      }
-#pragma unroll
-      for (int l = 0; l < 4; ++l) a0[l] = __fadd_rn(a0[l], a1[l]);
-      if (end1 > end2) {
-#pragma unroll
-        for (int l = 0; l < 4; ++l) a0[l] = __fadd_rn(a0[l], at(end2 + l));
-      }
-    }
-    res = __fadd_rn(__fadd_rn(a0[0], a0[2]), __fadd_rn(a0[1], a0[3]));
-    for (int i = 0; i < s; ++i) res = __fadd_rn(res, at(i));
-    for (int i = end1; i < n; ++i) res = __fadd_rn(res, at(i));
-  } else {
-    res = at(0);
-    for (int i = 1; i < n; ++i) res = __fadd_rn(res, at(i));
-  }
-  return res;
-}
-
-template <int LAYOUT>
-__device__ void walk_cell_runtime(const float* tile, int tw, int p, int t, float disc_thr, CellRaw& out) {
-  const int n = p * p;
-  float vxx = 0.f, vxy = 0.f, vxz = 0.f, vyy = 0.f, vyz = 0.f, vzz = 0.f;
-  int valid = 0, hcnt = 0, vcnt = 0;
-  float hprev = 0.f, vprev = 0.f;
-  for (int i = 0; i < p; ++i)
-    for (int j = 0; j < p; ++j) {
-      const int k = i * p + j;
-      const float px = tile[tile_index<LAYOUT>(tw, p, i, t * p + j, 0)];
-      const float py = tile[tile_index<LAYOUT>(tw, p, i, t * p + j, 1)];
-      const float pz = tile[tile_index<LAYOUT>(tw, p, i, t * p + j, 2)];
-      if (k == 0) { out.first[0] = px; out.first[1] = py; out.first[2] = pz; }
-      if (k == n - 1) { out.last[0] = px; out.last[1] = py; out.last[2] = pz; }
-      vxx = __fadd_rn(__fmul_rn(px, px), vxx);
-      vxy = __fadd_rn(__fmul_rn(px, py), vxy);
-      vxz = __fadd_rn(__fmul_rn(px, pz), vxz);
-      vyy = __fadd_rn(__fmul_rn(py, py), vyy);
-      vyz = __fadd_rn(__fmul_rn(py, pz), vyz);
-      vzz = __fadd_rn(__fmul_rn(pz, pz), vzz);
-      valid += (pz > 0.f) ? 1 : 0;
-      if (k == n / 2) hprev = pz;
-      if (k >= n / 2 && k < n / 2 + p) scan_step(pz, hprev, hcnt, disc_thr);
-      if (j == p / 2) {
-        if (i == 0) vprev = pz;
-        scan_step(pz, vprev, vcnt, disc_thr);
-      }
-    }
-  out.m.n = n;
-  for (int a = 0; a < 3; ++a) out.m.s[a] = column_sum_runtime<LAYOUT>(tile, tw, p, t, a, n, (4 - (a * n) % 4) % 4);
-  out.m.v[0] = vxx; out.m.v[1] = vxy; out.m.v[2] = vxz; out.m.v[3] = vyy; out.m.v[4] = vyz; out.m.v[5] = vzz;
-  out.valid_cnt = valid; out.hcnt = hcnt; out.vcnt = vcnt;
-}
-
-// Everything after the moments: validity, plane fit, planarity, merge tolerance, histogram bin.
-__device__ __forceinline__ void finish_cell(const CellRaw& raw, const Thresholds& th, const Tables& tb, long long cell) {
-  const bool valid = static_cast<unsigned long long>(raw.valid_cnt) >= th.valid_pts_threshold &&
-                     raw.hcnt < th.max_number_depth_discontinuity && raw.vcnt < th.max_number_depth_discontinuity;
-  uint8_t flags = 0;
-  int bin = -1;
-  if (valid) {
-    flags = kFlagValid;
-    PlaneFit fit;
-    fit_plane(raw.m, fit);
-
-    // hasSmallPlaneError (cell_segment.cpp:99-102): fp32 threshold, compared in fp64
-    const float thr = __fadd_rn(__fmul_rn(th.depth_sigma_coeff, __fmul_rn(fit.mean[2], fit.mean[2])), th.depth_sigma_margin);
-    const bool planar = static_cast<double>(fit.mse) <= __dmul_rn(static_cast<double>(thr), static_cast<double>(thr));
-
-    // calculateMergeTolerance (cell_segment.cpp:104-110), minimum 20.0 hard-coded at :34
-    const float sin_merge = __fsqrt_rn(__fsub_rn(1.0f, __fmul_rn(th.min_cos_angle_merge, th.min_cos_angle_merge)));
-    const float dx = __fsub_rn(raw.first[0], raw.last[0]);
-    const float dy = __fsub_rn(raw.first[1], raw.last[1]);
-    const float dz = __fsub_rn(raw.first[2], raw.last[2]);
-    const float diam = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dz, dz))));
-    const float a = __fmul_rn(diam, sin_merge);
-    const float mx = (a < 20.0f) ? 20.0f : a;                              // std::max(a, 20.0f)
-    const float tr = (th.max_merge_dist < mx) ? th.max_merge_dist : mx;    // std::min(mx, max_merge_dist)
-    const float tol = __fmul_rn(tr, tr);
-
-    if (planar) {
-      // normals_histogram.cpp:33-45 (isZero() precision 1e-5; fp64 trigonometry)
-      const float nx = fit.normal[0], ny = fit.normal[1], nz = fit.normal[2];
-      if (!(fabsf(nx) <= 1e-5f && fabsf(ny) <= 1e-5f && fabsf(nz) <= 1e-5f)) {
-        const int B = th.histogram_bins_per_coord;
-        const f64 dnx = static_cast<double>(nx), dny = static_cast<double>(ny);
-        const f64 proj = sqrt(dnx * dnx + dny * dny);
-        const double polar = ::acos(static_cast<double>(-nz));
-        const double azimuth = ::atan2((dnx / proj).v, (dny / proj).v);
-        const double kPi = 3.14159265358979323846;
-        const int xq = __double2int_rz(((f64(static_cast<double>(B - 1)) * (f64(polar) - f64(0.0))) / f64(kPi)).v);
-        int yq = 0;
-        if (xq > 0)
-          yq = __double2int_rz(
-              ((f64(static_cast<double>(B - 1)) * (f64(azimuth) - f64(-kPi))) / (f64(kPi) - f64(-kPi))).v);
-        const int b = yq * B + xq;
-        // outside [0, B*B) the reference writes out of bounds; such a cell is dropped here
-        if (b >= 0 && b < B * B) {
-          bin = b;
-          flags |= kFlagPlanar;
-        }
-      }
-    }
-    tb.rec_a[2 * cell] = make_float4(fit.normal[0], fit.normal[1], fit.normal[2], fit.d);
-    tb.rec_a[2 * cell + 1] = make_float4(fit.mean[0], fit.mean[1], fit.mean[2], tol);
-    tb.rec_b[3 * cell] = make_float4(raw.m.s[0], raw.m.s[1], raw.m.s[2], raw.m.v[0]);
-    tb.rec_b[3 * cell + 1] = make_float4(raw.m.v[1], raw.m.v[2], raw.m.v[3], raw.m.v[4]);
-    tb.rec_b[3 * cell + 2] = make_float4(raw.m.v[5], fit.mse, fit.score, 0.f);
-  }
-  tb.flags[cell] = flags;
-  tb.bin[cell] = static_cast<int16_t>(bin);
-}
 
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   float4 r;
@@ -343,9 +43,11 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   return r;
 }
 
-// One CTA = one tile of up to `tile_cells` cells of one cell-row of one frame.
+// ---------------------------------------------------------------------------------------------------
+// Fallback: one CTA = one tile of up to `tile_cells` cells of one cell-row of one frame.
+// ---------------------------------------------------------------------------------------------------
 template <int LAYOUT, int PATCH>
-__global__ void __launch_bounds__(kCellStatsThreads) cell_stats_kernel(const CellStatsArgs args) {
+__global__ void __launch_bounds__(kCellStatsThreads) cell_stats_tile_kernel(const CellStatsArgs args) {
   extern __shared__ float4 smem_f4[];
   float* tile = reinterpret_cast<float*>(smem_f4);
 
@@ -366,7 +68,6 @@ __global__ void __launch_bounds__(kCellStatsThreads) cell_stats_kernel(const Cel
   const float* src = args.xyz + static_cast<long long>(frame) * 3 * g.n_points;
   const long long row0 = static_cast<long long>(strip) * p * g.width + static_cast<long long>(c0) * p;
 
-  // ---- stage the tile: coalesced, streaming (read-once) loads -------------------------------------
   if (LAYOUT == kLayoutRowMajor) {
     const int row_floats = seg * 3;
     const bool vec = args.vec_ok && (row_floats % 4 == 0) && ((row0 * 3) % 4 == 0);
@@ -401,25 +102,181 @@ __global__ void __launch_bounds__(kCellStatsThreads) cell_stats_kernel(const Cel
   }
   __syncthreads();
 
-  // ---- one thread per cell ------------------------------------------------------------------------
   const int t = threadIdx.x;
   if (t < cnt) {
     CellRaw raw;
-    if (PATCH)
-      walk_cell_static<LAYOUT, PATCH ? PATCH : 4>(tile, tw, t, args.thr.depth_discontinuity_threshold, raw);
-    else
+    if (PATCH) {
+      constexpr int P = PATCH ? PATCH : 4;
+      CellWalk<P> walk;
+      walk.reset();
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        float x[P], y[P], z[P];
+        load_cell_row<LAYOUT, P>(tile, tw, P, i, t, x, y, z);
+        walk.row(i, x, y, z, args.thr.depth_discontinuity_threshold);
+      }
+      walk.finish(raw);
+    } else {
       walk_cell_runtime<LAYOUT>(tile, tw, p, t, args.thr.depth_discontinuity_threshold, raw);
+    }
     const long long cell = static_cast<long long>(frame) * g.n_cells + static_cast<long long>(strip) * g.nh + c0 + t;
     finish_cell(raw, args.thr, args.tables, cell);
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fast path: persistent, warp-private TMA-bulk row pipeline.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kRing = 4;  // slots per warp
+
+// rows staged per slot: the largest divisor of P whose slot stays <= 4 KB (else one row)
+__host__ __device__ constexpr int rows_per_slot(int P) {
+  int best = 1;
+  for (int r = 1; r <= P; ++r)
+    if (P % r == 0 && r * 32 * P * 12 <= 4096) best = r;
+  return best;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int LAYOUT, int P, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) cell_stats_stream_kernel(const CellStatsArgs args) {
+  constexpr int kStreamWarps = WARPS;
+  constexpr int RPS = rows_per_slot(P);
+  constexpr int SPT = P / RPS;               // stages (slots) per tile
+  constexpr int TW = 32 * P;                 // points per staged row
+  constexpr int SLOT_FLOATS = RPS * TW * 3;
+  extern __shared__ float4 smem_f4[];
+  __shared__ __align__(8) uint64_t bars[kStreamWarps * kRing];
+
+  const Geometry& g = args.geom;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* ring = reinterpret_cast<float*>(smem_f4) + static_cast<size_t>(warp) * kRing * SLOT_FLOATS;
+  uint64_t* bar = bars + warp * kRing;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kRing; ++s) mbar_init(bar + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  const long long total_tiles = static_cast<long long>(args.n_frames) * g.nv * args.tiles_per_strip;
+  const long long gw = static_cast<long long>(blockIdx.x) * kStreamWarps + warp;
+  const long long total_warps = static_cast<long long>(gridDim.x) * kStreamWarps;
+  if (gw >= total_tiles) return;
+  const long long my_tiles = (total_tiles - gw + total_warps - 1) / total_warps;
+  const long long total_stages = my_tiles * SPT;
+
+  // lane 0: arm the slot's mbarrier and issue the bulk copies of stage q (global stage index of this warp)
+  auto issue = [&](long long q) {
+    if (q >= total_stages || lane != 0) return;
+    const long long n = q / SPT;
+    const int st = static_cast<int>(q - n * SPT);
+    long long tile = gw + n * total_warps;
+    const int tix = static_cast<int>(tile % args.tiles_per_strip);
+    tile /= args.tiles_per_strip;
+    const int strip = static_cast<int>(tile % g.nv);
+    const long long frame = tile / g.nv;
+    const int c0 = tix * 32;
+    const int cnt = min(32, g.nh - c0);
+    const unsigned seg_bytes = static_cast<unsigned>(cnt) * P * 4;  // one component of one row segment
+    const int slot = static_cast<int>(q % kRing);
+    float* dst = ring + slot * SLOT_FLOATS;
+    const float* src = args.xyz + frame * 3 * g.n_points;
+    const long long row0 = (static_cast<long long>(strip) * P + st * RPS) * g.width + static_cast<long long>(c0) * P;
+    mbar_expect_tx(bar + slot, seg_bytes * 3 * RPS);
+    if (LAYOUT == kLayoutRowMajor) {
+#pragma unroll
+      for (int rr = 0; rr < RPS; ++rr)
+        bulk_g2s(dst + rr * TW * 3, src + (row0 + static_cast<long long>(rr) * g.width) * 3, seg_bytes * 3, bar + slot);
+    } else {
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int rr = 0; rr < RPS; ++rr)
+          bulk_g2s(dst + (a * RPS + rr) * TW, src + a * g.n_points + row0 + static_cast<long long>(rr) * g.width, seg_bytes,
+                   bar + slot);
+    }
+  };
+
+#pragma unroll
+  for (int s = 0; s < kRing; ++s) issue(s);
+
+  long long q = 0;
+  for (long long n = 0; n < my_tiles; ++n) {
+    long long tile = gw + n * total_warps;
+    const int tix = static_cast<int>(tile % args.tiles_per_strip);
+    tile /= args.tiles_per_strip;
+    const int strip = static_cast<int>(tile % g.nv);
+    const long long frame = tile / g.nv;
+    const int c0 = tix * 32;
+    const int cnt = min(32, g.nh - c0);
+
+    CellWalk<P> walk;
+    walk.reset();
+#pragma unroll
+    for (int st = 0; st < SPT; ++st, ++q) {
+      const int slot = static_cast<int>(q % kRing);
+      mbar_wait(bar + slot, static_cast<unsigned>((q / kRing) & 1));
+      const float* blk = ring + slot * SLOT_FLOATS;
+      if (lane < cnt) {
+#pragma unroll
+        for (int rr = 0; rr < RPS; ++rr) {
+          float x[P], y[P], z[P];
+          load_cell_row<LAYOUT, P>(blk, TW, RPS, rr, lane, x, y, z);
+          walk.row(st * RPS + rr, x, y, z, args.thr.depth_discontinuity_threshold);
+        }
+      }
+      __syncwarp();        // every lane is done reading the slot ...
+      issue(q + kRing);    // ... before the async proxy refills it
+    }
+    if (lane < cnt) {
+      CellRaw raw;
+      walk.finish(raw);
+      const long long cell = frame * g.n_cells + static_cast<long long>(strip) * g.nh + c0 + lane;
+      finish_cell(raw, args.thr, args.tables, cell);
+    }
+  }
+}
+
 template <int LAYOUT>
-cudaError_t launch_layout(const CellStatsArgs& a, int grid, size_t smem, cudaStream_t st) {
-#define DPX_CASE(P)                                                                                          \
-  case P:                                                                                                    \
-    cudaFuncSetAttribute(cell_stats_kernel<LAYOUT, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    cell_stats_kernel<LAYOUT, P><<<grid, kCellStatsThreads, smem, st>>>(a);                                  \
+cudaError_t launch_tile(const CellStatsArgs& a, int grid, size_t smem, cudaStream_t st) {
+#define DPX_CASE(P)                                                                                               \
+  case P:                                                                                                         \
+    cudaFuncSetAttribute(cell_stats_tile_kernel<LAYOUT, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    cell_stats_tile_kernel<LAYOUT, P><<<grid, kCellStatsThreads, smem, st>>>(a);                                  \
     break;
   switch (a.geom.patch) {
     DPX_CASE(4)
@@ -428,19 +285,48 @@ cudaError_t launch_layout(const CellStatsArgs& a, int grid, size_t smem, cudaStr
     DPX_CASE(8)
     DPX_CASE(10)
     default:
-      cudaFuncSetAttribute(cell_stats_kernel<LAYOUT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cell_stats_kernel<LAYOUT, 0><<<grid, kCellStatsThreads, smem, st>>>(a);
+      cudaFuncSetAttribute(cell_stats_tile_kernel<LAYOUT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cell_stats_tile_kernel<LAYOUT, 0><<<grid, kCellStatsThreads, smem, st>>>(a);
       break;
   }
 #undef DPX_CASE
   return cudaGetLastError();
 }
 
+template <int LAYOUT, int P, int WARPS>
+cudaError_t launch_stream_pw(const CellStatsArgs& a, cudaStream_t st) {
+  constexpr size_t smem = static_cast<size_t>(WARPS) * kRing * rows_per_slot(P) * 32 * P * 12;
+  static_assert(smem <= 200 * 1024, "ring does not fit");
+  cudaFuncSetAttribute(cell_stats_stream_kernel<LAYOUT, P, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const long long total_tiles = static_cast<long long>(a.n_frames) * a.geom.nv * a.tiles_per_strip;
+  const long long ctas = (total_tiles + WARPS - 1) / WARPS;
+  const int grid = static_cast<int>(ctas < a.sm_count ? ctas : a.sm_count);
+  cell_stats_stream_kernel<LAYOUT, P, WARPS><<<grid, WARPS * 32, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <int LAYOUT, int P>
+cudaError_t launch_stream_p(const CellStatsArgs& a, cudaStream_t st) {
+  return a.stream_warps == 12 ? launch_stream_pw<LAYOUT, P, 12>(a, st) : launch_stream_pw<LAYOUT, P, 8>(a, st);
+}
+
+template <int LAYOUT>
+bool launch_stream(const CellStatsArgs& a, cudaStream_t st, cudaError_t* err) {
+  switch (a.geom.patch) {
+    case 4: *err = launch_stream_p<LAYOUT, 4>(a, st); return true;
+    case 5: *err = launch_stream_p<LAYOUT, 5>(a, st); return true;
+    case 6: *err = launch_stream_p<LAYOUT, 6>(a, st); return true;
+    case 8: *err = launch_stream_p<LAYOUT, 8>(a, st); return true;
+    case 10: *err = launch_stream_p<LAYOUT, 10>(a, st); return true;
+    default: return false;
+  }
+}
+
 }  // namespace
 
 int cell_stats_tile_cells(int patch, int nh) {
-  // largest power-of-two tile (<= one thread per cell per CTA) whose staging buffer stays <= 40 KB,
-  // so that several CTAs are resident per SM and loads of one overlap the walk of another
+  // fallback kernel: largest power-of-two tile (<= one thread per cell per CTA) whose staging buffer stays
+  // <= 40 KB, so that several CTAs are resident per SM and loads of one overlap the walk of another
   const size_t per_cell = static_cast<size_t>(patch) * patch * 12;
   int tc = kCellStatsThreads;
   while (tc > 4 && tc * per_cell > 40 * 1024) tc >>= 1;
@@ -448,16 +334,35 @@ int cell_stats_tile_cells(int patch, int nh) {
   return tc;
 }
 
+bool cell_stats_stream_eligible(const CellStatsArgs& a) {
+  const Geometry& g = a.geom;
+  if (!a.vec_ok || a.force_tile_kernel) return false;
+  const int p = g.patch;
+  if (!(p == 4 || p == 5 || p == 6 || p == 8 || p == 10)) return false;
+  // every bulk copy must start on a 16-byte boundary and move a multiple of 16 bytes
+  if ((32 * p) % 4 != 0) return false;
+  const int tail = g.nh % 32;
+  if ((tail * p) % 4 != 0) return false;
+  return true;
+}
+
 cudaError_t launch_cell_stats(const CellStatsArgs& args_in, cudaStream_t stream) {
   CellStatsArgs a = args_in;
   const Geometry& g = a.geom;
   if (g.n_cells == 0 || a.n_frames == 0) return cudaSuccess;
+  if (cell_stats_stream_eligible(a)) {
+    a.tiles_per_strip = (g.nh + 31) / 32;
+    cudaError_t err = cudaSuccess;
+    const bool ok = a.layout == kLayoutRowMajor ? launch_stream<kLayoutRowMajor>(a, stream, &err)
+                                                : launch_stream<kLayoutColMajor>(a, stream, &err);
+    if (ok) return err;
+  }
   a.tiles_per_strip = (g.nh + a.tile_cells - 1) / a.tile_cells;
   const size_t smem = static_cast<size_t>(a.tile_cells) * g.patch * g.patch * 12;
   const long long grid = static_cast<long long>(a.n_frames) * g.nv * a.tiles_per_strip;
   if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
-  return a.layout == kLayoutRowMajor ? launch_layout<kLayoutRowMajor>(a, static_cast<int>(grid), smem, stream)
-                                     : launch_layout<kLayoutColMajor>(a, static_cast<int>(grid), smem, stream);
+  return a.layout == kLayoutRowMajor ? launch_tile<kLayoutRowMajor>(a, static_cast<int>(grid), smem, stream)
+                                     : launch_tile<kLayoutColMajor>(a, static_cast<int>(grid), smem, stream);
 }
 
 }  // namespace dpx

@@ -13,6 +13,9 @@ struct CellStatsArgs {
   int tile_cells;       // cells staged per CTA (from cell_stats_tile_cells)
   int tiles_per_strip;  // filled by the launcher
   int vec_ok;           // base pointer and plane strides allow 16-byte loads
+  int sm_count;         // persistent grid size of the streaming kernel
+  int force_tile_kernel;  // diagnostics: always take the fallback kernel
+  int stream_warps;     // warps per persistent CTA of the streaming kernel (8 or 12)
   Geometry geom;
   Thresholds thr;
   Tables tables;

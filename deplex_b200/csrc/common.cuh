@@ -5,6 +5,7 @@
 //   rec_b   float4[F][C][3]  {Sx,Sy,Sz,Vxx} {Vxy,Vxz,Vyy,Vyz} {Vzz,mse,score,0}    48 B/cell  (read by the accumulation)
 //   bin     int16 [F][C]     initial NormalsHistogram bin, -1 when the cell is not planar
 //   flags   uint8 [F][C]     bit0 = valid (stats exist), bit1 = planar
+//   mse     float [F][C]     per-cell MSE again, dense, for the seed scan (written for valid cells only)
 //   seg_label / cell_label int32[F][C], queue int32[F][C], pairs uint32[F][2C], segs float[F][Pcap][24],
 //   merge int32[F][Pcap], n_planes int32[F]
 // rec_a / rec_b are only written for valid cells; nothing reads them for the others.
@@ -23,6 +24,8 @@ constexpr uint8_t kFlagPlanar = 2;
 constexpr int kSegFloats = 24;  // n(int) S3 V6 mean3 normal3 d mse score + pad
 // offsets inside one segment record
 constexpr int kSegN = 0, kSegS = 1, kSegV = 4, kSegMean = 10, kSegNormal = 13, kSegD = 16, kSegMse = 17, kSegScore = 18;
+// while regions are being grown, the record also remembers where the region's cells sit in the cell list
+constexpr int kSegOff = 19, kSegCnt = 20;
 
 struct Geometry {
   int height, width;
@@ -49,6 +52,7 @@ struct Tables {
   float4* rec_b;
   int16_t* bin;
   uint8_t* flags;
+  float* mse;          // [F][C] dense copy of the per-cell MSE (seed selection scans it)
   int32_t* seg_label;
   int32_t* cell_label;
   int32_t* queue;

@@ -4,15 +4,22 @@
 
 namespace dpx {
 
+// Where the per-frame working set lives (shared memory when it fits, else the global scratch tables).
+struct RegionPlan {
+  int bins_smem, list_smem, members_smem;
+  int off_hist, off_binoff, off_cursor, off_rowbits, off_bins, off_list, off_members, off_msem;
+  size_t bytes;  // dynamic shared memory per CTA
+};
+
 struct RegionArgs {
   int n_frames;
-  int bins_in_smem;  // per-cell working bins fit in shared memory (else Tables::bin_work)
+  RegionPlan plan;
   Geometry geom;
   Thresholds thr;
   Tables tables;
 };
 
-size_t region_grow_smem_bytes(const Geometry& g, const Thresholds& th, bool bins_in_smem);
+RegionPlan region_grow_plan(const Geometry& g, const Thresholds& th);
 cudaError_t launch_region_grow(const RegionArgs& args, cudaStream_t stream);
 
 }  // namespace dpx
