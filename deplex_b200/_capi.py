@@ -14,7 +14,7 @@ STAGE_NAMES = ("cell_stats", "region_grow", "labeling", "refine")
 EXPORTS = (
     "dpx_config_default", "dpx_config_load_ini", "dpx_create", "dpx_destroy", "dpx_last_error", "dpx_get_info",
     "dpx_process_host", "dpx_process_batch_host", "dpx_process_batch_device", "dpx_get_cells", "dpx_get_planes",
-    "dpx_set_profiling", "dpx_get_stage_ms", "dpx_kernel_launches", "dpx_host_alloc", "dpx_host_free", "dpx_version",
+    "dpx_set_profiling", "dpx_get_stage_ms", "dpx_get_region_profile", "dpx_kernel_launches", "dpx_host_alloc", "dpx_host_free", "dpx_version",
 )
 
 
@@ -80,6 +80,7 @@ def load():
         "dpx_get_planes": (C.c_int, [vp, i32, C.POINTER(dpx_plane), i32, C.POINTER(i32)]),
         "dpx_set_profiling": (C.c_int, [vp, i32]),
         "dpx_get_stage_ms": (C.c_int, [vp, C.POINTER(C.c_float * N_STAGES)]),
+        "dpx_get_region_profile": (C.c_int, [vp, i32, C.POINTER(C.c_int64 * 12)]),
         "dpx_kernel_launches": (i64, [vp]),
         "dpx_host_alloc": (C.c_int, [C.POINTER(vp), C.c_size_t]),
         "dpx_host_free": (None, [vp]),

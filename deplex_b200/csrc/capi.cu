@@ -39,6 +39,7 @@ struct dpx_extractor {
   int stream_warps = 8;       // env DPX_STREAM_WARPS=8|12
   int force_tile_kernel = 0;  // env DPX_CELL_KERNEL=tile (A/B measurement of the two stage-1 kernels)
   RegionPlan plan{};
+  long long* region_prof = nullptr;  // [max_batch][kRegionProfSlots], written while profiling is on
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
   // host-pointer path: double-buffered staging + three streams
@@ -103,6 +104,7 @@ size_t carve_tables(const Geometry& g, int max_batch, bool bins_in_smem, char* b
   tb->bin = reinterpret_cast<int16_t*>(take(F * C * sizeof(int16_t)));
   tb->flags = reinterpret_cast<uint8_t*>(take(F * C));
   tb->mse = reinterpret_cast<float*>(take(F * C * sizeof(float)));
+  tb->edge = reinterpret_cast<uint8_t*>(take(F * C));
   tb->seg_label = reinterpret_cast<int32_t*>(take(F * C * sizeof(int32_t)));
   tb->cell_label = reinterpret_cast<int32_t*>(take(F * C * sizeof(int32_t)));
   tb->queue = reinterpret_cast<int32_t*>(take(F * C * sizeof(int32_t)));
@@ -139,11 +141,12 @@ dpx_status run_stages(dpx_extractor* ex, const float* d_xyz, int n_frames, int l
     RegionArgs ra{};
     ra.n_frames = n_frames;
     ra.plan = ex->plan;
+    ra.prof = ex->profiling ? ex->region_prof : nullptr;
     ra.geom = ex->geom;
     ra.thr = ex->thr;
     ra.tables = ex->tb;
     DPX_CUDA(ex, launch_region_grow(ra, st));
-    ++ex->launches;
+    ex->launches += 2;  // edge masks + region growing
   }
   if (prof) DPX_CUDA(ex, cudaEventRecord(ex->e_stage[2], st));
   {
@@ -233,6 +236,7 @@ dpx_status dpx_create(int32_t height, int32_t width, const dpx_config* cfg_in, i
     const long long mca = cfg.min_region_growing_cells_activated;
     g.plane_cap = static_cast<int>(mca >= 1 ? g.n_cells / mca : g.n_cells) + 1;
     if (g.plane_cap > 65535) return fail(nullptr, DPX_ERR_UNSUPPORTED, "more than 65535 possible plane segments per frame");
+    if (g.n_cells > 131071) return fail(nullptr, DPX_ERR_UNSUPPORTED, "more than 131071 cells per frame");
     // size_t valid_pts_threshold = cell_points.size() / config.min_pts_per_cell  (signed division, then cast)
     th.valid_pts_threshold = static_cast<unsigned long long>(static_cast<long long>(3LL * p * p) / static_cast<long long>(cfg.min_pts_per_cell));
   } else {
@@ -287,6 +291,10 @@ dpx_status dpx_create(int32_t height, int32_t width, const dpx_config* cfg_in, i
     if (e != cudaSuccess) { delete ex; return cuda_fail(nullptr, e, "cudaMalloc(scratch tables)"); }
     carve_tables(g, max_batch, ex->plan.bins_smem != 0, static_cast<char*>(ex->scratch), &ex->tb);
   }
+  {
+    cudaError_t e = cudaMalloc(&ex->region_prof, sizeof(long long) * kRegionProfSlots * max_batch);
+    if (e != cudaSuccess) { dpx_destroy(ex); return cuda_fail(nullptr, e, "cudaMalloc(region profile)"); }
+  }
   for (int i = 0; i <= DPX_N_STAGES; ++i) {
     cudaError_t e = cudaEventCreate(&ex->e_stage[i]);
     if (e != cudaSuccess) { dpx_destroy(ex); return cuda_fail(nullptr, e, "cudaEventCreate"); }
@@ -312,6 +320,7 @@ void dpx_destroy(dpx_extractor* ex) {
   for (int i = 0; i <= DPX_N_STAGES; ++i)
     if (ex->e_stage[i]) cudaEventDestroy(ex->e_stage[i]);
   if (ex->scratch) cudaFree(ex->scratch);
+  if (ex->region_prof) cudaFree(ex->region_prof);
   delete ex;
 }
 
@@ -475,6 +484,18 @@ dpx_status dpx_get_stage_ms(dpx_extractor* ex, float ms[DPX_N_STAGES]) {
   DeviceGuard guard(ex->device);
   DPX_CUDA(ex, cudaEventSynchronize(ex->e_stage[DPX_N_STAGES]));
   for (int i = 0; i < DPX_N_STAGES; ++i) DPX_CUDA(ex, cudaEventElapsedTime(&ms[i], ex->e_stage[i], ex->e_stage[i + 1]));
+  return DPX_OK;
+}
+
+dpx_status dpx_get_region_profile(dpx_extractor* ex, int32_t frame, int64_t out[DPX_REGION_PROFILE_SLOTS]) {
+  if (!ex || !out) return DPX_ERR_ARGUMENT;
+  static_assert(DPX_REGION_PROFILE_SLOTS == kRegionProfSlots, "header and kernel disagree");
+  if (!ex->stage_valid) return fail(ex, DPX_ERR_ARGUMENT, "no profiled batch: call dpx_set_profiling(ex, 1) first");
+  if (frame < 0 || frame >= ex->last_frames) return fail(ex, DPX_ERR_ARGUMENT, "frame index outside the last batch");
+  DeviceGuard guard(ex->device);
+  DPX_CUDA(ex, cudaDeviceSynchronize());
+  DPX_CUDA(ex, cudaMemcpy(out, ex->region_prof + static_cast<size_t>(frame) * kRegionProfSlots,
+                          sizeof(long long) * kRegionProfSlots, cudaMemcpyDeviceToHost));
   return DPX_OK;
 }
 

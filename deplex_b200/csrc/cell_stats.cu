@@ -163,11 +163,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   }
 }
 // 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
+// The input is read exactly once: an L2 evict-first policy keeps it from displacing the per-cell tables this
+// kernel writes, which the next stage reads back from L2.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
 }
 
 template <int LAYOUT, int P, int WARPS>
@@ -192,6 +200,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cell_stats_stream_kernel(const 
   }
   __syncwarp();
 
+  const uint64_t policy = l2_evict_first_policy();
   const long long total_tiles = static_cast<long long>(args.n_frames) * g.nv * args.tiles_per_strip;
   const long long gw = static_cast<long long>(blockIdx.x) * kStreamWarps + warp;
   const long long total_warps = static_cast<long long>(gridDim.x) * kStreamWarps;
@@ -220,14 +229,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cell_stats_stream_kernel(const 
     if (LAYOUT == kLayoutRowMajor) {
 #pragma unroll
       for (int rr = 0; rr < RPS; ++rr)
-        bulk_g2s(dst + rr * TW * 3, src + (row0 + static_cast<long long>(rr) * g.width) * 3, seg_bytes * 3, bar + slot);
+        bulk_g2s(dst + rr * TW * 3, src + (row0 + static_cast<long long>(rr) * g.width) * 3, seg_bytes * 3, bar + slot,
+                 policy);
     } else {
 #pragma unroll
       for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int rr = 0; rr < RPS; ++rr)
           bulk_g2s(dst + (a * RPS + rr) * TW, src + a * g.n_points + row0 + static_cast<long long>(rr) * g.width, seg_bytes,
-                   bar + slot);
+                   bar + slot, policy);
     }
   };
 

@@ -53,6 +53,7 @@ struct Tables {
   int16_t* bin;
   uint8_t* flags;
   float* mse;          // [F][C] dense copy of the per-cell MSE (seed selection scans it)
+  uint8_t* edge;       // [F][C] precomputed growSeed edge tests, bit s = neighbour slot s (up, down, left, right)
   int32_t* seg_label;
   int32_t* cell_label;
   int32_t* queue;

@@ -74,6 +74,43 @@ __device__ __forceinline__ void store_seg(float* rec, const Moments& m, const Pl
   __stcg(rec + kSegScore, f.score);
 }
 
+// Directed edge tests of growSeed (plane_extractor.cpp:369-383) for every cell and neighbour slot.  The test
+// between a frontier cell u and its neighbour v reads only per-cell constants (n_u, d_u, n_v, mean_v, tol_v),
+// never BFS state, so all 4*C tests of a frame are evaluated up front, fully in parallel over the batch;
+// the sequential BFS then only consults one byte per popped cell.  Bit s of edge[u] = "u may activate its
+// neighbour in slot s" (slots in the reference's push order: up, down, left, right).
+__global__ void __launch_bounds__(256) edge_mask_kernel(const RegionArgs args) {
+  const Geometry& g = args.geom;
+  const long long total = static_cast<long long>(args.n_frames) * g.n_cells;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % g.n_cells);
+  const long long base = idx - c;  // first cell of this frame
+  const int r = c / g.nh, q = c - r * g.nh;
+  unsigned mask = 0;
+  if (args.tables.bin[idx] >= 0) {
+    const float4 nu = __ldg(args.tables.rec_a + 2 * idx);
+    const double min_cos = static_cast<double>(args.thr.min_cos_angle_merge);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      int v = -1;
+      if (s == 0) v = (r >= 1) ? c - g.nh : -1;
+      else if (s == 1) v = (r + 1 < g.nv) ? c + g.nh : -1;
+      else if (s == 2) v = (q >= 1) ? c - 1 : -1;
+      else v = (q + 1 < g.nh) ? c + 1 : -1;
+      if (v < 0 || args.tables.bin[base + v] < 0) continue;
+      const float4 nv = __ldg(args.tables.rec_a + 2 * (base + v));
+      const float4 mv = __ldg(args.tables.rec_a + 2 * (base + v) + 1);
+      const double cos_angle = static_cast<double>(dot3(nu.x, nu.y, nu.z, nv.x, nv.y, nv.z));
+      const double t = __dadd_rn(static_cast<double>(dot3(nu.x, nu.y, nu.z, mv.x, mv.y, mv.z)), static_cast<double>(nu.w));
+      const double merge_dist = __dmul_rn(t, t);
+      if (cos_angle >= min_cos && merge_dist <= static_cast<double>(mv.w)) mask |= 1u << s;
+    }
+  }
+  args.tables.edge[idx] = static_cast<uint8_t>(mask);
+}
+
+template <bool SMEM>
 __global__ void __launch_bounds__(32) region_grow_kernel(const RegionArgs args) {
   extern __shared__ float4 smem_f4[];
   const Geometry& g = args.geom;
@@ -82,51 +119,65 @@ __global__ void __launch_bounds__(32) region_grow_kernel(const RegionArgs args) 
   const int frame = blockIdx.x;
   const int C = g.n_cells, nh = g.nh, nv = g.nv;
   const int B2 = th.histogram_bins_per_coord * th.histogram_bins_per_coord;
+  const long long fc = static_cast<long long>(frame) * C;
 
   // ---- shared-memory carve-up (offsets computed by region_grow_plan on the host) ------------------
   char* smem = reinterpret_cast<char*>(smem_f4);
   float* stage = reinterpret_cast<float*>(smem);                  // [32][12] staging for the accumulation
   int* hist = reinterpret_cast<int*>(smem + args.plan.off_hist);
-  unsigned* rowbits = reinterpret_cast<unsigned*>(smem + args.plan.off_rowbits);
-  int16_t* bins = args.plan.bins_smem ? reinterpret_cast<int16_t*>(smem + args.plan.off_bins)
-                                      : args.tables.bin_work + static_cast<long long>(frame) * C;
-  int32_t* list = args.plan.list_smem ? reinterpret_cast<int32_t*>(smem + args.plan.off_list)
-                                      : args.tables.queue + static_cast<long long>(frame) * C;
-  const float* mse_g = args.tables.mse + static_cast<long long>(frame) * C;
   int* bin_off = reinterpret_cast<int*>(smem + args.plan.off_binoff);   // [B2 + 1] start of each bin's member run
-  int* cursor = reinterpret_cast<int*>(smem + args.plan.off_cursor);    // [B2] fill cursors
+  int* run_end = reinterpret_cast<int*>(smem + args.plan.off_cursor);   // [B2] end of the still-unassigned members
+  unsigned* rowbits = reinterpret_cast<unsigned*>(smem + args.plan.off_rowbits);
+  // bins: working bin per cell during growing (-1 = assigned / not planar); afterwards reused for the segment labels
+  // SMEM = the whole working set is in shared memory: pointers are then provably shared and the compiler
+  // emits LDS/STS instead of generic accesses
+  int16_t* bins = (SMEM || args.plan.bins_smem) ? reinterpret_cast<int16_t*>(smem + args.plan.off_bins) : args.tables.bin_work + fc;
+  uint8_t* edge = (SMEM || args.plan.bins_smem) ? reinterpret_cast<uint8_t*>(smem + args.plan.off_edge) : args.tables.edge + fc;
+  int32_t* list = (SMEM || args.plan.list_smem) ? reinterpret_cast<int32_t*>(smem + args.plan.off_list) : args.tables.queue + fc;
   // members of each bin (cell ids, grouped by initial bin) and their MSE, in the same order
-  int32_t* members = args.plan.members_smem
-                         ? reinterpret_cast<int32_t*>(smem + args.plan.off_members)
-                         : reinterpret_cast<int32_t*>(args.tables.pairs + 2LL * frame * C);
-  float* msem = args.plan.members_smem ? reinterpret_cast<float*>(smem + args.plan.off_msem)
-                                       : reinterpret_cast<float*>(args.tables.pairs + 2LL * frame * C + C);
+  int32_t* members = (SMEM || args.plan.members_smem) ? reinterpret_cast<int32_t*>(smem + args.plan.off_members)
+                                            : reinterpret_cast<int32_t*>(args.tables.pairs + 2 * fc);
+  float* msem = (SMEM || args.plan.members_smem) ? reinterpret_cast<float*>(smem + args.plan.off_msem)
+                                       : reinterpret_cast<float*>(args.tables.pairs + 2 * fc + C);
+  int32_t* merge = (SMEM || args.plan.merge_smem) ? reinterpret_cast<int32_t*>(smem + args.plan.off_merge)
+                                        : args.tables.merge + static_cast<long long>(frame) * g.plane_cap;
 
-  const float4* rec_a = args.tables.rec_a + 2LL * frame * C;
-  const float4* rec_b4 = args.tables.rec_b + 3LL * frame * C;
-  const int16_t* bin_in = args.tables.bin + static_cast<long long>(frame) * C;
-  int32_t* seg_label = args.tables.seg_label + static_cast<long long>(frame) * C;
-  int32_t* cell_label = args.tables.cell_label + static_cast<long long>(frame) * C;
-  uint32_t* pairs = args.tables.pairs + 2LL * frame * C;
+  const float4* rec_b4 = args.tables.rec_b + 3 * fc;
+  const int16_t* bin_in = args.tables.bin + fc;
+  const uint8_t* edge_in = args.tables.edge + fc;
+  const float* mse_g = args.tables.mse + fc;
+  int32_t* seg_label = args.tables.seg_label + fc;
+  int32_t* cell_label = args.tables.cell_label + fc;
   float* segs = args.tables.segs + static_cast<long long>(frame) * g.plane_cap * kSegFloats;
-  int32_t* merge = args.tables.merge + static_cast<long long>(frame) * g.plane_cap;
+  int32_t* merge_out = args.tables.merge + static_cast<long long>(frame) * g.plane_cap;
+
+  const bool prof = args.prof != nullptr;
+  const long long t_kernel0 = prof ? clock64() : 0;
 
   // ---- histogram of planar-cell bins (normals_histogram.cpp:21-49; bins come from stage 1) --------
   for (int i = lane; i < B2; i += 32) hist[i] = 0;
   __syncwarp();
   int remaining = 0;
-  for (int c0 = 0; c0 < C; c0 += 128) {
-    int b[4];
+  float* mse_tmp = reinterpret_cast<float*>(list);  // per-cell MSE parked in the (still unused) cell list
+  for (int c0 = 0; c0 < C; c0 += 256) {
+    int b[8];
+    float m[8];
+    unsigned ed[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 8; ++k) {
       const int c = c0 + 32 * k + lane;
-      b[k] = (c < C) ? static_cast<int>(__ldg(bin_in + c)) : -2;
+      const bool in = c < C;
+      b[k] = in ? static_cast<int>(__ldg(bin_in + c)) : -2;
+      m[k] = in ? __ldg(mse_g + c) : 0.f;
+      ed[k] = in ? static_cast<unsigned>(__ldg(edge_in + c)) : 0u;
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 8; ++k) {
       const int c = c0 + 32 * k + lane;
       if (b[k] == -2) continue;
       bins[c] = static_cast<int16_t>(b[k]);
+      if (SMEM || args.plan.bins_smem) edge[c] = static_cast<uint8_t>(ed[k]);
+      mse_tmp[c] = m[k];
       seg_label[c] = 0;
       if (b[k] >= 0) {
         atomicAdd(&hist[b[k]], 1);
@@ -157,88 +208,96 @@ __global__ void __launch_bounds__(32) region_grow_kernel(const RegionArgs args) 
       const int b = lane * per + i;
       if (b < B2) {
         bin_off[b] = run;
-        cursor[b] = run;
+        run_end[b] = run;
         run += hist[b];
       }
     }
     if (lane == 31) bin_off[B2] = incl;
   }
   __syncwarp();
-  for (int c0 = 0; c0 < C; c0 += 128) {
-    float m[4];
-    int b[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = c0 + 32 * k + lane;
-      b[k] = (c < C) ? static_cast<int>(bins[c]) : -1;
-      m[k] = (b[k] >= 0) ? __ldg(mse_g + c) : 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const int b = bins[c];
+    if (b >= 0) {
+      const int pos = atomicAdd(&run_end[b], 1);
+      members[pos] = c;
+      msem[pos] = mse_tmp[c];
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (b[k] < 0) continue;
-      const int pos = atomicAdd(&cursor[b[k]], 1);
-      members[pos] = c0 + 32 * k + lane;
-      msem[pos] = m[k];
-    }
-  }
-  // warm L1 with this frame's BFS records (32 B per cell, read-only in this kernel)
-  {
-    const char* base = reinterpret_cast<const char*>(rec_a);
-    const int lines = (C * 32 + 127) / 128;
-    for (int i = lane; i < lines; i += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + 128LL * i));
   }
   __syncwarp();
 
   const double min_cos = static_cast<double>(th.min_cos_angle_merge);
-  // exact u / nh for u * nh < 2^32 (u < n_cells)
-  const unsigned nh_magic = static_cast<unsigned>((0x100000000ull + nh - 1) / nh);
   const int cell_pts = g.patch * g.patch;
   int n_regions = 0;  // grown regions with enough cells, in seed order
   int list_off = 0;   // their cells are stored back to back in `list`
+  const int slot = lane & 3;
+  const int delta = (slot == 0) ? -nh : (slot == 1) ? nh : (slot == 2) ? -1 : 1;
+
+  long long t_seed = 0, t_bfs = 0, t_acc = 0, t_mark = 0;
+  int n_seeds = 0, n_steps = 0;
+  const long long t_init = prof ? clock64() - t_kernel0 : 0;
 
   // ---- createPlaneSegments, sequential part (plane_extractor.cpp:302-331) -------------------------
   while (remaining > 0) {
+    if (prof) t_mark = clock64();
     // most frequent bin, first maximum (normals_histogram.cpp:54-56)
-    int bc = -1, bi = kNoSeed;
-    for (int i = lane; i < B2; i += 32) {
-      const int h = hist[i];
-      if (h > bc) { bc = h; bi = i; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const int oc = __shfl_xor_sync(kFull, bc, o), oi = __shfl_xor_sync(kFull, bi, o);
-      if (oc > bc || (oc == bc && oi < bi)) { bc = oc; bi = oi; }
-    }
+    // key = count << 15 | (0x7fff - bin): the maximum key is the largest count with the smallest bin id
+    // (count <= n_cells < 2^17 and bin < 2^15 are enforced at create)
+    unsigned key = 0;
+#pragma unroll 4
+    for (int i = lane; i < B2; i += 32) key = max(key, (static_cast<unsigned>(hist[i]) << 15) | (0x7fffu - i));
+    key = __reduce_max_sync(kFull, key);
+    const int bc = static_cast<int>(key >> 15), bi = static_cast<int>(0x7fffu - (key & 0x7fffu));
     const unsigned long long n_cand = bc > 0 ? static_cast<unsigned long long>(bc) : 0ull;
     if (n_cand < th.min_candidate_size) break;  // plane_extractor.cpp:305-307
 
     // seed = first strict minimum of the MSE among the bin's cells (plane_extractor.cpp:309-316);
-    // float -> double is monotonic, so the comparison against (double)INT_MAX is done once at the end
+    // float -> double is monotonic, so the comparison against (double)INT_MAX is done once at the end.
+    // The scan also compacts the bin's member run down to the cells that are still unassigned.
     float lm = __int_as_float(0x7f800000);  // +inf
     int seed = kNoSeed;
     {
-      const int end = bin_off[bi + 1];
-      for (int i = bin_off[bi] + lane; i < end; i += 32) {
-        const int c = members[i];
-        if (bins[c] == bi) {  // still unassigned
-          const float m = msem[i];
-          if (m < lm || (m == lm && c < seed)) { lm = m; seed = c; }
+      const int start = bin_off[bi], end = run_end[bi];
+      int w = start;
+      for (int i0 = start; i0 < end; i0 += 32) {
+        const int i = i0 + lane;
+        const bool in = i < end;
+        const int c = in ? members[i] : 0;
+        const float m = in ? msem[i] : 0.f;
+        const bool alive = in && bins[c] == bi;
+        if (alive && (m < lm || (m == lm && c < seed))) { lm = m; seed = c; }
+        const unsigned am = __ballot_sync(kFull, alive);
+        if (alive) {
+          const int pos = w + __popc(am & ((1u << lane) - 1u));
+          members[pos] = c;
+          msem[pos] = m;
         }
+        w += __popc(am);
+        __syncwarp();
       }
+      if (lane == 0) run_end[bi] = w;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float om = __shfl_xor_sync(kFull, lm, o);
-      const int os = __shfl_xor_sync(kFull, seed, o);
-      if (os != kNoSeed && (seed == kNoSeed || om < lm || (om == lm && os < seed))) { lm = om; seed = os; }
+    {
+      // lexicographic minimum of (mse, cell id) over the lanes: two integer warp reductions on the
+      // order-preserving integer image of the float
+      const unsigned fb = __float_as_uint(lm);
+      const unsigned ord = fb ^ ((fb >> 31) ? 0xffffffffu : 0x80000000u);
+      const unsigned best = __reduce_min_sync(kFull, seed == kNoSeed ? 0xffffffffu : ord);
+      const unsigned cand = (seed != kNoSeed && ord == best) ? static_cast<unsigned>(seed) : static_cast<unsigned>(kNoSeed);
+      seed = static_cast<int>(__reduce_min_sync(kFull, cand));
+      const unsigned bb = best ^ ((best >> 31) ? 0x80000000u : 0xffffffffu);
+      lm = __uint_as_float(bb);
     }
     // no candidate with mse < INT_MAX: the reference reads an uninitialised seed id here
     if (seed == kNoSeed || !(static_cast<double>(lm) < 2147483647.0)) break;
 
-    // growSeed (plane_extractor.cpp:349-392): batched FIFO BFS into list[list_off ...)
+    if (prof) { const long long t = clock64(); t_seed += t - t_mark; t_mark = t; ++n_seeds; }
+    // growSeed (plane_extractor.cpp:349-392): batched FIFO BFS into list[list_off ...).  Edge tests were
+    // precomputed (edge_mask_kernel); a neighbour is taken if its edge bit is set and it is still unassigned.
+    // Queue entries carry the cell id in the low 24 bits and the cell's edge mask in the high 8, so a pop
+    // costs one shared-memory read; a lane's neighbour is v = u + delta(slot) whenever its edge bit is set.
     int32_t* q = list + list_off;
     if (lane == 0) {
-      q[0] = seed;
+      q[0] = seed | (static_cast<int>(edge[seed]) << 24);
       bins[seed] = -1;
       hist[bi] -= 1;
     }
@@ -246,74 +305,81 @@ __global__ void __launch_bounds__(32) region_grow_kernel(const RegionArgs args) 
     int head = 0, tail = 1;
     while (head < tail) {
       const int nb = min(8, tail - head);
-      const int e = lane >> 2, s = lane & 3;
-      int v = -1, u = -1;
-      if (e < nb) {
-        u = q[head + e];
-        const int r = static_cast<int>(__umulhi(static_cast<unsigned>(u), nh_magic)), qc = u - r * nh;
-        if (s == 0) v = (r >= 1) ? u - nh : -1;
-        else if (s == 1) v = (r + 1 < nv) ? u + nh : -1;
-        else if (s == 2) v = (qc >= 1) ? u - 1 : -1;
-        else v = (qc + 1 < nh) ? u + 1 : -1;
-      }
-      bool pass = false;
-      int vb = -1;
-      if (v >= 0) {
-        vb = bins[v];
-        if (vb >= 0) {  // unassigned and not yet activated
-          const float4 nu = __ldg(rec_a + 2 * u);
-          const float4 nvv = __ldg(rec_a + 2 * v);
-          const float4 mv = __ldg(rec_a + 2 * v + 1);
-          const double cos_angle = static_cast<double>(dot3(nu.x, nu.y, nu.z, nvv.x, nvv.y, nvv.z));
-          const double t = __dadd_rn(static_cast<double>(dot3(nu.x, nu.y, nu.z, mv.x, mv.y, mv.z)),
-                                     static_cast<double>(nu.w));
-          const double merge_dist = __dmul_rn(t, t);
-          pass = cos_angle >= min_cos && merge_dist <= static_cast<double>(mv.w);
+      int v = 0, vb = -1;
+      unsigned ev = 0;
+      if ((lane >> 2) < nb) {
+        const unsigned pk = static_cast<unsigned>(q[head + (lane >> 2)]);
+        if ((pk >> (24 + slot)) & 1u) {
+          v = static_cast<int>(pk & 0xffffffu) + delta;
+          vb = bins[v];
+          ev = edge[v];
         }
       }
+      const bool pass = vb >= 0;  // edge test passed, still unassigned, not yet activated
       const unsigned pm = __ballot_sync(kFull, pass);
+      unsigned wm = 0;
       if (pm) {
-        bool win = false;
-        if (pass) {
+        // a cell reached by several lanes goes to the lowest one (= the earliest in FIFO order); conflicts
+        // need at least two passing lanes from different queue entries
+        bool win = pass;
+        // (lanes of one queue entry have distinct targets: only passing lanes of different entries can clash)
+        const unsigned lo = pm & (0u - pm);                       // lowest passing lane
+        const unsigned same_entry = (lo | (lo << 1) | (lo << 2) | (lo << 3)) | (0xfu << ((__ffs(pm) - 1) & ~3));
+        if (pass && (pm & ~same_entry)) {
           const unsigned grp = __match_any_sync(pm, v);
           win = (__ffs(grp) - 1) == lane;
         }
-        const unsigned wm = __ballot_sync(kFull, win);
+        wm = __ballot_sync(kFull, win);
         if (win) {
-          q[tail + __popc(wm & ((1u << lane) - 1u))] = v;
+          q[tail + __popc(wm & ((1u << lane) - 1u))] = v | static_cast<int>(ev << 24);
           bins[v] = -1;             // removePoint + unassigned_mask[v] = false (plane_extractor.cpp:324-325)
           atomicSub(&hist[vb], 1);
         }
-        tail += __popc(wm);
       }
+      tail += __popc(wm);
       head += nb;
+      ++n_steps;
       __syncwarp();
     }
+    // strip the edge masks: the list keeps plain cell ids for the later phases
+    for (int i = lane; i < tail; i += 32) q[i] &= 0xffffff;
+    __syncwarp();
     remaining -= tail;
+    if (prof) { const long long t = clock64(); t_bfs += t - t_mark; t_mark = t; }
     if (static_cast<unsigned long long>(tail) < th.min_cells_activated) continue;  // plane_extractor.cpp:329-331
 
     // merge the activated cells into the candidate, seed first and twice (plane_extractor.cpp:318-323):
     // 32 cell records per round trip, staged through shared memory, then 9 sequential fp32 chains
     float acc = 0.f;
     if (lane < 9) acc = reinterpret_cast<const float*>(rec_b4)[12 * seed + lane];
-    float4 r0, r1, r2;
-    {
-      const int c = q[min(lane, tail - 1)];
-      r0 = __ldg(rec_b4 + 3 * c); r1 = __ldg(rec_b4 + 3 * c + 1); r2 = __ldg(rec_b4 + 3 * c + 2);
-    }
+    // records are fetched two chunks (64 cells) ahead of the additions
+    float4 ra[3], rb[3];
+    auto fetch = [&](int i0, float4 (&r)[3]) {
+      if (i0 < tail) {
+        const int c = q[min(i0 + lane, tail - 1)];
+        r[0] = __ldg(rec_b4 + 3 * c); r[1] = __ldg(rec_b4 + 3 * c + 1); r[2] = __ldg(rec_b4 + 3 * c + 2);
+      }
+    };
+    fetch(0, ra);
+    fetch(32, rb);
     for (int i0 = 0; i0 < tail; i0 += 32) {
       const int cnt = min(32, tail - i0);
       float4* st4 = reinterpret_cast<float4*>(stage + 12 * lane);
-      st4[0] = r0; st4[1] = r1; st4[2] = r2;
-      if (i0 + 32 < tail) {  // prefetch the next 32 records while this chunk is summed
-        const int c = q[min(i0 + 32 + lane, tail - 1)];
-        r0 = __ldg(rec_b4 + 3 * c); r1 = __ldg(rec_b4 + 3 * c + 1); r2 = __ldg(rec_b4 + 3 * c + 2);
+      st4[0] = ra[0]; st4[1] = ra[1]; st4[2] = ra[2];
+      ra[0] = rb[0]; ra[1] = rb[1]; ra[2] = rb[2];
+      fetch(i0 + 64, rb);
+      __syncwarp();
+      if (lane < 9) {
+        if (cnt == 32) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) acc = __fadd_rn(acc, stage[12 * k + lane]);
+        } else {
+          for (int k = 0; k < cnt; ++k) acc = __fadd_rn(acc, stage[12 * k + lane]);
+        }
       }
       __syncwarp();
-      if (lane < 9)
-        for (int k = 0; k < cnt; ++k) acc = __fadd_rn(acc, stage[12 * k + lane]);
-      __syncwarp();
     }
+    if (prof) t_acc += clock64() - t_mark;
     if (n_regions < g.plane_cap) {
       float* rec = segs + static_cast<long long>(n_regions) * kSegFloats;
       if (lane < 9) __stcg(rec + kSegS + lane, acc);
@@ -327,6 +393,12 @@ __global__ void __launch_bounds__(32) region_grow_kernel(const RegionArgs args) 
   }
   __syncwarp();
 
+  // growing is over: the bins array now becomes the per-cell segment label (labels_map_), all zero
+  uint16_t* segl = reinterpret_cast<uint16_t*>(bins);
+  for (int c = lane; c < C; c += 32) segl[c] = 0;
+  __syncwarp();
+
+  const long long t_grow_end = prof ? clock64() : 0;
   // ---- plane fit of every grown region, one lane per region (plane_extractor.cpp:333-343) ---------
   int nseg = 0;
   for (int base = 0; base < n_regions; base += 32) {
@@ -354,15 +426,22 @@ __global__ void __launch_bounds__(32) region_grow_kernel(const RegionArgs args) 
       todo &= todo - 1;
       const int o = __shfl_sync(kFull, off, src), n = __shfl_sync(kFull, cnt, src);
       const int label = __shfl_sync(kFull, id, src) + 1;
-      for (int i = lane; i < n; i += 32) seg_label[list[o + i]] = label;
+      for (int i = lane; i < n; i += 32) {
+        const int c = list[o + i];
+        segl[c] = static_cast<uint16_t>(label);
+        seg_label[c] = label;
+      }
     }
     nseg += __popc(am);
     __syncwarp();
   }
   if (lane == 0) args.tables.n_planes[frame] = nseg;
+  const long long t_fit_end = prof ? clock64() : 0;
   __syncwarp();
 
   // ---- getConnectedComponents (plane_extractor.cpp:430-453): boundary pairs, last row/column skipped ----
+  // (the pair list reuses the member runs' storage: 2*C words, free once growing is over)
+  uint32_t* pairs = reinterpret_cast<uint32_t*>(members);
   int n_pairs = 0;
   if (nseg > 1) {
     const int limit = (nv - 1) * nh;
@@ -371,22 +450,22 @@ __global__ void __launch_bounds__(32) region_grow_kernel(const RegionArgs args) 
       unsigned p0 = 0xffffffffu, p1 = 0xffffffffu;
       if (c < limit) {
         const int qc = c % nh;
-        const int id = seg_label[c];
+        const int id = segl[c];
         if (qc < nh - 1 && id > 0) {
-          const int right = seg_label[c + 1], down = seg_label[c + nh];
+          const int right = segl[c + 1], down = segl[c + nh];
           if (right > 0 && right != id) p0 = (static_cast<unsigned>(min(id, right) - 1) << 16) | static_cast<unsigned>(max(id, right) - 1);
           if (down > 0 && down != id) p1 = (static_cast<unsigned>(min(id, down) - 1) << 16) | static_cast<unsigned>(max(id, down) - 1);
         }
       }
       const unsigned m0 = __ballot_sync(kFull, p0 != 0xffffffffu);
-      if (p0 != 0xffffffffu) __stcg(pairs + n_pairs + __popc(m0 & ((1u << lane) - 1u)), p0);
+      if (p0 != 0xffffffffu) pairs[n_pairs + __popc(m0 & ((1u << lane) - 1u))] = p0;
       n_pairs += __popc(m0);
       const unsigned m1 = __ballot_sync(kFull, p1 != 0xffffffffu);
-      if (p1 != 0xffffffffu) __stcg(pairs + n_pairs + __popc(m1 & ((1u << lane) - 1u)), p1);
+      if (p1 != 0xffffffffu) pairs[n_pairs + __popc(m1 & ((1u << lane) - 1u))] = p1;
       n_pairs += __popc(m1);
     }
   }
-  for (int i = lane; i < nseg; i += 32) __stcg(merge + i, i);
+  for (int i = lane; i < nseg; i += 32) merge[i] = i;
   __syncwarp();
 
   // ---- findMergedLabels (plane_extractor.cpp:402-423) ---------------------------------------------
@@ -396,7 +475,7 @@ __global__ void __launch_bounds__(32) region_grow_kernel(const RegionArgs args) 
     __syncwarp();
     bool any = false;
     for (int i = lane; i < n_pairs; i += 32) {
-      const unsigned pr = __ldcg(pairs + i);
+      const unsigned pr = pairs[i];
       if (static_cast<int>(pr >> 16) == r) {
         const unsigned t = pr & 0xffffu;
         atomicOr(&rowbits[t >> 5], 1u << (t & 31));
@@ -407,7 +486,7 @@ __global__ void __launch_bounds__(32) region_grow_kernel(const RegionArgs args) 
     __syncwarp();
     if (!any) continue;
 
-    const int a = __ldcg(merge + r);
+    const int a = merge[r];
     Moments ma;
     PlaneFit fa;
     load_seg(segs + static_cast<long long>(a) * kSegFloats, ma, fa);
@@ -430,7 +509,7 @@ __global__ void __launch_bounds__(32) region_grow_kernel(const RegionArgs args) 
           for (int i = 0; i < 3; ++i) ma.s[i] = __fadd_rn(ma.s[i], mt.s[i]);
 #pragma unroll
           for (int i = 0; i < 6; ++i) ma.v[i] = __fadd_rn(ma.v[i], mt.v[i]);
-          if (lane == 0) __stcg(merge + t, a);
+          if (lane == 0) merge[t] = a;
           expanded = true;
         }
       }
@@ -443,10 +522,29 @@ __global__ void __launch_bounds__(32) region_grow_kernel(const RegionArgs args) 
   }
   __syncwarp();
 
+  const long long t_merge_end = prof ? clock64() : 0;
   // ---- per-cell final labels (plane_extractor.cpp:464-465) -----------------------------------------
   for (int c = lane; c < C; c += 32) {
-    const int l = seg_label[c];
-    cell_label[c] = (l == 0) ? 0 : __ldcg(merge + l - 1) + 1;
+    const int l = segl[c];
+    cell_label[c] = (l == 0) ? 0 : merge[l - 1] + 1;
+  }
+  if (SMEM || args.plan.merge_smem)
+    for (int i = lane; i < nseg; i += 32) merge_out[i] = merge[i];
+  if (prof && lane == 0) {
+    long long* o = args.prof + static_cast<long long>(frame) * kRegionProfSlots;
+    const long long t_end = clock64();
+    o[0] = t_end - t_kernel0;          // whole frame
+    o[1] = t_init;                     // histogram + grouping + prefetch
+    o[2] = t_seed;                     // bin argmax + seed search (all seeds)
+    o[3] = t_bfs;                      // BFS (all seeds)
+    o[4] = t_acc;                      // moment accumulation (regions with enough cells)
+    o[5] = t_fit_end - t_grow_end;     // plane fits + label painting
+    o[6] = t_merge_end - t_fit_end;    // adjacency pairs + merging
+    o[7] = t_end - t_merge_end;        // final labels
+    o[8] = n_seeds;
+    o[9] = n_steps;
+    o[10] = n_regions;
+    o[11] = nseg;
   }
 }
 
@@ -467,10 +565,12 @@ RegionPlan region_grow_plan(const Geometry& g, const Thresholds& th) {
   p.off_rowbits = static_cast<int>(off);
   off = align16(off + static_cast<size_t>((g.plane_cap + 31) / 32) * 4);
   const size_t C = static_cast<size_t>(g.n_cells);
-  if (off + C * 2 <= budget) {
+  if (off + C * 3 <= budget) {  // working bins (int16) + edge masks (uint8)
     p.bins_smem = 1;
     p.off_bins = static_cast<int>(off);
     off = align16(off + C * 2);
+    p.off_edge = static_cast<int>(off);
+    off = align16(off + C);
   }
   if (off + C * 4 <= budget) {
     p.list_smem = 1;
@@ -484,14 +584,29 @@ RegionPlan region_grow_plan(const Geometry& g, const Thresholds& th) {
     p.off_msem = static_cast<int>(off);
     off = align16(off + C * 4);
   }
+  if (off + static_cast<size_t>(g.plane_cap) * 4 <= budget) {
+    p.merge_smem = 1;
+    p.off_merge = static_cast<int>(off);
+    off = align16(off + static_cast<size_t>(g.plane_cap) * 4);
+  }
   p.bytes = off;
   return p;
 }
 
 cudaError_t launch_region_grow(const RegionArgs& args, cudaStream_t stream) {
   if (args.n_frames == 0) return cudaSuccess;
-  cudaFuncSetAttribute(region_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(args.plan.bytes));
-  region_grow_kernel<<<args.n_frames, 32, args.plan.bytes, stream>>>(args);
+  const long long cells = static_cast<long long>(args.n_frames) * args.geom.n_cells;
+  edge_mask_kernel<<<static_cast<unsigned>((cells + 255) / 256), 256, 0, stream>>>(args);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const bool all_smem = args.plan.bins_smem && args.plan.list_smem && args.plan.members_smem && args.plan.merge_smem;
+  if (all_smem) {
+    cudaFuncSetAttribute(region_grow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(args.plan.bytes));
+    region_grow_kernel<true><<<args.n_frames, 32, args.plan.bytes, stream>>>(args);
+  } else {
+    cudaFuncSetAttribute(region_grow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(args.plan.bytes));
+    region_grow_kernel<false><<<args.n_frames, 32, args.plan.bytes, stream>>>(args);
+  }
   return cudaGetLastError();
 }
 

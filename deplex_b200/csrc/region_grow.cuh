@@ -6,13 +6,16 @@ namespace dpx {
 
 // Where the per-frame working set lives (shared memory when it fits, else the global scratch tables).
 struct RegionPlan {
-  int bins_smem, list_smem, members_smem;
-  int off_hist, off_binoff, off_cursor, off_rowbits, off_bins, off_list, off_members, off_msem;
+  int bins_smem, list_smem, members_smem, merge_smem;
+  int off_hist, off_binoff, off_cursor, off_rowbits, off_bins, off_edge, off_list, off_members, off_msem, off_merge;
   size_t bytes;  // dynamic shared memory per CTA
 };
 
+constexpr int kRegionProfSlots = 12;
+
 struct RegionArgs {
   int n_frames;
+  long long* prof;  // optional [F][kRegionProfSlots] per-phase cycle counters, or nullptr
   RegionPlan plan;
   Geometry geom;
   Thresholds thr;

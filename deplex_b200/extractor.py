@@ -202,5 +202,13 @@ class PlaneExtractor:
         self._check(self._lib.dpx_get_stage_ms(self._h, C.byref(ms)))
         return dict(zip(_capi.STAGE_NAMES, [float(x) for x in ms]))
 
+    def region_profile(self, frame=0):
+        """Cycle counters of the region-growing stage for one frame of the last profiled batch."""
+        buf = (C.c_int64 * 12)()
+        self._check(self._lib.dpx_get_region_profile(self._h, frame, C.byref(buf)))
+        names = ("total", "init", "seed", "bfs", "accumulate", "fit", "merge", "final", "n_seeds", "n_steps",
+                 "n_regions", "n_segments")
+        return dict(zip(names, [int(x) for x in buf]))
+
     def kernel_launches(self):
         return int(self._lib.dpx_kernel_launches(self._h))
