@@ -323,8 +323,7 @@ __global__ void __launch_bounds__(32) region_grow_kernel(const RegionArgs args) 
         // need at least two passing lanes from different queue entries
         bool win = pass;
         // (lanes of one queue entry have distinct targets: only passing lanes of different entries can clash)
-        const unsigned lo = pm & (0u - pm);                       // lowest passing lane
-        const unsigned same_entry = (lo | (lo << 1) | (lo << 2) | (lo << 3)) | (0xfu << ((__ffs(pm) - 1) & ~3));
+        const unsigned same_entry = 0xfu << ((__ffs(pm) - 1) & ~3);  // the 4 lanes of the lowest passing entry
         if (pass && (pm & ~same_entry)) {
           const unsigned grp = __match_any_sync(pm, v);
           win = (__ffs(grp) - 1) == lane;
