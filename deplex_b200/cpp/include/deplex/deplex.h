@@ -1,0 +1,4 @@
+#pragma once
+#include "deplex/config.h"
+#include "deplex/plane_extractor.h"
+#include "deplex/utils/utils.h"

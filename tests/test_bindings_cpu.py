@@ -1,0 +1,103 @@
+"""Host-side checks of the C++ drop-in layer and the pybind module `deplex.pybind` (no GPU needed).
+
+Reference surface: cpp/pybind/deplex_pybind.cpp:20-24, plane_extraction/plane_extraction.cpp:28-37,
+utils/utils.cpp:29-36, python/deplex/__init__.py:1-2; tests: cpp/tests/test_config.cpp:24-29,
+cpp/tests/test_depth_image.cpp:24-48."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, load_frame
+
+PYPKG = os.path.join(ROOT, "deplex_b200", "python")
+
+
+@pytest.fixture(scope="module")
+def deplex_mod(lib_built):
+    if PYPKG not in sys.path:
+        sys.path.insert(0, PYPKG)
+    try:
+        import deplex
+    except ImportError:
+        import __graft_entry__
+        __graft_entry__.build()
+        import deplex
+    return deplex
+
+
+def test_module_layout_matches_reference(deplex_mod):
+    import deplex.pybind as pb
+    assert hasattr(pb, "plane_extraction") and hasattr(pb, "utils")
+    assert deplex_mod.PlaneExtractor is pb.plane_extraction.PlaneExtractor
+    assert deplex_mod.Config is pb.plane_extraction.Config
+    assert deplex_mod.utils.DepthImage is pb.utils.DepthImage
+    # the extension links the in-tree CUDA library, not a copy of it
+    maps = open("/proc/self/maps").read()
+    assert os.path.join(ROOT, "deplex_b200", "libdeplex_b200.so") in maps
+
+
+def test_config_from_ini(deplex_mod, capfd):
+    c = deplex_mod.Config(path=os.path.join(GOLDEN, "MissingParameters.ini"))
+    d = deplex_mod.Config(os.path.join(GOLDEN, "TUM_fr3_long_val.ini"))
+    assert c.patch_size == 12 and d.patch_size == 10
+    # ';'-commented and unknown keys leave the defaults and are reported on stderr (config.cpp:77)
+    assert c.depth_sigma_coeff == pytest.approx(1.425e-6) and c.max_merge_dist == 500 and c.min_pts_per_cell == 3
+    assert "Unknown parameter name: ;maxMergeDist" in capfd.readouterr().err
+    with pytest.raises(RuntimeError, match="Couldn't open ini file: __INVALID_PATH"):
+        deplex_mod.Config("__INVALID_PATH")
+
+
+def test_depth_image_png16_and_backprojection(deplex_mod, tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    from deplex_b200 import synth
+    for name in ("tum", "icl"):
+        depth, k, _ = load_frame(name)
+        path = str(tmp_path / f"{name}.png")
+        assert cv2.imwrite(path, depth)
+        img = deplex_mod.utils.DepthImage(path)
+        assert (img.height, img.width) == (480, 640)
+        K = np.array([[k["fx"], 0, k["cx"]], [0, k["fy"], k["cy"]], [0, 0, 1]])
+        pts = img.transform_to_pcd(K)
+        assert pts.shape == (480 * 640, 3) and pts.dtype == np.float32
+        assert np.array_equal(pts[:, 2], depth.reshape(-1).astype(np.float32))
+        want = synth.depth_to_cloud(depth, k, "rowmajor")
+        assert np.array_equal(pts.view(np.uint32), want.view(np.uint32))
+    # cpp/tests/test_depth_image.cpp:42-48: z range of the TUM frame
+    depth, k, _ = load_frame("tum")
+    assert depth.max() == 46655 and depth.min() == 0
+
+
+def test_depth_image_other_png_flavours(deplex_mod, tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    g8 = rng.integers(0, 256, (37, 53), dtype=np.uint8)
+    cv2.imwrite(str(tmp_path / "g8.png"), g8)
+    img = deplex_mod.utils.DepthImage(str(tmp_path / "g8.png"))
+    z = img.transform_to_pcd(np.eye(3))[:, 2].reshape(37, 53)
+    assert np.array_equal(z, g8.astype(np.float32) * 257)  # 8-bit samples widen as v * 257 (stb_image)
+    rgb16 = rng.integers(0, 65536, (21, 34, 3), dtype=np.uint16)
+    cv2.imwrite(str(tmp_path / "rgb16.png"), rgb16[:, :, ::-1])  # cv2 writes BGR
+    img.reset(str(tmp_path / "rgb16.png"))
+    z = img.transform_to_pcd(np.eye(3))[:, 2].reshape(21, 34)
+    r, g, b = (rgb16[:, :, i].astype(np.uint32) for i in range(3))
+    assert np.array_equal(z, ((r * 77 + g * 150 + b * 29) >> 8).astype(np.float32))
+    # invalid / empty files throw (cpp/tests/test_depth_image.cpp:30-40)
+    (tmp_path / "empty.png").write_bytes(b"")
+    for bad in ("empty.png", "missing.png"):
+        with pytest.raises(RuntimeError, match="Error: Couldn't read image"):
+            deplex_mod.utils.DepthImage(str(tmp_path / bad))
+
+
+def test_no_cpu_fallback_through_the_bindings(deplex_mod):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no usable CUDA device"):
+        deplex_mod.PlaneExtractor(image_height=480, image_width=640)
+
+
+def test_cpp_binaries_built(lib_built):
+    for exe in ("process_cloud", "test_api"):
+        assert os.access(os.path.join(ROOT, "deplex_b200", "cpp", "build", exe), os.X_OK)
