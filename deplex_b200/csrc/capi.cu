@@ -36,7 +36,7 @@ struct dpx_extractor {
   Tables tb;
   int device = 0, max_batch = 0, sm_count = 0;
   int tile_cells = 0;
-  int stream_warps = 12;      // env DPX_STREAM_WARPS=8|12
+  int stream_warps = 16;      // env DPX_STREAM_WARPS=8|12|16 (A/B measurement)
   int force_tile_kernel = 0;  // env DPX_CELL_KERNEL=tile (A/B measurement of the two stage-1 kernels)
   RegionPlan plan{};
   long long* region_prof = nullptr;  // [max_batch][kRegionProfSlots], written while profiling is on
@@ -282,7 +282,7 @@ dpx_status dpx_create(int32_t height, int32_t width, const dpx_config* cfg_in, i
   ex->sm_count = prop.multiProcessorCount;
   if (g.n_cells > 0) {
     ex->tile_cells = cell_stats_tile_cells(g.patch, g.nh);
-    if (const char* e = std::getenv("DPX_STREAM_WARPS")) ex->stream_warps = std::atoi(e) == 8 ? 8 : 12;
+    if (const char* e = std::getenv("DPX_STREAM_WARPS")) { const int w = std::atoi(e); ex->stream_warps = (w == 8 || w == 12) ? w : 16; }
     if (const char* e = std::getenv("DPX_CELL_KERNEL")) ex->force_tile_kernel = std::strcmp(e, "tile") == 0;
     ex->plan = region_grow_plan(g, th);
     Tables probe{};

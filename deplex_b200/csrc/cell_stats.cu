@@ -30,7 +30,10 @@
 // Algorithmic bytes: 12 B/pixel read once; <= 87 B/cell written.
 #include "cell_stats.cuh"
 
+#include <type_traits>
+
 #include "cell_walk.cuh"
+#include "cell_walk_packed.cuh"
 
 namespace dpx {
 namespace {
@@ -127,7 +130,6 @@ __global__ void __launch_bounds__(kCellStatsThreads) cell_stats_tile_kernel(cons
 // ---------------------------------------------------------------------------------------------------
 // Fast path: persistent, warp-private TMA-bulk row pipeline.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kRing = 4;  // slots per warp
 
 // rows staged per slot: the largest divisor of P whose slot stays <= 4 KB (else one row)
 __host__ __device__ constexpr int rows_per_slot(int P) {
@@ -178,106 +180,139 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
       : "memory");
 }
 
-template <int LAYOUT, int P, int WARPS>
+// scalar walk behind the same row-at-a-time interface (odd patch sizes)
+template <int LAYOUT, int P>
+struct CellWalkScalar {
+  CellWalk<P> w;
+  __device__ __forceinline__ void reset() { w.reset(); }
+  __device__ __forceinline__ void row(int i, const float* blk, int tw, int rows, int rr, int t, float disc_thr) {
+    float x[P], y[P], z[P];
+    load_cell_row<LAYOUT, P>(blk, tw, rows, rr, t, x, y, z);
+    w.row(i, x, y, z, disc_thr);
+  }
+  __device__ __forceinline__ void finish(CellRaw& out) const { w.finish(out); }
+};
+
+template <int LAYOUT, int P>
+struct WalkFor {
+  using type = typename std::conditional<P % 2 == 0, CellWalkPacked<LAYOUT, P>, CellWalkScalar<LAYOUT, P>>::type;
+};
+
+// where a warp's tile starts in the input, and where its cells go
+struct TileDesc {
+  const float* src;     // first point of the tile's first row (component 0 for column-major input)
+  long long cell0;      // frame * n_cells + strip * nh + c0
+  unsigned seg_bytes;   // bytes of one component of one row segment (cnt * P * 4)
+  int cnt;              // cells in the tile (32, fewer at the right edge); 0 = past the end
+};
+
+template <int LAYOUT, int P, int WARPS, int RING>
 __global__ void __launch_bounds__(WARPS * 32, 1) cell_stats_stream_kernel(const CellStatsArgs args) {
-  constexpr int kStreamWarps = WARPS;
   constexpr int RPS = rows_per_slot(P);
   constexpr int SPT = P / RPS;               // stages (slots) per tile
   constexpr int TW = 32 * P;                 // points per staged row
   constexpr int SLOT_FLOATS = RPS * TW * 3;
   extern __shared__ float4 smem_f4[];
-  __shared__ __align__(8) uint64_t bars[kStreamWarps * kRing];
+  __shared__ __align__(8) uint64_t bars[WARPS * RING];
 
   const Geometry& g = args.geom;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* ring = reinterpret_cast<float*>(smem_f4) + static_cast<size_t>(warp) * kRing * SLOT_FLOATS;
-  uint64_t* bar = bars + warp * kRing;
+  float* ring = reinterpret_cast<float*>(smem_f4) + static_cast<size_t>(warp) * RING * SLOT_FLOATS;
+  uint64_t* bar = bars + warp * RING;
 
   if (lane == 0) {
 #pragma unroll
-    for (int s = 0; s < kRing; ++s) mbar_init(bar + s, 1);
+    for (int s = 0; s < RING; ++s) mbar_init(bar + s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
 
   const uint64_t policy = l2_evict_first_policy();
   const long long total_tiles = static_cast<long long>(args.n_frames) * g.nv * args.tiles_per_strip;
-  const long long gw = static_cast<long long>(blockIdx.x) * kStreamWarps + warp;
-  const long long total_warps = static_cast<long long>(gridDim.x) * kStreamWarps;
+  const long long gw = static_cast<long long>(blockIdx.x) * WARPS + warp;
+  const long long total_warps = static_cast<long long>(gridDim.x) * WARPS;
   if (gw >= total_tiles) return;
   const long long my_tiles = (total_tiles - gw + total_warps - 1) / total_warps;
-  const long long total_stages = my_tiles * SPT;
+  const long long row_stride = (LAYOUT == kLayoutRowMajor) ? 3LL * g.width : g.width;  // floats between image rows
 
-  // lane 0: arm the slot's mbarrier and issue the bulk copies of stage q (global stage index of this warp)
-  auto issue = [&](long long q) {
-    if (q >= total_stages || lane != 0) return;
-    const long long n = q / SPT;
-    const int st = static_cast<int>(q - n * SPT);
+  // tile n of this warp (the divisions run once per tile, not once per stage)
+  auto locate = [&](long long n, TileDesc& d) {
+    if (n >= my_tiles) {
+      d.cnt = 0;
+      return;
+    }
     long long tile = gw + n * total_warps;
     const int tix = static_cast<int>(tile % args.tiles_per_strip);
     tile /= args.tiles_per_strip;
     const int strip = static_cast<int>(tile % g.nv);
     const long long frame = tile / g.nv;
     const int c0 = tix * 32;
-    const int cnt = min(32, g.nh - c0);
-    const unsigned seg_bytes = static_cast<unsigned>(cnt) * P * 4;  // one component of one row segment
-    const int slot = static_cast<int>(q % kRing);
+    d.cnt = min(32, g.nh - c0);
+    d.seg_bytes = static_cast<unsigned>(d.cnt) * P * 4;
+    d.cell0 = frame * g.n_cells + static_cast<long long>(strip) * g.nh + c0;
+    const long long px0 = static_cast<long long>(strip) * P * g.width + static_cast<long long>(c0) * P;
+    d.src = args.xyz + frame * 3 * g.n_points + (LAYOUT == kLayoutRowMajor ? 3 * px0 : px0);
+  };
+  // lane 0: arm the slot's mbarrier and issue the bulk copies of stage `st` of tile `d`
+  auto issue = [&](const TileDesc& d, int st, int slot) {
+    if (d.cnt == 0 || lane != 0) return;
     float* dst = ring + slot * SLOT_FLOATS;
-    const float* src = args.xyz + frame * 3 * g.n_points;
-    const long long row0 = (static_cast<long long>(strip) * P + st * RPS) * g.width + static_cast<long long>(c0) * P;
-    mbar_expect_tx(bar + slot, seg_bytes * 3 * RPS);
+    const float* src = d.src + static_cast<long long>(st) * RPS * row_stride;
+    mbar_expect_tx(bar + slot, d.seg_bytes * 3 * RPS);
     if (LAYOUT == kLayoutRowMajor) {
 #pragma unroll
-      for (int rr = 0; rr < RPS; ++rr)
-        bulk_g2s(dst + rr * TW * 3, src + (row0 + static_cast<long long>(rr) * g.width) * 3, seg_bytes * 3, bar + slot,
-                 policy);
+      for (int rr = 0; rr < RPS; ++rr) bulk_g2s(dst + rr * TW * 3, src + rr * row_stride, d.seg_bytes * 3, bar + slot, policy);
     } else {
 #pragma unroll
       for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int rr = 0; rr < RPS; ++rr)
-          bulk_g2s(dst + (a * RPS + rr) * TW, src + a * g.n_points + row0 + static_cast<long long>(rr) * g.width, seg_bytes,
-                   bar + slot, policy);
+          bulk_g2s(dst + (a * RPS + rr) * TW, src + a * g.n_points + rr * row_stride, d.seg_bytes, bar + slot, policy);
     }
   };
 
+  // the issue cursor runs RING stages ahead of the consumer
+  TileDesc cur, ahead;
+  locate(0, cur);
+  ahead = cur;
+  long long ahead_n = 0;
+  int ahead_st = 0;
+  auto issue_next = [&](int slot) {
+    issue(ahead, ahead_st, slot);
+    if (++ahead_st == SPT) {
+      ahead_st = 0;
+      locate(++ahead_n, ahead);
+    }
+  };
 #pragma unroll
-  for (int s = 0; s < kRing; ++s) issue(s);
+  for (int s = 0; s < RING; ++s) issue_next(s);
 
-  long long q = 0;
+  int slot = 0;
+  unsigned phase = 0;
   for (long long n = 0; n < my_tiles; ++n) {
-    long long tile = gw + n * total_warps;
-    const int tix = static_cast<int>(tile % args.tiles_per_strip);
-    tile /= args.tiles_per_strip;
-    const int strip = static_cast<int>(tile % g.nv);
-    const long long frame = tile / g.nv;
-    const int c0 = tix * 32;
-    const int cnt = min(32, g.nh - c0);
-
-    CellWalk<P> walk;
+    typename WalkFor<LAYOUT, P>::type walk;
     walk.reset();
 #pragma unroll
-    for (int st = 0; st < SPT; ++st, ++q) {
-      const int slot = static_cast<int>(q % kRing);
-      mbar_wait(bar + slot, static_cast<unsigned>((q / kRing) & 1));
+    for (int st = 0; st < SPT; ++st) {
+      mbar_wait(bar + slot, phase);
       const float* blk = ring + slot * SLOT_FLOATS;
-      if (lane < cnt) {
+      if (lane < cur.cnt) {
 #pragma unroll
-        for (int rr = 0; rr < RPS; ++rr) {
-          float x[P], y[P], z[P];
-          load_cell_row<LAYOUT, P>(blk, TW, RPS, rr, lane, x, y, z);
-          walk.row(st * RPS + rr, x, y, z, args.thr.depth_discontinuity_threshold);
-        }
+        for (int rr = 0; rr < RPS; ++rr) walk.row(st * RPS + rr, blk, TW, RPS, rr, lane, args.thr.depth_discontinuity_threshold);
       }
       __syncwarp();        // every lane is done reading the slot ...
-      issue(q + kRing);    // ... before the async proxy refills it
+      issue_next(slot);    // ... before the async proxy refills it
+      if (++slot == RING) {
+        slot = 0;
+        phase ^= 1u;
+      }
     }
-    if (lane < cnt) {
+    if (lane < cur.cnt) {
       CellRaw raw;
       walk.finish(raw);
-      const long long cell = frame * g.n_cells + static_cast<long long>(strip) * g.nh + c0 + lane;
-      finish_cell(raw, args.thr, args.tables, cell);
+      finish_cell(raw, args.thr, args.tables, cur.cell0 + lane);
     }
+    locate(n + 1, cur);
   }
 }
 
@@ -303,21 +338,26 @@ cudaError_t launch_tile(const CellStatsArgs& a, int grid, size_t smem, cudaStrea
   return cudaGetLastError();
 }
 
-template <int LAYOUT, int P, int WARPS>
+template <int LAYOUT, int P, int WARPS, int RING>
 cudaError_t launch_stream_pw(const CellStatsArgs& a, cudaStream_t st) {
-  constexpr size_t smem = static_cast<size_t>(WARPS) * kRing * rows_per_slot(P) * 32 * P * 12;
+  constexpr size_t smem = static_cast<size_t>(WARPS) * RING * rows_per_slot(P) * 32 * P * 12;
   static_assert(smem <= 200 * 1024, "ring does not fit");
-  cudaFuncSetAttribute(cell_stats_stream_kernel<LAYOUT, P, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(cell_stats_stream_kernel<LAYOUT, P, WARPS, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const long long total_tiles = static_cast<long long>(a.n_frames) * a.geom.nv * a.tiles_per_strip;
   const long long ctas = (total_tiles + WARPS - 1) / WARPS;
   const int grid = static_cast<int>(ctas < a.sm_count ? ctas : a.sm_count);
-  cell_stats_stream_kernel<LAYOUT, P, WARPS><<<grid, WARPS * 32, smem, st>>>(a);
+  cell_stats_stream_kernel<LAYOUT, P, WARPS, RING><<<grid, WARPS * 32, smem, st>>>(a);
   return cudaGetLastError();
 }
 
 template <int LAYOUT, int P>
 cudaError_t launch_stream_p(const CellStatsArgs& a, cudaStream_t st) {
-  return a.stream_warps == 12 ? launch_stream_pw<LAYOUT, P, 12>(a, st) : launch_stream_pw<LAYOUT, P, 8>(a, st);
+  switch (a.stream_warps) {
+    case 8: return launch_stream_pw<LAYOUT, P, 8, 4>(a, st);
+    case 16: return launch_stream_pw<LAYOUT, P, 16, 3>(a, st);
+    case 12: return launch_stream_pw<LAYOUT, P, 12, 4>(a, st);
+    default: return launch_stream_pw<LAYOUT, P, 16, 3>(a, st);
+  }
 }
 
 template <int LAYOUT>

@@ -15,7 +15,7 @@ struct CellStatsArgs {
   int vec_ok;           // base pointer and plane strides allow 16-byte loads
   int sm_count;         // persistent grid size of the streaming kernel
   int force_tile_kernel;  // diagnostics: always take the fallback kernel
-  int stream_warps;     // warps per persistent CTA of the streaming kernel (8 or 12)
+  int stream_warps;     // warps per persistent CTA of the streaming kernel (8, 12 or 16)
   Geometry geom;
   Thresholds thr;
   Tables tables;
