@@ -26,6 +26,9 @@
 // it fits (always at 640x480 / patch 10: 36 KB), else in the global scratch tables.
 #include "region_grow.cuh"
 
+#include <cstdlib>
+#include <cstring>
+
 #include "plane_fit.cuh"
 
 namespace dpx {
@@ -109,6 +112,14 @@ __global__ void __launch_bounds__(256) edge_mask_kernel(const RegionArgs args) {
   }
   args.tables.edge[idx] = static_cast<uint8_t>(mask);
 }
+
+}  // namespace
+}  // namespace dpx
+
+#include "region_grow_cta.cuh"
+
+namespace dpx {
+namespace {
 
 template <bool SMEM>
 __global__ void __launch_bounds__(32) region_grow_kernel(const RegionArgs args) {
@@ -598,8 +609,13 @@ cudaError_t launch_region_grow(const RegionArgs& args, cudaStream_t stream) {
   edge_mask_kernel<<<static_cast<unsigned>((cells + 255) / 256), 256, 0, stream>>>(args);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  const CtaPlan cta = region_grow_cta_plan(args.geom, args.thr);
+  static const bool force_warp_kernel = std::getenv("DPX_REGION_KERNEL") && std::strcmp(std::getenv("DPX_REGION_KERNEL"), "warp") == 0;
   const bool all_smem = args.plan.bins_smem && args.plan.list_smem && args.plan.members_smem && args.plan.merge_smem;
-  if (all_smem) {
+  if (cta.bytes > 0 && !force_warp_kernel) {
+    cudaFuncSetAttribute(region_grow_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cta.bytes));
+    region_grow_cta_kernel<<<args.n_frames, kCtaThreads, cta.bytes, stream>>>(args, cta);
+  } else if (all_smem) {
     cudaFuncSetAttribute(region_grow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(args.plan.bytes));
     region_grow_kernel<true><<<args.n_frames, 32, args.plan.bytes, stream>>>(args);
   } else {

@@ -1,0 +1,562 @@
+// region_grow_cta.cuh -- stage 2 for frames whose working set fits in shared memory (every BASELINE
+// 640x480 / patch >= 6 configuration): one CTA of four warps per frame.
+//
+// Same algorithm and the same exactness arguments as region_grow_kernel (region_grow.cu); what changes is
+// who does what, so that only the truly sequential part sits on the critical path:
+//
+//   warp 0      the sequential chain of createPlaneSegments (plane_extractor.cpp:302-331): most frequent bin,
+//               seed, FIFO BFS.  One 32-bit word per cell {bin, edge mask, alive} makes a BFS probe a single
+//               shared-memory read; the histogram is a compacted array of keys {count, bin} over the non-empty
+//               bins (one read + one redux for the first-max bin), decremented once per region for the seed's
+//               bin and by rare atomics for the others.
+//   warps 1-3   consume finished regions from a shared-memory ring while warp 0 keeps growing: the fp32
+//               moment chains over the region's FIFO list (plane_extractor.cpp:318-327).
+//   all warps   setup (histogram, grouping by bin), then after growing: plane fits one region per thread
+//               (:333-337), ordered compaction into segment ids, labels_map_ painting (:339-342), adjacency
+//               bit matrix (:430-453), final per-cell labels (:464-465).  findMergedLabels (:402-423) is a
+//               short sequential loop run by warp 0 on shared-memory plane records.
+#pragma once
+
+namespace dpx {
+namespace {
+
+constexpr int kCtaThreads = 128;
+constexpr int kCtaWarps = kCtaThreads / 32;
+constexpr unsigned kAlive = 1u << 20;   // cell word: bits 0-15 bin, 16-19 edge mask, 20 alive (planar and unassigned)
+constexpr int kRecFloats = kSegFloats;  // region / plane records use the segs layout
+
+struct CtaPlan {
+  int off_stage, off_hkey, off_binslot, off_binoff, off_runend, off_cw, off_list, off_members, off_msem, off_recs, off_merge,
+      off_misc;
+  int rec_cap;       // region / plane records held in shared memory (the rest spill to the global segs table)
+  int adj_bytes;     // bytes available to the adjacency bit matrix (the member runs' storage)
+  size_t bytes;
+};
+
+__device__ __noinline__ void fit_plane_call(const Moments& m, PlaneFit& f) { fit_plane(m, f); }
+
+__global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const RegionArgs args, const CtaPlan plan) {
+  extern __shared__ float4 smem_f4[];
+  const Geometry& g = args.geom;
+  const Thresholds& th = args.thr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int frame = blockIdx.x;
+  const int C = g.n_cells, nh = g.nh, nv = g.nv;
+  const int B2 = th.histogram_bins_per_coord * th.histogram_bins_per_coord;
+  const long long fc = static_cast<long long>(frame) * C;
+
+  char* smem = reinterpret_cast<char*>(smem_f4);
+  float* stage_all = reinterpret_cast<float*>(smem + plan.off_stage);        // [3 warps][32][12]
+  unsigned* hkey = reinterpret_cast<unsigned*>(smem + plan.off_hkey);        // [K] count << 15 | (0x7fff - bin), non-empty bins
+  int16_t* binslot = reinterpret_cast<int16_t*>(smem + plan.off_binslot);    // [B2] bin -> slot in hkey (or -1)
+  int* bin_off = reinterpret_cast<int*>(smem + plan.off_binoff);             // [K] start of the bin's member run
+  int* run_end = reinterpret_cast<int*>(smem + plan.off_runend);             // [K] end of its still-unassigned members
+  unsigned* cw = reinterpret_cast<unsigned*>(smem + plan.off_cw);            // [C] cell words; later the segment labels
+  int32_t* list = reinterpret_cast<int32_t*>(smem + plan.off_list);          // [C] BFS queues = region cell lists
+  int32_t* members = reinterpret_cast<int32_t*>(smem + plan.off_members);    // [C] cell ids grouped by initial bin
+  float* msem = reinterpret_cast<float*>(smem + plan.off_msem);              // [C] their MSE, same order
+  float* recs = reinterpret_cast<float*>(smem + plan.off_recs);              // [rec_cap][24]
+  int32_t* merge = reinterpret_cast<int32_t*>(smem + plan.off_merge);        // [plane_cap]
+  volatile int* misc = reinterpret_cast<volatile int*>(smem + plan.off_misc);
+  // misc: [0] regions published, [1] growing finished, [2] scratch counter, [3] remaining planar cells, [4] K,
+  //       [8..8+kCtaWarps) per-warp counts for the ordered compaction
+  int* hist_tmp = reinterpret_cast<int*>(list);  // [B2] raw histogram during setup (the list is still unused)
+
+  const float4* rec_b4 = args.tables.rec_b + 3 * fc;
+  const int16_t* bin_in = args.tables.bin + fc;
+  const uint8_t* edge_in = args.tables.edge + fc;
+  const float* mse_g = args.tables.mse + fc;
+  int32_t* seg_label = args.tables.seg_label + fc;
+  int32_t* cell_label = args.tables.cell_label + fc;
+  float* segs_g = args.tables.segs + static_cast<long long>(frame) * g.plane_cap * kSegFloats;
+  int32_t* merge_out = args.tables.merge + static_cast<long long>(frame) * g.plane_cap;
+  auto rec_ptr = [&](int r) -> float* {
+    return r < plan.rec_cap ? recs + r * kRecFloats : segs_g + static_cast<long long>(r) * kSegFloats;
+  };
+
+  const bool prof = args.prof != nullptr;
+  const long long t_kernel0 = prof ? clock64() : 0;
+
+  // ---- setup: cell words, histogram (normals_histogram.cpp:21-49; bins come from stage 1) ----------
+  for (int i = tid; i < B2; i += kCtaThreads) {
+    hist_tmp[i] = 0;
+    binslot[i] = -1;
+  }
+  if (tid < 8 + kCtaWarps) misc[tid] = 0;
+  __syncthreads();
+  for (int c = tid; c < C; c += kCtaThreads) {
+    const int b = static_cast<int>(__ldg(bin_in + c));
+    const unsigned e = static_cast<unsigned>(__ldg(edge_in + c));
+    cw[c] = b >= 0 ? (static_cast<unsigned>(b) | (e << 16) | kAlive) : 0u;
+    seg_label[c] = 0;
+    if (b >= 0) atomicAdd(&hist_tmp[b], 1);
+  }
+  __syncthreads();
+  // compact the non-empty bins and lay out their member runs (warp 0; ascending bin order)
+  if (warp == 0) {
+    int K = 0, run = 0;
+    for (int b0 = 0; b0 < B2; b0 += 32) {
+      const int b = b0 + lane;
+      const int cnt = b < B2 ? hist_tmp[b] : 0;
+      const unsigned nz = __ballot_sync(kFull, cnt > 0);
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (cnt > 0) {
+        const int slot = K + __popc(nz & ((1u << lane) - 1u));
+        binslot[b] = static_cast<int16_t>(slot);
+        hkey[slot] = (static_cast<unsigned>(cnt) << 15) | (0x7fffu - static_cast<unsigned>(b));
+        bin_off[slot] = run + incl - cnt;
+        run_end[slot] = run + incl - cnt;
+      }
+      K += __popc(nz);
+      run += __shfl_sync(kFull, incl, 31);
+    }
+    if (lane == 0) {
+      misc[3] = run;
+      misc[4] = K;
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += kCtaThreads) {
+    const unsigned w = cw[c];
+    if (w & kAlive) {
+      const int pos = atomicAdd(&run_end[binslot[w & 0xffffu]], 1);
+      members[pos] = c;
+      msem[pos] = __ldg(mse_g + c);
+    }
+  }
+  __syncthreads();  // (hist_tmp aliases the list: nobody touches the list before this barrier)
+
+  const int cell_pts = g.patch * g.patch;
+  long long t_seed = 0, t_bfs = 0, t_mark = 0;
+  int n_seeds = 0, n_steps = 0;
+  const long long t_init = prof ? clock64() - t_kernel0 : 0;
+
+  if (warp == 0) {
+    // ================= the sequential chain: createPlaneSegments (plane_extractor.cpp:302-331) ==========
+    int remaining = misc[3];
+    const int K = misc[4];
+    int n_regions = 0, list_off = 0;
+    const int slot4 = lane & 3;
+    const int delta = (slot4 == 0) ? -nh : (slot4 == 1) ? nh : (slot4 == 2) ? -1 : 1;
+    while (remaining > 0) {
+      if (prof) t_mark = clock64();
+      // most frequent bin, first maximum (normals_histogram.cpp:54-56): max key = largest count, smallest bin id
+      unsigned key = 0;
+      for (int i = lane; i < K; i += 32) key = max(key, hkey[i]);
+      key = __reduce_max_sync(kFull, key);
+      const int bc = static_cast<int>(key >> 15), bi = static_cast<int>(0x7fffu - (key & 0x7fffu));
+      const unsigned long long n_cand = bc > 0 ? static_cast<unsigned long long>(bc) : 0ull;
+      if (n_cand < th.min_candidate_size) break;  // plane_extractor.cpp:305-307
+      const int bslot = binslot[bi];
+
+      // seed = first strict minimum of the MSE among the bin's unassigned cells (plane_extractor.cpp:309-316);
+      // the scan also compacts the bin's member run down to the cells that are still unassigned
+      float lm = __int_as_float(0x7f800000);
+      int seed = kNoSeed;
+      {
+        const int start = bin_off[bslot], end = run_end[bslot];
+        int w = start;
+        for (int i0 = start; i0 < end; i0 += 32) {
+          const int i = i0 + lane;
+          const bool in = i < end;
+          const int c = in ? members[i] : 0;
+          const float m = in ? msem[i] : 0.f;
+          const bool alive = in && (cw[c] & kAlive);
+          if (alive && (m < lm || (m == lm && c < seed))) { lm = m; seed = c; }
+          const unsigned am = __ballot_sync(kFull, alive);
+          if (am != kFull || w != i0) {
+            if (alive) {
+              const int pos = w + __popc(am & ((1u << lane) - 1u));
+              members[pos] = c;
+              msem[pos] = m;
+            }
+          }
+          w += __popc(am);
+          __syncwarp();
+        }
+        if (lane == 0) run_end[bslot] = w;
+      }
+      {
+        const unsigned fb = __float_as_uint(lm);
+        const unsigned ord = fb ^ ((fb >> 31) ? 0xffffffffu : 0x80000000u);
+        const unsigned best = __reduce_min_sync(kFull, seed == kNoSeed ? 0xffffffffu : ord);
+        const unsigned cand = (seed != kNoSeed && ord == best) ? static_cast<unsigned>(seed) : static_cast<unsigned>(kNoSeed);
+        seed = static_cast<int>(__reduce_min_sync(kFull, cand));
+        const unsigned bb = best ^ ((best >> 31) ? 0x80000000u : 0xffffffffu);
+        lm = __uint_as_float(bb);
+      }
+      // no candidate with mse < INT_MAX: the reference reads an uninitialised seed id here
+      if (seed == kNoSeed || !(static_cast<double>(lm) < 2147483647.0)) break;
+      if (prof) { const long long t = clock64(); t_seed += t - t_mark; t_mark = t; ++n_seeds; }
+
+      // growSeed (plane_extractor.cpp:349-392): batched FIFO BFS into list[list_off ...)
+      int32_t* q = list + list_off;
+      int same = 0;  // cells of the seed's bin activated by this lane (histogram is settled after the BFS)
+      const unsigned seed_w = cw[seed];
+      __syncwarp();
+      if (lane == 0) {
+        q[0] = seed | static_cast<int>(((seed_w >> 16) & 0xfu) << 24);
+        cw[seed] = seed_w & ~kAlive;
+        same = 1;
+      }
+      __syncwarp();
+      // a seed without a single passing edge is a region of one cell: no BFS step needed
+      int head = ((seed_w >> 16) & 0xfu) ? 0 : 1, tail = 1;
+      while (head < tail) {
+        const int nb = min(8, tail - head);
+        int v = 0;
+        unsigned w = 0;
+        if ((lane >> 2) < nb) {
+          const unsigned pk = static_cast<unsigned>(q[head + (lane >> 2)]);
+          if ((pk >> (24 + slot4)) & 1u) {
+            v = static_cast<int>(pk & 0xffffffu) + delta;
+            w = cw[v];
+          }
+        }
+        const bool pass = (w & kAlive) != 0;  // edge test passed, still unassigned, not yet activated
+        const unsigned pm = __ballot_sync(kFull, pass);
+        unsigned wm = 0;
+        if (pm) {
+          bool win = pass;
+          // lanes of one queue entry have distinct targets: only passing lanes of different entries can clash
+          const unsigned same_entry = 0xfu << ((__ffs(pm) - 1) & ~3);
+          if (pass && (pm & ~same_entry)) {
+            const unsigned grp = __match_any_sync(pm, v);
+            win = (__ffs(grp) - 1) == lane;
+          }
+          wm = __ballot_sync(kFull, win);
+          if (win) {
+            q[tail + __popc(wm & ((1u << lane) - 1u))] = v | static_cast<int>(((w >> 16) & 0xfu) << 24);
+            cw[v] = w & ~kAlive;  // removePoint + unassigned_mask[v] = false (plane_extractor.cpp:324-325)
+            const int b = static_cast<int>(w & 0xffffu);
+            if (b == bi) ++same;
+            else atomicSub(&hkey[binslot[b]], 1u << 15);
+          }
+        }
+        tail += __popc(wm);
+        head += nb;
+        ++n_steps;
+        __syncwarp();
+      }
+      same = __reduce_add_sync(kFull, same);
+      if (lane == 0) hkey[bslot] -= static_cast<unsigned>(same) << 15;
+      remaining -= tail;
+      if (prof) { const long long t = clock64(); t_bfs += t - t_mark; t_mark = t; }
+      if (static_cast<unsigned long long>(tail) < th.min_cells_activated) { __syncwarp(); continue; }  // :329-331
+      if (n_regions < g.plane_cap) {
+        // publish the region to the accumulating warps
+        if (lane == 0) {
+          float* rec = rec_ptr(n_regions);
+          rec[kSegOff] = __int_as_float(list_off);
+          rec[kSegCnt] = __int_as_float(tail);
+          rec[kSegN] = __int_as_float(seed);  // the consumer replaces it by the point count
+          __threadfence_block();
+          misc[0] = n_regions + 1;
+        }
+        ++n_regions;
+        list_off += tail;
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {
+      __threadfence_block();
+      misc[1] = 1;
+    }
+  } else {
+    // ================= consumers: region moments in FIFO order (plane_extractor.cpp:318-327) ================
+    float* stage = stage_all + (warp - 1) * 32 * 12;
+    for (int r = warp - 1;; r += kCtaWarps - 1) {
+      while (misc[0] <= r && misc[1] == 0) __nanosleep(64);
+      if (misc[0] <= r) {
+        // growing may have finished between the two reads: look once more
+        __threadfence_block();
+        if (misc[0] <= r) break;
+      }
+      __threadfence_block();
+      float* rec = rec_ptr(r);
+      const int off = __float_as_int(*reinterpret_cast<volatile float*>(rec + kSegOff));
+      const int cnt = __float_as_int(*reinterpret_cast<volatile float*>(rec + kSegCnt));
+      const int seed = __float_as_int(*reinterpret_cast<volatile float*>(rec + kSegN));
+      const volatile int32_t* q = list + off;
+      // seed first and twice: the candidate starts as a copy of the seed's stats, then every activated cell,
+      // the seed included, is added (plane_extractor.cpp:318-323)
+      float acc = 0.f;
+      if (lane < 9) acc = __ldg(reinterpret_cast<const float*>(rec_b4) + 12 * seed + lane);
+      float4 ra[3], rb[3];
+      auto fetch = [&](int i0, float4 (&rr)[3]) {
+        if (i0 < cnt) {
+          const int c = q[min(i0 + lane, cnt - 1)] & 0xffffff;
+          rr[0] = __ldg(rec_b4 + 3 * c); rr[1] = __ldg(rec_b4 + 3 * c + 1); rr[2] = __ldg(rec_b4 + 3 * c + 2);
+        }
+      };
+      fetch(0, ra);
+      fetch(32, rb);
+      for (int i0 = 0; i0 < cnt; i0 += 32) {
+        const int n = min(32, cnt - i0);
+        float4* st4 = reinterpret_cast<float4*>(stage + 12 * lane);
+        st4[0] = ra[0]; st4[1] = ra[1]; st4[2] = ra[2];
+        ra[0] = rb[0]; ra[1] = rb[1]; ra[2] = rb[2];
+        fetch(i0 + 64, rb);
+        __syncwarp();
+        if (lane < 9) {
+          if (n == 32) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) acc = __fadd_rn(acc, stage[12 * k + lane]);
+          } else {
+            for (int k = 0; k < n; ++k) acc = __fadd_rn(acc, stage[12 * k + lane]);
+          }
+        }
+        __syncwarp();
+      }
+      if (lane < 9) rec[kSegS + lane] = acc;
+      if (lane == 9) rec[kSegN] = __int_as_float(cell_pts * (cnt + 1));
+    }
+  }
+  __syncthreads();
+  const long long t_grow_end = prof ? clock64() : 0;
+  const int n_regions = misc[0];
+
+  // ---- labels_map_ starts at zero; cw becomes the per-cell segment label ------------------------------
+  for (int c = tid; c < C; c += kCtaThreads) cw[c] = 0;
+
+  // ---- plane fit of every grown region, one thread per region (plane_extractor.cpp:333-343) -----------
+  int nseg = 0;
+  for (int base = 0; base < n_regions; base += kCtaThreads) {
+    const int r = base + tid;
+    Moments mom;
+    PlaneFit fit;
+    int off = 0, cnt = 0;
+    bool accept = false;
+    if (r < n_regions) {
+      const float* rec = rec_ptr(r);
+      mom.n = __float_as_int(rec[kSegN]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) mom.s[i] = rec[kSegS + i];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) mom.v[i] = rec[kSegV + i];
+      off = __float_as_int(rec[kSegOff]);
+      cnt = __float_as_int(rec[kSegCnt]);
+      fit_plane_call(mom, fit);
+      accept = fit.score > th.min_region_planarity_score;  // strict (plane_extractor.cpp:336)
+    }
+    const unsigned am = __ballot_sync(kFull, accept);
+    if (lane == 0) misc[8 + warp] = __popc(am);
+    __syncthreads();  // every record of this chunk has been read; warp counts are visible
+    int before = nseg;
+    for (int w = 0; w < warp; ++w) before += misc[8 + w];
+    int total = 0;
+    for (int w = 0; w < kCtaWarps; ++w) total += misc[8 + w];
+    if (accept) {
+      const int id = before + __popc(am & ((1u << lane) - 1u));  // 0-based segment index, in seed order
+      float* rec = rec_ptr(id);
+      rec[kSegN] = __int_as_float(mom.n);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) rec[kSegS + i] = mom.s[i];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) rec[kSegV + i] = mom.v[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) rec[kSegMean + i] = fit.mean[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) rec[kSegNormal + i] = fit.normal[i];
+      rec[kSegD] = fit.d;
+      rec[kSegMse] = fit.mse;
+      rec[kSegScore] = fit.score;
+      rec[kSegOff] = __int_as_float(off);
+      rec[kSegCnt] = __int_as_float(cnt);
+      merge[id] = id;
+    }
+    nseg += total;
+    __syncthreads();
+  }
+  if (tid == 0) args.tables.n_planes[frame] = nseg;
+  __threadfence_block();
+  __syncthreads();
+  // paint labels_map_ (plane_extractor.cpp:339-342): one warp per segment
+  for (int s = warp; s < nseg; s += kCtaWarps) {
+    const float* rec = rec_ptr(s);
+    const int off = __float_as_int(rec[kSegOff]), cnt = __float_as_int(rec[kSegCnt]);
+    for (int i = lane; i < cnt; i += 32) {
+      const int c = list[off + i] & 0xffffff;
+      cw[c] = static_cast<unsigned>(s + 1);
+      seg_label[c] = s + 1;
+    }
+  }
+  __syncthreads();
+  const long long t_fit_end = prof ? clock64() : 0;
+
+  // ---- getConnectedComponents (plane_extractor.cpp:430-453): upper-triangle adjacency bits --------------
+  const int words = (nseg + 31) / 32;
+  unsigned* adj = reinterpret_cast<unsigned*>(members);  // [nseg][words], reuses the member runs
+  const bool adj_fits = static_cast<long long>(nseg) * words * 4 <= plan.adj_bytes;
+  unsigned* rowbits = adj;  // fallback: one row at a time
+  const int limit = (nv - 1) * nh;
+  if (nseg > 1 && adj_fits) {
+    for (int i = tid; i < nseg * words; i += kCtaThreads) adj[i] = 0;
+    __syncthreads();
+    for (int c = tid; c < limit; c += kCtaThreads) {
+      const int qc = c % nh;
+      const int id = static_cast<int>(cw[c]);
+      if (qc < nh - 1 && id > 0) {
+        const int right = static_cast<int>(cw[c + 1]), down = static_cast<int>(cw[c + nh]);
+        if (right > 0 && right != id) {
+          const int a = min(id, right) - 1, b = max(id, right) - 1;
+          atomicOr(&adj[a * words + (b >> 5)], 1u << (b & 31));
+        }
+        if (down > 0 && down != id) {
+          const int a = min(id, down) - 1, b = max(id, down) - 1;
+          atomicOr(&adj[a * words + (b >> 5)], 1u << (b & 31));
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- findMergedLabels (plane_extractor.cpp:402-423) ---------------------------------------------------
+  const double min_cos = static_cast<double>(th.min_cos_angle_merge);
+  if (nseg > 1) {
+    for (int r = 0; r < nseg; ++r) {
+      if (!adj_fits) {
+        // pathological segment counts: build row r alone from the label map
+        __syncthreads();
+        for (int i = tid; i < words; i += kCtaThreads) rowbits[i] = 0;
+        __syncthreads();
+        for (int c = tid; c < limit; c += kCtaThreads) {
+          const int qc = c % nh;
+          const int id = static_cast<int>(cw[c]);
+          if (qc < nh - 1 && id > 0) {
+            const int right = static_cast<int>(cw[c + 1]), down = static_cast<int>(cw[c + nh]);
+            if (right > 0 && right != id && min(id, right) - 1 == r) {
+              const int b = max(id, right) - 1;
+              atomicOr(&rowbits[b >> 5], 1u << (b & 31));
+            }
+            if (down > 0 && down != id && min(id, down) - 1 == r) {
+              const int b = max(id, down) - 1;
+              atomicOr(&rowbits[b >> 5], 1u << (b & 31));
+            }
+          }
+        }
+        __syncthreads();
+      }
+      if (warp != 0) continue;
+      const unsigned* row = adj_fits ? adj + r * words : rowbits;
+      bool any = false;
+      for (int w = lane; w < words; w += 32) any |= row[w] != 0;
+      if (!__any_sync(kFull, any)) continue;
+
+      const int a = merge[r];
+      float* ra = rec_ptr(a);
+      Moments ma;
+      ma.n = __float_as_int(ra[kSegN]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) ma.s[i] = ra[kSegS + i];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) ma.v[i] = ra[kSegV + i];
+      // normal/d of `a` are the ones it had when the row started (stats are refit after the row)
+      const float an0 = ra[kSegNormal], an1 = ra[kSegNormal + 1], an2 = ra[kSegNormal + 2], ad = ra[kSegD];
+      bool expanded = false;
+      for (int w = 0; w < words; ++w) {
+        unsigned bits = row[w];
+        while (bits) {
+          const int t = w * 32 + __ffs(bits) - 1;
+          bits &= bits - 1;
+          const float* rt = rec_ptr(t);
+          const double cos_angle = static_cast<double>(dot3(an0, an1, an2, rt[kSegNormal], rt[kSegNormal + 1], rt[kSegNormal + 2]));
+          const float df = __fadd_rn(dot3(an0, an1, an2, rt[kSegMean], rt[kSegMean + 1], rt[kSegMean + 2]), ad);
+          const double distance = __dmul_rn(static_cast<double>(df), static_cast<double>(df));
+          if (cos_angle > min_cos && distance < static_cast<double>(th.max_merge_dist)) {
+            ma.n += __float_as_int(rt[kSegN]);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) ma.s[i] = __fadd_rn(ma.s[i], rt[kSegS + i]);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) ma.v[i] = __fadd_rn(ma.v[i], rt[kSegV + i]);
+            if (lane == 0) merge[t] = a;
+            expanded = true;
+          }
+        }
+      }
+      if (expanded) {
+        PlaneFit fa;
+        fit_plane_call(ma, fa);
+        __syncwarp();
+        if (lane == 0) {
+          ra[kSegN] = __int_as_float(ma.n);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) ra[kSegS + i] = ma.s[i];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) ra[kSegV + i] = ma.v[i];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) ra[kSegMean + i] = fa.mean[i];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) ra[kSegNormal + i] = fa.normal[i];
+          ra[kSegD] = fa.d;
+          ra[kSegMse] = fa.mse;
+          ra[kSegScore] = fa.score;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+  const long long t_merge_end = prof ? clock64() : 0;
+
+  // ---- per-cell final labels (plane_extractor.cpp:464-465), plane records back to the global tables ---------
+  for (int c = tid; c < C; c += kCtaThreads) {
+    const int l = static_cast<int>(cw[c]);
+    cell_label[c] = (l == 0) ? 0 : merge[l - 1] + 1;
+  }
+  for (int i = tid; i < nseg; i += kCtaThreads) merge_out[i] = merge[i];
+  {
+    const int n_smem = min(nseg, plan.rec_cap);
+    for (int i = tid; i < n_smem * kSegFloats; i += kCtaThreads) segs_g[i] = recs[i];
+  }
+  if (prof && tid == 0) {
+    long long* o = args.prof + static_cast<long long>(frame) * kRegionProfSlots;
+    const long long t_end = clock64();
+    o[0] = t_end - t_kernel0;          // whole frame
+    o[1] = t_init;                     // setup
+    o[2] = t_seed;                     // bin argmax + seed search (all seeds)
+    o[3] = t_bfs;                      // BFS (all seeds)
+    o[4] = 0;                          // moment accumulation runs concurrently on warps 1-3
+    o[5] = t_fit_end - t_grow_end;     // plane fits + label painting
+    o[6] = t_merge_end - t_fit_end;    // adjacency + merging
+    o[7] = t_end - t_merge_end;        // final labels
+    o[8] = n_seeds;
+    o[9] = n_steps;
+    o[10] = n_regions;
+    o[11] = nseg;
+  }
+}
+
+// Shared-memory layout of the CTA kernel; bytes == 0 means "does not fit, use the generic kernel".
+inline CtaPlan region_grow_cta_plan(const Geometry& g, const Thresholds& th) {
+  CtaPlan p{};
+  auto align16 = [](size_t v) { return (v + 15) & ~static_cast<size_t>(15); };
+  const size_t B2 = static_cast<size_t>(th.histogram_bins_per_coord) * th.histogram_bins_per_coord;
+  const size_t C = static_cast<size_t>(g.n_cells);
+  size_t off = 0;
+  p.off_stage = static_cast<int>(off);   off = align16(off + static_cast<size_t>(kCtaWarps - 1) * 32 * 12 * 4);
+  p.off_hkey = static_cast<int>(off);    off = align16(off + B2 * 4);
+  p.off_binslot = static_cast<int>(off); off = align16(off + B2 * 2);
+  p.off_binoff = static_cast<int>(off);  off = align16(off + B2 * 4);
+  p.off_runend = static_cast<int>(off);  off = align16(off + B2 * 4);
+  p.off_cw = static_cast<int>(off);      off = align16(off + C * 4);
+  p.off_list = static_cast<int>(off);    off = align16(off + (C > B2 ? C : B2) * 4);
+  p.off_members = static_cast<int>(off); off = align16(off + C * 4);
+  p.off_msem = static_cast<int>(off);    off = align16(off + C * 4);
+  p.adj_bytes = static_cast<int>(off - p.off_members);
+  p.rec_cap = g.plane_cap < 128 ? g.plane_cap : 128;
+  p.off_recs = static_cast<int>(off);    off = align16(off + static_cast<size_t>(p.rec_cap) * kRecFloats * 4);
+  p.off_merge = static_cast<int>(off);   off = align16(off + static_cast<size_t>(g.plane_cap) * 4);
+  p.off_misc = static_cast<int>(off);    off = align16(off + 64);
+  p.bytes = off <= 100 * 1024 ? off : 0;
+  return p;
+}
+
+}  // namespace
+}  // namespace dpx
