@@ -17,6 +17,7 @@
 #include "cell_stats.cuh"
 #include "error_state.h"
 #include "labeling.cuh"
+#include "refine.cuh"
 #include "region_grow.cuh"
 
 namespace dpx {
@@ -39,6 +40,7 @@ struct dpx_extractor {
   int stream_warps = 16;      // env DPX_STREAM_WARPS=8|12|16 (A/B measurement)
   int force_tile_kernel = 0;  // env DPX_CELL_KERNEL=tile (A/B measurement of the two stage-1 kernels)
   RegionPlan plan{};
+  uint32_t* mt_init = nullptr;       // std::mt19937 default state for the refinement stage
   long long* region_prof = nullptr;  // [max_batch][kRegionProfSlots], written while profiling is on
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
@@ -158,9 +160,24 @@ dpx_status run_stages(dpx_extractor* ex, const float* d_xyz, int n_frames, int l
     DPX_CUDA(ex, launch_labeling(la, st));
     if (ex->geom.n_cells > 0) ++ex->launches;
   }
+  if (prof) DPX_CUDA(ex, cudaEventRecord(ex->e_stage[3], st));
+  if (ex->cfg.ransac_refinement && ex->geom.n_cells > 0) {  // plane_extractor.cpp:265-267
+    RefineArgs fa{};
+    fa.xyz = d_xyz;
+    fa.layout = layout;
+    fa.n_frames = n_frames;
+    fa.max_iterations = ex->cfg.ransac_max_iterations;
+    fa.threshold = ex->cfg.ransac_threshold;
+    fa.inliers_ratio = ex->cfg.ransac_inliers_ratio;
+    fa.mt_init = ex->mt_init;
+    fa.geom = ex->geom;
+    fa.tables = ex->tb;
+    fa.labels = d_labels;
+    DPX_CUDA(ex, launch_refine(fa, st));
+    ++ex->launches;
+  }
   if (prof) {
-    DPX_CUDA(ex, cudaEventRecord(ex->e_stage[3], st));
-    DPX_CUDA(ex, cudaEventRecord(ex->e_stage[4], st));  // refinement stage placeholder (not enabled)
+    DPX_CUDA(ex, cudaEventRecord(ex->e_stage[4], st));
     ex->stage_valid = true;
   }
   ex->last_frames = n_frames;
@@ -291,6 +308,13 @@ dpx_status dpx_create(int32_t height, int32_t width, const dpx_config* cfg_in, i
     if (e != cudaSuccess) { delete ex; return cuda_fail(nullptr, e, "cudaMalloc(scratch tables)"); }
     carve_tables(g, max_batch, ex->plan.bins_smem != 0, static_cast<char*>(ex->scratch), &ex->tb);
   }
+  if (cfg.ransac_refinement) {
+    uint32_t mt[kMtN];
+    mt19937_default_state(mt);
+    cudaError_t e = cudaMalloc(&ex->mt_init, sizeof(mt));
+    if (e == cudaSuccess) e = cudaMemcpy(ex->mt_init, mt, sizeof(mt), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { dpx_destroy(ex); return cuda_fail(nullptr, e, "cudaMalloc(mt19937 state)"); }
+  }
   {
     cudaError_t e = cudaMalloc(&ex->region_prof, sizeof(long long) * kRegionProfSlots * max_batch);
     if (e != cudaSuccess) { dpx_destroy(ex); return cuda_fail(nullptr, e, "cudaMalloc(region profile)"); }
@@ -321,6 +345,7 @@ void dpx_destroy(dpx_extractor* ex) {
     if (ex->e_stage[i]) cudaEventDestroy(ex->e_stage[i]);
   if (ex->scratch) cudaFree(ex->scratch);
   if (ex->region_prof) cudaFree(ex->region_prof);
+  if (ex->mt_init) cudaFree(ex->mt_init);
   delete ex;
 }
 

@@ -1,0 +1,397 @@
+// refine.cu -- stage 4 of the hot path (opt-in, ransacRefinement=1): per-plane RANSAC refinement of the labels.
+//
+// Replaces, per frame (reference file:line):
+//   PlaneExtractor::Impl::refineLabels                          plane_extractor.cpp:472-509
+//   RTL::PlaneRANSAC::FindBest / FindInliers / IsContinued /
+//     GenerateModel / EvaluateModel                             libs/rtl/include/rtl/RANSAC.hpp:25-98
+//   PlaneEstimator::ComputeModel / ComputeError                 libs/rtl/include/rtl/Plane.hpp:13-49
+//   std::mt19937 (default seed 5489, one generator per process() call, shared across the labels) and
+//   libstdc++'s std::uniform_int_distribution<int> (GCC >= 11: Lemire's multiply-shift with rejection)
+//
+// One CTA per frame.  The reference's loop is sequential twice over -- labels share one random stream, and each
+// label's iterations stop as soon as a hypothesis reaches the target inlier ratio -- so the CTA walks the labels in
+// order and evaluates the next 32 hypotheses of the current label speculatively and at once:
+//   warp 0     draws the sample ranks of 32 hypotheses from the generator (state in shared memory, twist done by
+//              the warp), remembering how many draws each one took;
+//   96 threads turn (hypothesis, sample) ranks into pixels: the k-th pixel of a label in image order follows
+//              from the label's cells sorted by cell id (cells are painted whole), no per-pixel index lists;
+//   32 threads build the plane models (fp32, the reference's expression order);
+//   all warps  score: a warp stages 32 points in shared memory, then lane g scores hypothesis g on each of them
+//              (the loss is a count, so the order of the points is free);
+//   thread 0   replays the reference's sequential loop over the 32 losses (best-so-far, IsContinued) and reports how
+//              many hypotheses were really consumed; warp 0 rewinds the generator to exactly that point.
+// FindInliers + the relabelling loop (which stops at the last inlier, plane_extractor.cpp:500-507) become two
+// passes: the largest inlier pixel index, then "non-inlier before it -> 0".
+#include "refine.cuh"
+
+#include "exact_math.cuh"
+
+namespace dpx {
+namespace {
+
+constexpr int kRefThreads = 512;
+constexpr int kRefWarps = kRefThreads / 32;
+constexpr int kHyp = 32;  // hypotheses evaluated per round = lanes of a warp
+constexpr unsigned kFullMask = 0xffffffffu;
+
+struct RefShared {
+  uint32_t mt[kMtN];
+  uint32_t mt_bak[kMtN];
+  float model[kHyp][4];
+  unsigned loss[kHyp];
+  int draws_cum[kHyp];        // generator draws used up to and including hypothesis g
+  int rank[kHyp][3];          // sample ranks, ascending (std::set order)
+  long long pix[kHyp][3];     // their pixels
+  float best[4];
+  double bestloss;            // HUGE_VAL until a hypothesis has been accepted
+  int iteration, consumed, go_on;
+  int max_inlier_pix;
+  float4 stage[kRefWarps][32];
+};
+
+// ---- std::mt19937, executed by warp 0 (all lanes compute the same values; lane 0 owns the stores) ----------
+__device__ __forceinline__ void mt_twist_warp(uint32_t* mt, int lane) {
+  // new[i] = old[(i + 397) % 624] ^ f(old[i], old[i + 1]); entries i >= 227 read already updated entries,
+  // so the update runs in waves of 227 (dependency distance) with a warp barrier in between.
+  auto f = [](uint32_t a, uint32_t b) {
+    const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+  };
+  for (int base = 0; base < kMtN; base += 224) {  // 224 <= 227, multiple of 32
+    const int end = min(base + 224, kMtN);
+    uint32_t v[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const int i = base + k * 32 + lane;
+      if (i < end) {
+        const uint32_t nxt = mt[(i + 1) % kMtN];  // for i = 623 this is the already updated mt[0], as in the reference
+        v[k] = mt[(i + 397) % kMtN] ^ f(mt[i], nxt);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const int i = base + k * 32 + lane;
+      if (i < end) mt[i] = v[k];
+    }
+    __syncwarp();
+  }
+}
+
+// `idx` is the generator's position, held in a register by every lane of warp 0 (all lanes agree)
+__device__ __forceinline__ uint32_t mt_next_warp(RefShared& s, int lane, int& idx) {
+  if (idx >= kMtN) {
+    mt_twist_warp(s.mt, lane);
+    idx = 0;
+  }
+  uint32_t y = s.mt[idx++];
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= y >> 18;
+  return y;
+}
+
+// std::uniform_int_distribution<int>(0, n - 1)(gen) for a 32-bit generator, libstdc++ >= 11 (bits/uniform_int_dist.h,
+// _S_nd): Lemire's nearly divisionless method.  `draws` counts generator calls.
+__device__ __forceinline__ int uniform_below_warp(RefShared& s, int lane, int& idx, uint32_t n, int& draws) {
+  unsigned long long product = static_cast<unsigned long long>(mt_next_warp(s, lane, idx)) * n;
+  ++draws;
+  uint32_t low = static_cast<uint32_t>(product);
+  if (low < n) {
+    const uint32_t threshold = (0u - n) % n;
+    while (low < threshold) {
+      product = static_cast<unsigned long long>(mt_next_warp(s, lane, idx)) * n;
+      ++draws;
+      low = static_cast<uint32_t>(product);
+    }
+  }
+  return static_cast<int>(product >> 32);
+}
+
+struct LabelCells {
+  const int32_t* cells;  // the label's cells, ascending cell id
+  int count;             // number of cells
+};
+
+// The k-th pixel (image order) among the pixels of a label whose cells are `lc` (plane_extractor.cpp:473-478 builds
+// this list explicitly).  A cell row holding m of the label's cells contributes p image rows of m*p pixels each.
+__device__ __forceinline__ long long kth_pixel(const LabelCells& lc, int k, int p, int nh, int width) {
+  const int p2 = p * p;
+  const int t = k / p2;
+  const int r = lc.cells[t] / nh;  // cell row containing rank k
+  int s = t, e = t + 1;
+  while (s > 0 && lc.cells[s - 1] / nh == r) --s;
+  while (e < lc.count && lc.cells[e] / nh == r) ++e;
+  const int m = e - s;
+  const int kk = k - s * p2;
+  const int i = kk / (p * m), rem = kk - i * (p * m);
+  const int j = rem / p, xo = rem - j * p;
+  const int cell = lc.cells[s + j];
+  const int q = cell - r * nh;
+  return static_cast<long long>(r * p + i) * width + q * p + xo;
+}
+
+template <int LAYOUT>
+__device__ __forceinline__ void load_point(const float* xyz, long long n_points, long long pix, float& x, float& y, float& z) {
+  if (LAYOUT == kLayoutRowMajor) {
+    x = __ldg(xyz + 3 * pix); y = __ldg(xyz + 3 * pix + 1); z = __ldg(xyz + 3 * pix + 2);
+  } else {
+    x = __ldg(xyz + pix); y = __ldg(xyz + n_points + pix); z = __ldg(xyz + 2 * n_points + pix);
+  }
+}
+
+// PlaneEstimator::ComputeError (Plane.hpp:45-48): fp32, left to right
+__device__ __forceinline__ float plane_error(const float (&m)[4], float x, float y, float z) {
+  return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], x), __fmul_rn(m[1], y)), __fmul_rn(m[2], z)), m[3]);
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs args) {
+  __shared__ RefShared s;
+  const Geometry& g = args.geom;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int frame = blockIdx.x;
+  const int C = g.n_cells, p = g.patch, p2 = p * p, nh = g.nh;
+  const long long fc = static_cast<long long>(frame) * C;
+  const int nseg = args.tables.n_planes[frame];
+  if (nseg <= 0) return;  // no plane: nothing is labelled (plane_extractor.cpp:230-232)
+
+  const int32_t* cell_label = args.tables.cell_label + fc;
+  int32_t* lab_cells = args.tables.queue + fc;                               // [C] cells sorted by (label, cell id)
+  int* lab_end = reinterpret_cast<int*>(args.tables.pairs + 2 * fc);          // [nseg] end of each label's run
+  const float* xyz = args.xyz + static_cast<long long>(frame) * 3 * g.n_points;
+  int32_t* labels = args.labels + static_cast<long long>(frame) * g.n_points;
+  const double thr = static_cast<double>(args.threshold);      // SetParamThreshold(double) <- float config value
+  const double ratio = static_cast<double>(args.inliers_ratio);
+
+  // ---- labels_indices (plane_extractor.cpp:473-478), per cell instead of per pixel ---------------------
+  for (int i = tid; i < nseg; i += kRefThreads) lab_end[i] = 0;
+  for (int i = tid; i < kMtN; i += kRefThreads) s.mt[i] = args.mt_init[i];
+  int mt_idx = kMtN, mt_idx_bak = kMtN;  // meaningful in warp 0 only
+  __syncthreads();
+  for (int c = tid; c < C; c += kRefThreads) {
+    const int l = cell_label[c];
+    if (l > 0) atomicAdd(&lab_end[l - 1], 1);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    // exclusive scan of the counts -> run starts (kept as running cursors), then a stable fill in ascending cell id
+    int run = 0;
+    for (int b0 = 0; b0 < nseg; b0 += 32) {
+      const int i = b0 + lane;
+      const int cnt = i < nseg ? lab_end[i] : 0;
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (i < nseg) lab_end[i] = run + incl - cnt;
+      run += __shfl_sync(kFullMask, incl, 31);
+    }
+    __syncwarp();
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      const int c = c0 + lane;
+      const int l = c < C ? cell_label[c] : 0;
+      const unsigned act = __ballot_sync(kFullMask, l > 0);
+      if (l > 0) {
+        const unsigned grp = __match_any_sync(act, l);
+        const int leader = __ffs(grp) - 1;
+        int base = 0;
+        if (lane == leader) {
+          base = lab_end[l - 1];
+          lab_end[l - 1] = base + __popc(grp);
+        }
+        base = __shfl_sync(grp, base, leader);
+        lab_cells[base + __popc(grp & ((1u << lane) - 1u))] = c;
+      }
+      __syncwarp();
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+
+  // ---- one label after the other (plane_extractor.cpp:486-508) ----------------------------------------------
+  for (int L = 0; L < nseg; ++L) {
+    const int start = L ? lab_end[L - 1] : 0;
+    LabelCells lc;
+    lc.cells = lab_cells + start;
+    lc.count = lab_end[L] - start;
+    if (lc.count == 0) continue;  // labels_indices[label].size() == 0
+    const int n = lc.count * p2;
+
+    if (tid == 0) {
+      s.best[0] = s.best[1] = s.best[2] = s.best[3] = 0.f;  // Eigen::Vector4f::Zero()
+      s.bestloss = HUGE_VAL;
+      s.iteration = 0;
+      // IsContinued(0, N - HUGE_VAL, N): int(-inf) is INT_MIN on x86-64
+      s.go_on = (0 < args.max_iterations) && (static_cast<double>(INT_MIN) < ratio * n);
+    }
+    __syncthreads();
+
+    // ---- FindBest (RANSAC.hpp:25-51), 32 hypotheses per round -------------------------------------------------
+    while (s.go_on) {
+      if (warp == 0) {
+        // remember the generator, then draw the samples of 32 consecutive iterations (RANSAC.hpp:81-87)
+        for (int i = lane; i < kMtN; i += 32) s.mt_bak[i] = s.mt[i];
+        mt_idx_bak = mt_idx;
+        __syncwarp();
+        int draws = 0;
+        for (int h = 0; h < kHyp; ++h) {
+          int a = -1, b = -1, c = -1, cnt = 0;  // the std::set<int>, kept sorted
+          while (cnt < 3) {
+            const int v = uniform_below_warp(s, lane, mt_idx, static_cast<uint32_t>(n), draws);
+            if (v == a || v == b || v == c) continue;
+            if (cnt == 0) a = v;
+            else if (cnt == 1) { if (v < a) { b = a; a = v; } else b = v; }
+            else {
+              if (v < a) { c = b; b = a; a = v; }
+              else if (v < b) { c = b; b = v; }
+              else c = v;
+            }
+            ++cnt;
+          }
+          if (lane == 0) {
+            s.rank[h][0] = a; s.rank[h][1] = b; s.rank[h][2] = c;
+            s.draws_cum[h] = draws;
+          }
+        }
+      }
+      if (tid < kHyp) s.loss[tid] = 0;
+      __syncthreads();
+      if (tid < kHyp * 3) s.pix[tid / 3][tid % 3] = kth_pixel(lc, s.rank[tid / 3][tid % 3], p, nh, g.width);
+      __syncthreads();
+      if (tid < kHyp) {
+        // PlaneEstimator::ComputeModel (Plane.hpp:13-43), fp32 in the reference's expression order
+        float x0, y0, z0, x1, y1, z1, x2, y2, z2;
+        load_point<LAYOUT>(xyz, g.n_points, s.pix[tid][0], x0, y0, z0);
+        load_point<LAYOUT>(xyz, g.n_points, s.pix[tid][1], x1, y1, z1);
+        load_point<LAYOUT>(xyz, g.n_points, s.pix[tid][2], x2, y2, z2);
+        const f32 X0(x0), X1(x1), X2(x2), Y0(y0), Y1(y1), Y2(y2), Z0(z0), Z1(z1), Z2(z2);
+        const f32 D = X0 * Y1 - X1 * Y0 - X0 * Y2 + X2 * Y0 + X1 * Y2 - X2 * Y1;
+        const f32 a = (Z0 * (Y1 - Y2)) / D - (Z1 * (Y0 - Y2)) / D + (Z2 * (Y0 - Y1)) / D;
+        const f32 b = (Z1 * (X0 - X2)) / D - (Z0 * (X1 - X2)) / D - (Z2 * (X0 - X1)) / D;
+        const f32 d = (Z2 * (X0 * Y1 - X1 * Y0)) / D - (Z1 * (X0 * Y2 - X2 * Y0)) / D + (Z0 * (X1 * Y2 - X2 * Y1)) / D;
+        const f32 c(-1.0f);
+        // `sqrt(float)` in Plane.hpp:36 resolves to ::sqrt(double): double square root, rounded to float on assignment
+        const f32 l(__double2float_rn(__dsqrt_rn(static_cast<double>((a * a + b * b + c * c).v))));
+        s.model[tid][0] = (a / l).v; s.model[tid][1] = (b / l).v; s.model[tid][2] = (c / l).v; s.model[tid][3] = (d / l).v;
+      }
+      __syncthreads();
+      {
+        // EvaluateModel (RANSAC.hpp:89-98): lane g scores hypothesis g; loss += (fabs(error) >= threshold)
+        float m[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m[k] = s.model[lane][k];
+        unsigned loss = 0;
+        for (int e0 = warp * 32; e0 < n; e0 += kRefThreads) {
+          const int e = e0 + lane;
+          float x = 0.f, y = 0.f, z = 0.f;
+          if (e < n) {
+            const int t = e / p2, in = e - t * p2;
+            const int cell = lc.cells[t];
+            const int r = cell / nh, q = cell - r * nh;
+            const int i = in / p, j = in - i * p;
+            load_point<LAYOUT>(xyz, g.n_points, static_cast<long long>(r * p + i) * g.width + q * p + j, x, y, z);
+          }
+          s.stage[warp][lane] = make_float4(x, y, z, 0.f);
+          __syncwarp();
+          const int cnt = min(32, n - e0);
+          for (int k = 0; k < cnt; ++k) {
+            const float4 pt = s.stage[warp][k];
+            const double err = static_cast<double>(plane_error(m, pt.x, pt.y, pt.z));
+            loss += (::fabs(err) >= thr) ? 1u : 0u;
+          }
+          __syncwarp();
+        }
+        atomicAdd(&s.loss[lane], loss);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        // the reference's sequential loop over these hypotheses (RANSAC.hpp:33-46)
+        int consumed = 0;
+        bool go = true;
+        for (int h = 0; h < kHyp; ++h) {
+          const int inl = ::isinf(s.bestloss) ? INT_MIN : static_cast<int>(n - s.bestloss);
+          go = (s.iteration < args.max_iterations) && (static_cast<double>(inl) < ratio * n);
+          if (!go) break;
+          ++s.iteration;
+          ++consumed;
+          const double loss = static_cast<double>(s.loss[h]);
+          if (loss < s.bestloss) {
+            s.best[0] = s.model[h][0]; s.best[1] = s.model[h][1]; s.best[2] = s.model[h][2]; s.best[3] = s.model[h][3];
+            s.bestloss = loss;
+          }
+        }
+        if (go) {
+          const int inl = ::isinf(s.bestloss) ? INT_MIN : static_cast<int>(n - s.bestloss);
+          go = (s.iteration < args.max_iterations) && (static_cast<double>(inl) < ratio * n);
+        }
+        s.consumed = consumed;
+        s.go_on = go ? 1 : 0;
+      }
+      __syncthreads();
+      if (warp == 0 && s.consumed < kHyp) {
+        // rewind the generator to just after the last iteration the reference would have run
+        for (int i = lane; i < kMtN; i += 32) s.mt[i] = s.mt_bak[i];
+        mt_idx = mt_idx_bak;
+        __syncwarp();
+        const int redo = s.consumed > 0 ? s.draws_cum[s.consumed - 1] : 0;
+        for (int k = 0; k < redo; ++k) (void)mt_next_warp(s, lane, mt_idx);
+      }
+      __syncthreads();
+    }
+
+    // ---- FindInliers + relabelling (RANSAC.hpp:53-62, plane_extractor.cpp:498-507) ---------------------------
+    if (tid == 0) s.max_inlier_pix = -1;
+    __syncthreads();
+    float m[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m[k] = s.best[k];
+    for (int pass = 0; pass < 2; ++pass) {
+      const int last = s.max_inlier_pix;
+      if (pass == 1 && last < 0) break;  // no inlier at all: the relabelling loop never runs
+      int local_max = -1;
+      for (int e = tid; e < n; e += kRefThreads) {
+        const int t = e / p2, in = e - t * p2;
+        const int cell = lc.cells[t];
+        const int r = cell / nh, q = cell - r * nh;
+        const int i = in / p, j = in - i * p;
+        const long long pix = static_cast<long long>(r * p + i) * g.width + q * p + j;
+        float x, y, z;
+        load_point<LAYOUT>(xyz, g.n_points, pix, x, y, z);
+        const bool inlier = ::fabs(static_cast<double>(plane_error(m, x, y, z))) < thr;
+        if (pass == 0) {
+          if (inlier) local_max = max(local_max, static_cast<int>(pix));
+        } else if (!inlier && pix < last) {
+          labels[pix] = 0;  // points after the last inlier keep their label, as in the reference's loop
+        }
+      }
+      if (pass == 0) {
+        local_max = __reduce_max_sync(kFullMask, local_max);
+        if (lane == 0 && local_max >= 0) atomicMax(&s.max_inlier_pix, local_max);
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+void mt19937_default_state(uint32_t out[kMtN]) {
+  out[0] = 5489u;
+  for (int i = 1; i < kMtN; ++i) out[i] = 1812433253u * (out[i - 1] ^ (out[i - 1] >> 30)) + static_cast<uint32_t>(i);
+}
+
+cudaError_t launch_refine(const RefineArgs& args, cudaStream_t stream) {
+  if (args.n_frames == 0 || args.geom.n_cells == 0) return cudaSuccess;
+  if (args.layout == kLayoutRowMajor)
+    refine_kernel<kLayoutRowMajor><<<args.n_frames, kRefThreads, 0, stream>>>(args);
+  else
+    refine_kernel<kLayoutColMajor><<<args.n_frames, kRefThreads, 0, stream>>>(args);
+  return cudaGetLastError();
+}
+
+}  // namespace dpx

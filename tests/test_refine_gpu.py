@@ -1,0 +1,66 @@
+"""RANSAC refinement (ransacRefinement=1) on the GPU against the oracle: plane_extractor.cpp:472-509,
+libs/rtl RANSAC.hpp / Plane.hpp, std::mt19937 + libstdc++ uniform_int_distribution.  The bar is bit-exact labels:
+the random stream, the sample order, the fp32 model arithmetic and the early-exit rule all have to agree."""
+import time
+
+import numpy as np
+import pytest
+
+from conftest import frame_cloud, to_oracle_cfg
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["tum", "icl"])
+@pytest.mark.parametrize("layout", ["rowmajor", "colmajor"])
+def test_shipped_frames_refined_labels_identical(oracle_mod, name, layout):
+    from deplex_b200 import Config, PlaneExtractor
+    xyz, ini = frame_cloud(name)
+    cfg = Config(ini, ransac_refinement=1)   # shipped ini: threshold 1, ratio 0.15, 1000 iterations
+    host = xyz if layout == "rowmajor" else np.asfortranarray(xyz)
+    labels = PlaneExtractor(480, 640, cfg).process(host)
+    ref = oracle_mod.process(480, 640, to_oracle_cfg(oracle_mod, cfg), xyz)
+    coarse = PlaneExtractor(480, 640, Config(ini)).process(host)
+    assert ((labels == 0) | (labels == coarse)).all()      # refinement only removes labels
+    assert (labels != coarse).any()                          # ... and it does remove some
+    assert np.array_equal(labels, ref), f"{(labels != ref).sum()} pixels differ"
+
+
+@pytest.mark.parametrize("threshold,ratio,iters", [(1.0, 0.15, 1000), (25.0, 0.9, 40), (3.0, 0.5, 7), (1.0, 0.9, 0)])
+def test_refinement_parameters_and_batches(oracle_mod, threshold, ratio, iters):
+    """Different early-exit regimes (immediate hit, iteration cap in the middle of a 32-hypothesis round, zero
+    iterations), several frames per batch: every frame restarts the generator, like one process() call each."""
+    from deplex_b200 import Config, PlaneExtractor, synth, LAYOUT_ROWMAJOR
+    h, w, F = 480, 640, 4
+    cfg = Config(ransac_refinement=1, ransac_threshold=threshold, ransac_inliers_ratio=ratio, ransac_max_iterations=iters)
+    batch = synth.make_batch(h, w, 4242, F, "rowmajor")
+    labels = PlaneExtractor(h, w, cfg, max_batch=F).process_batch_host(batch, LAYOUT_ROWMAJOR)
+    ocfg = to_oracle_cfg(oracle_mod, cfg)
+    for f in range(F):
+        ref = oracle_mod.process(h, w, ocfg, batch[f])
+        assert np.array_equal(labels[f], ref), f"frame {f}: {(labels[f] != ref).sum()} pixels differ"
+
+
+def test_refinement_mse_not_worse():
+    """cpp/tests/test_refinement.cpp:43-75 on the GPU path: the MSE of the points labelled 1 does not grow."""
+    from deplex_b200 import Config, PlaneExtractor
+    for name in ("tum", "icl"):
+        xyz, ini = frame_cloud(name)
+
+        def plane_mse(cfg):
+            labels = PlaneExtractor(480, 640, cfg).process(xyz)
+            pts = xyz[labels == 1].astype(np.float64)
+            return np.linalg.eigvalsh(np.cov(pts.T, bias=True))[0]
+
+        assert plane_mse(Config(ini, ransac_refinement=1)) <= plane_mse(Config(ini))
+
+
+def test_refinement_fine_grid_and_fhd(oracle_mod):
+    from deplex_b200 import Config, PlaneExtractor, synth
+    for (h, w, patch) in ((480, 640, 4), (1080, 1920, 10)):
+        cfg = Config(patch_size=patch, ransac_refinement=1, ransac_threshold=4.0, ransac_inliers_ratio=0.6, ransac_max_iterations=50)
+        xyz = synth.make_cloud(h, w, 77)
+        t0 = time.time()
+        labels = PlaneExtractor(h, w, cfg).process(xyz)
+        ref = oracle_mod.process(h, w, to_oracle_cfg(oracle_mod, cfg), xyz)
+        assert np.array_equal(labels, ref), f"{h}x{w}/p{patch}: {(labels != ref).sum()} pixels differ ({time.time() - t0:.1f}s)"
