@@ -13,7 +13,8 @@ STAGE_NAMES = ("cell_stats", "region_grow", "labeling", "refine")
 # every symbol include/deplex_b200.h declares (checked by tests/test_capi_cpu.py)
 EXPORTS = (
     "dpx_config_default", "dpx_config_load_ini", "dpx_create", "dpx_destroy", "dpx_last_error", "dpx_get_info",
-    "dpx_process_host", "dpx_process_batch_host", "dpx_process_batch_device", "dpx_get_cells", "dpx_get_planes",
+    "dpx_process_host", "dpx_process_batch_host", "dpx_process_batch_device", "dpx_process_depth_batch_host",
+    "dpx_process_depth_batch_device", "dpx_get_cells", "dpx_get_planes",
     "dpx_set_profiling", "dpx_get_stage_ms", "dpx_get_region_profile", "dpx_kernel_launches", "dpx_host_alloc", "dpx_host_free", "dpx_version",
 )
 
@@ -29,6 +30,10 @@ class dpx_config(C.Structure):
         ("ransac_refinement", C.c_int32), ("ransac_max_iterations", C.c_int32),
         ("ransac_threshold", C.c_float), ("ransac_inliers_ratio", C.c_float),
     ]
+
+
+class dpx_intrinsics(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float)]
 
 
 class dpx_info(C.Structure):
@@ -76,6 +81,8 @@ def load():
         "dpx_process_host": (C.c_int, [vp, vp, i64, C.c_int, vp]),
         "dpx_process_batch_host": (C.c_int, [vp, vp, i32, C.c_int, vp]),
         "dpx_process_batch_device": (C.c_int, [vp, vp, i32, C.c_int, vp, vp]),
+        "dpx_process_depth_batch_host": (C.c_int, [vp, vp, i32, C.POINTER(dpx_intrinsics), vp]),
+        "dpx_process_depth_batch_device": (C.c_int, [vp, vp, i32, C.POINTER(dpx_intrinsics), vp, vp]),
         "dpx_get_cells": (C.c_int, [vp, i32, C.POINTER(dpx_cell), i32]),
         "dpx_get_planes": (C.c_int, [vp, i32, C.POINTER(dpx_plane), i32, C.POINTER(i32)]),
         "dpx_set_profiling": (C.c_int, [vp, i32]),

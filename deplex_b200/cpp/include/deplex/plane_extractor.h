@@ -74,6 +74,10 @@ class PlaneExtractor {
   void processBatchDevice(float const* d_points, int32_t n_frames, PointLayout layout, int32_t* d_labels,
                           void* cuda_stream = nullptr);
 
+  /** Raw uint16 depth frames + pinhole intrinsics instead of points: DepthImage::toPointCloud
+   *  (depth_image.cpp:55-78) is evaluated on the device, fused into the first kernel where the geometry allows. */
+  void processDepthBatch(uint16_t const* depth, int32_t n_frames, float fx, float fy, float cx, float cy, int32_t* labels);
+
   /** Planes of frame `frame` of the last call (post-merge statistics). */
   std::vector<PlaneParams> planes(int32_t frame = 0);
 

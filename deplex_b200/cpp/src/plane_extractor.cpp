@@ -63,6 +63,12 @@ void PlaneExtractor::processBatchDevice(float const* d_points, int32_t n_frames,
   impl_->check(dpx_process_batch_device(impl_->ex, d_points, n_frames, static_cast<dpx_layout>(layout), d_labels, cuda_stream));
 }
 
+void PlaneExtractor::processDepthBatch(uint16_t const* depth, int32_t n_frames, float fx, float fy, float cx, float cy,
+                                       int32_t* labels) {
+  dpx_intrinsics k{fx, fy, cx, cy};
+  impl_->check(dpx_process_depth_batch_host(impl_->ex, depth, n_frames, &k, labels));
+}
+
 std::vector<PlaneParams> PlaneExtractor::planes(int32_t frame) {
   dpx_info info;
   impl_->check(dpx_get_info(impl_->ex, &info));

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "cell_stats.cuh"
+#include "depth_points.cuh"
 #include "error_state.h"
 #include "labeling.cuh"
 #include "refine.cuh"
@@ -47,6 +48,9 @@ struct dpx_extractor {
   // host-pointer path: double-buffered staging + three streams
   int host_chunk = 0;
   float* d_xyz[2] = {nullptr, nullptr};
+  uint16_t* d_depth[2] = {nullptr, nullptr};  // staging of the raw-depth host path
+  float* d_conv = nullptr;                    // points generated from depth when the fused path cannot run
+  size_t d_conv_frames = 0;
   int32_t* d_lab[2] = {nullptr, nullptr};
   cudaStream_t s_h2d = nullptr, s_run = nullptr, s_d2h = nullptr;
   cudaEvent_t e_h2d[2] = {nullptr, nullptr}, e_run[2] = {nullptr, nullptr}, e_d2h[2] = {nullptr, nullptr};
@@ -119,12 +123,38 @@ size_t carve_tables(const Geometry& g, int max_batch, bool bins_in_smem, char* b
 }
 
 // The three stages on one stream (plane_extractor.cpp:195-283).
-dpx_status run_stages(dpx_extractor* ex, const float* d_xyz, int n_frames, int layout, int32_t* d_labels, cudaStream_t st) {
+// d_xyz + layout, or (layout == kLayoutDepth16) d_depth + pin
+dpx_status run_stages(dpx_extractor* ex, const float* d_xyz, int n_frames, int layout, int32_t* d_labels, cudaStream_t st,
+                      const uint16_t* d_depth = nullptr, const dpx_intrinsics* pin = nullptr) {
   const bool prof = ex->profiling;
   if (prof) DPX_CUDA(ex, cudaEventRecord(ex->e_stage[0], st));
+  Pinhole ph{};
+  if (layout == kLayoutDepth16 && ex->geom.n_cells > 0) {
+    ph.fx = pin->fx; ph.fy = pin->fy; ph.cx = pin->cx; ph.cy = pin->cy;
+    CellStatsArgs probe{};
+    probe.depth = d_depth;
+    probe.geom = ex->geom;
+    probe.force_tile_kernel = ex->force_tile_kernel;
+    if (ex->cfg.ransac_refinement || !cell_stats_depth_eligible(probe)) {
+      // materialise the points once (row-major) and continue on the ordinary path
+      if (ex->d_conv_frames < static_cast<size_t>(n_frames)) {
+        if (ex->d_conv) DPX_CUDA(ex, cudaFree(ex->d_conv));
+        ex->d_conv = nullptr;
+        ex->d_conv_frames = 0;
+        DPX_CUDA(ex, cudaMalloc(&ex->d_conv, static_cast<size_t>(ex->max_batch) * ex->geom.n_points * 3 * sizeof(float)));
+        ex->d_conv_frames = static_cast<size_t>(ex->max_batch);
+      }
+      DPX_CUDA(ex, launch_depth_to_points(d_depth, n_frames, ex->geom, ph, ex->d_conv, st));
+      ++ex->launches;
+      d_xyz = ex->d_conv;
+      layout = kLayoutRowMajor;
+    }
+  }
   if (ex->geom.n_cells > 0) {
     CellStatsArgs ca{};
     ca.xyz = d_xyz;
+    ca.depth = d_depth;
+    ca.pin = ph;
     ca.n_frames = n_frames;
     ca.layout = layout;
     ca.tile_cells = ex->tile_cells;
@@ -189,7 +219,6 @@ dpx_status ensure_host_path(dpx_extractor* ex) {
   ex->host_chunk = std::max(1, std::min(ex->max_batch, 32));
   const size_t np = static_cast<size_t>(ex->geom.n_points);
   for (int i = 0; i < 2; ++i) {
-    DPX_CUDA(ex, cudaMalloc(&ex->d_xyz[i], std::max<size_t>(16, np * 3 * sizeof(float) * ex->host_chunk)));
     DPX_CUDA(ex, cudaMalloc(&ex->d_lab[i], std::max<size_t>(16, np * sizeof(int32_t) * ex->host_chunk)));
     DPX_CUDA(ex, cudaEventCreateWithFlags(&ex->e_h2d[i], cudaEventDisableTiming));
     DPX_CUDA(ex, cudaEventCreateWithFlags(&ex->e_run[i], cudaEventDisableTiming));
@@ -334,6 +363,7 @@ void dpx_destroy(dpx_extractor* ex) {
   for (int i = 0; i < 2; ++i) {
     if (ex->d_xyz[i]) cudaFree(ex->d_xyz[i]);
     if (ex->d_lab[i]) cudaFree(ex->d_lab[i]);
+    if (ex->d_depth[i]) cudaFree(ex->d_depth[i]);
     if (ex->e_h2d[i]) cudaEventDestroy(ex->e_h2d[i]);
     if (ex->e_run[i]) cudaEventDestroy(ex->e_run[i]);
     if (ex->e_d2h[i]) cudaEventDestroy(ex->e_d2h[i]);
@@ -346,6 +376,7 @@ void dpx_destroy(dpx_extractor* ex) {
   if (ex->scratch) cudaFree(ex->scratch);
   if (ex->region_prof) cudaFree(ex->region_prof);
   if (ex->mt_init) cudaFree(ex->mt_init);
+  if (ex->d_conv) cudaFree(ex->d_conv);
   delete ex;
 }
 
@@ -377,32 +408,36 @@ dpx_status dpx_process_batch_device(dpx_extractor* ex, const float* d_xyz, int32
   return run_stages(ex, d_xyz, n_frames, layout, d_labels, static_cast<cudaStream_t>(cuda_stream));
 }
 
-dpx_status dpx_process_batch_host(dpx_extractor* ex, const float* xyz, int32_t n_frames, dpx_layout layout, int32_t* labels) {
-  if (!ex) return DPX_ERR_ARGUMENT;
-  if (n_frames < 0) return fail(ex, DPX_ERR_ARGUMENT, "negative n_frames");
-  if (layout != DPX_LAYOUT_COLMAJOR && layout != DPX_LAYOUT_ROWMAJOR) return fail(ex, DPX_ERR_ARGUMENT, "unknown layout");
-  if (n_frames == 0 || ex->geom.n_points == 0) return DPX_OK;
-  if (!xyz || !labels) return fail(ex, DPX_ERR_ARGUMENT, "null host pointer");
+namespace {
+// Host pointers: chunks of host_chunk frames, H2D / kernels / D2H on three streams, double-buffered.
+dpx_status process_host_impl(dpx_extractor* ex, const void* src, size_t bytes_per_frame, int32_t n_frames, int layout,
+                             const dpx_intrinsics* pin, int32_t* labels) {
   DeviceGuard guard(ex->device);
   if (!guard.ok) return fail(ex, DPX_ERR_CUDA, "cudaSetDevice failed");
   dpx_status st = ensure_host_path(ex);
   if (st != DPX_OK) return st;
-
+  const bool is_depth = layout == kLayoutDepth16;
   const size_t np = static_cast<size_t>(ex->geom.n_points);
   const int chunk = ex->host_chunk;
+  if (is_depth && !ex->d_depth[0])
+    for (int i = 0; i < 2; ++i) DPX_CUDA(ex, cudaMalloc(&ex->d_depth[i], std::max<size_t>(16, np * sizeof(uint16_t) * chunk)));
+  if (!is_depth && !ex->d_xyz[0])
+    for (int i = 0; i < 2; ++i) DPX_CUDA(ex, cudaMalloc(&ex->d_xyz[i], std::max<size_t>(16, np * 3 * sizeof(float) * chunk)));
   int n_chunks = 0;
   for (int f0 = 0; f0 < n_frames; f0 += chunk, ++n_chunks) {
     const int slot = n_chunks & 1;
     const int nf = std::min(chunk, n_frames - f0);
+    void* d_in = is_depth ? static_cast<void*>(ex->d_depth[slot]) : static_cast<void*>(ex->d_xyz[slot]);
     // H2D into slot: the kernels of the chunk that used this slot two rounds ago must be done reading it
     if (n_chunks >= 2) DPX_CUDA(ex, cudaStreamWaitEvent(ex->s_h2d, ex->e_run[slot], 0));
-    DPX_CUDA(ex, cudaMemcpyAsync(ex->d_xyz[slot], xyz + static_cast<size_t>(f0) * np * 3, np * 3 * sizeof(float) * nf,
-                                 cudaMemcpyHostToDevice, ex->s_h2d));
+    DPX_CUDA(ex, cudaMemcpyAsync(d_in, static_cast<const char*>(src) + static_cast<size_t>(f0) * bytes_per_frame,
+                                 bytes_per_frame * nf, cudaMemcpyHostToDevice, ex->s_h2d));
     DPX_CUDA(ex, cudaEventRecord(ex->e_h2d[slot], ex->s_h2d));
     // kernels: need the input, and the label slot must have been drained
     DPX_CUDA(ex, cudaStreamWaitEvent(ex->s_run, ex->e_h2d[slot], 0));
     if (n_chunks >= 2) DPX_CUDA(ex, cudaStreamWaitEvent(ex->s_run, ex->e_d2h[slot], 0));
-    st = run_stages(ex, ex->d_xyz[slot], nf, layout, ex->d_lab[slot], ex->s_run);
+    st = is_depth ? run_stages(ex, nullptr, nf, layout, ex->d_lab[slot], ex->s_run, ex->d_depth[slot], pin)
+                  : run_stages(ex, ex->d_xyz[slot], nf, layout, ex->d_lab[slot], ex->s_run);
     if (st != DPX_OK) return st;
     DPX_CUDA(ex, cudaEventRecord(ex->e_run[slot], ex->s_run));
     // D2H
@@ -415,6 +450,37 @@ dpx_status dpx_process_batch_host(dpx_extractor* ex, const float* xyz, int32_t n
   DPX_CUDA(ex, cudaStreamSynchronize(ex->s_run));
   DPX_CUDA(ex, cudaStreamSynchronize(ex->s_h2d));
   return DPX_OK;
+}
+}  // namespace
+
+dpx_status dpx_process_batch_host(dpx_extractor* ex, const float* xyz, int32_t n_frames, dpx_layout layout, int32_t* labels) {
+  if (!ex) return DPX_ERR_ARGUMENT;
+  if (n_frames < 0) return fail(ex, DPX_ERR_ARGUMENT, "negative n_frames");
+  if (layout != DPX_LAYOUT_COLMAJOR && layout != DPX_LAYOUT_ROWMAJOR) return fail(ex, DPX_ERR_ARGUMENT, "unknown layout");
+  if (n_frames == 0 || ex->geom.n_points == 0) return DPX_OK;
+  if (!xyz || !labels) return fail(ex, DPX_ERR_ARGUMENT, "null host pointer");
+  return process_host_impl(ex, xyz, static_cast<size_t>(ex->geom.n_points) * 3 * sizeof(float), n_frames, layout, nullptr, labels);
+}
+
+dpx_status dpx_process_depth_batch_host(dpx_extractor* ex, const uint16_t* depth, int32_t n_frames, const dpx_intrinsics* k,
+                                        int32_t* labels) {
+  if (!ex) return DPX_ERR_ARGUMENT;
+  if (n_frames < 0) return fail(ex, DPX_ERR_ARGUMENT, "negative n_frames");
+  if (n_frames == 0 || ex->geom.n_points == 0) return DPX_OK;
+  if (!depth || !labels || !k) return fail(ex, DPX_ERR_ARGUMENT, "null pointer");
+  return process_host_impl(ex, depth, static_cast<size_t>(ex->geom.n_points) * sizeof(uint16_t), n_frames, kLayoutDepth16, k, labels);
+}
+
+dpx_status dpx_process_depth_batch_device(dpx_extractor* ex, const uint16_t* d_depth, int32_t n_frames, const dpx_intrinsics* k,
+                                          int32_t* d_labels, void* cuda_stream) {
+  if (!ex) return DPX_ERR_ARGUMENT;
+  if (n_frames < 0 || n_frames > ex->max_batch)
+    return fail(ex, DPX_ERR_ARGUMENT, "n_frames " + std::to_string(n_frames) + " exceeds max_batch " + std::to_string(ex->max_batch));
+  if (n_frames == 0 || ex->geom.n_points == 0) return DPX_OK;
+  if (!d_depth || !d_labels || !k) return fail(ex, DPX_ERR_ARGUMENT, "null pointer");
+  DeviceGuard guard(ex->device);
+  if (!guard.ok) return fail(ex, DPX_ERR_CUDA, "cudaSetDevice failed");
+  return run_stages(ex, nullptr, n_frames, kLayoutDepth16, d_labels, static_cast<cudaStream_t>(cuda_stream), d_depth, k);
 }
 
 dpx_status dpx_process_host(dpx_extractor* ex, const float* xyz, int64_t n_points, dpx_layout layout, int32_t* labels) {

@@ -195,23 +195,28 @@ struct CellWalkScalar {
 
 template <int LAYOUT, int P>
 struct WalkFor {
-  using type = typename std::conditional<P % 2 == 0, CellWalkPacked<LAYOUT, P>, CellWalkScalar<LAYOUT, P>>::type;
+  // raw depth generates its points in registers and feeds them in the column-major pairing
+  static constexpr int kWalkLayout = LAYOUT == kLayoutDepth16 ? kLayoutColMajor : LAYOUT;
+  using type = typename std::conditional<P % 2 == 0, CellWalkPacked<kWalkLayout, P>, CellWalkScalar<kWalkLayout, P>>::type;
 };
 
 // where a warp's tile starts in the input, and where its cells go
 struct TileDesc {
-  const float* src;     // first point of the tile's first row (component 0 for column-major input)
+  const char* src;      // first sample of the tile's first row (component 0 for column-major input)
   long long cell0;      // frame * n_cells + strip * nh + c0
-  unsigned seg_bytes;   // bytes of one component of one row segment (cnt * P * 4)
+  unsigned seg_bytes;   // bytes of one component of one row segment
   int cnt;              // cells in the tile (32, fewer at the right edge); 0 = past the end
+  int col0, row0;       // image column / row of the tile's first pixel
 };
 
 template <int LAYOUT, int P, int WARPS, int RING>
 __global__ void __launch_bounds__(WARPS * 32, 1) cell_stats_stream_kernel(const CellStatsArgs args) {
+  static_assert(LAYOUT != kLayoutDepth16 || P % 2 == 0, "the fused depth path needs the packed walk");
   constexpr int RPS = rows_per_slot(P);
   constexpr int SPT = P / RPS;               // stages (slots) per tile
   constexpr int TW = 32 * P;                 // points per staged row
   constexpr int SLOT_FLOATS = RPS * TW * 3;
+  constexpr int ELEM = LAYOUT == kLayoutDepth16 ? 2 : 4;  // bytes per staged sample
   extern __shared__ float4 smem_f4[];
   __shared__ __align__(8) uint64_t bars[WARPS * RING];
 
@@ -233,7 +238,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cell_stats_stream_kernel(const 
   const long long total_warps = static_cast<long long>(gridDim.x) * WARPS;
   if (gw >= total_tiles) return;
   const long long my_tiles = (total_tiles - gw + total_warps - 1) / total_warps;
-  const long long row_stride = (LAYOUT == kLayoutRowMajor) ? 3LL * g.width : g.width;  // floats between image rows
+  // bytes between image rows / between the component planes of a column-major cloud
+  const long long row_bytes = static_cast<long long>(g.width) * (LAYOUT == kLayoutRowMajor ? 12 : ELEM);
+  const long long plane_bytes = g.n_points * 4;
+  const char* base = LAYOUT == kLayoutDepth16 ? reinterpret_cast<const char*>(args.depth) : reinterpret_cast<const char*>(args.xyz);
+  const long long frame_bytes = g.n_points * (LAYOUT == kLayoutDepth16 ? 2 : 12);
 
   // tile n of this warp (the divisions run once per tile, not once per stage)
   auto locate = [&](long long n, TileDesc& d) {
@@ -248,26 +257,33 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cell_stats_stream_kernel(const 
     const long long frame = tile / g.nv;
     const int c0 = tix * 32;
     d.cnt = min(32, g.nh - c0);
-    d.seg_bytes = static_cast<unsigned>(d.cnt) * P * 4;
+    d.seg_bytes = static_cast<unsigned>(d.cnt) * P * ELEM;
     d.cell0 = frame * g.n_cells + static_cast<long long>(strip) * g.nh + c0;
+    d.col0 = c0 * P;
+    d.row0 = strip * P;
     const long long px0 = static_cast<long long>(strip) * P * g.width + static_cast<long long>(c0) * P;
-    d.src = args.xyz + frame * 3 * g.n_points + (LAYOUT == kLayoutRowMajor ? 3 * px0 : px0);
+    d.src = base + frame * frame_bytes + px0 * (LAYOUT == kLayoutRowMajor ? 12 : ELEM);
   };
   // lane 0: arm the slot's mbarrier and issue the bulk copies of stage `st` of tile `d`
   auto issue = [&](const TileDesc& d, int st, int slot) {
     if (d.cnt == 0 || lane != 0) return;
-    float* dst = ring + slot * SLOT_FLOATS;
-    const float* src = d.src + static_cast<long long>(st) * RPS * row_stride;
-    mbar_expect_tx(bar + slot, d.seg_bytes * 3 * RPS);
+    char* dst = reinterpret_cast<char*>(ring + slot * SLOT_FLOATS);
+    const char* src = d.src + static_cast<long long>(st) * RPS * row_bytes;
     if (LAYOUT == kLayoutRowMajor) {
+      mbar_expect_tx(bar + slot, d.seg_bytes * 3 * RPS);
 #pragma unroll
-      for (int rr = 0; rr < RPS; ++rr) bulk_g2s(dst + rr * TW * 3, src + rr * row_stride, d.seg_bytes * 3, bar + slot, policy);
-    } else {
+      for (int rr = 0; rr < RPS; ++rr) bulk_g2s(dst + rr * TW * 12, src + rr * row_bytes, d.seg_bytes * 3, bar + slot, policy);
+    } else if (LAYOUT == kLayoutColMajor) {
+      mbar_expect_tx(bar + slot, d.seg_bytes * 3 * RPS);
 #pragma unroll
       for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int rr = 0; rr < RPS; ++rr)
-          bulk_g2s(dst + (a * RPS + rr) * TW, src + a * g.n_points + rr * row_stride, d.seg_bytes, bar + slot, policy);
+          bulk_g2s(dst + (a * RPS + rr) * TW * 4, src + a * plane_bytes + rr * row_bytes, d.seg_bytes, bar + slot, policy);
+    } else {
+      mbar_expect_tx(bar + slot, d.seg_bytes * RPS);
+#pragma unroll
+      for (int rr = 0; rr < RPS; ++rr) bulk_g2s(dst + rr * TW * 2, src + rr * row_bytes, d.seg_bytes, bar + slot, policy);
     }
   };
 
@@ -298,7 +314,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) cell_stats_stream_kernel(const 
       const float* blk = ring + slot * SLOT_FLOATS;
       if (lane < cur.cnt) {
 #pragma unroll
-        for (int rr = 0; rr < RPS; ++rr) walk.row(st * RPS + rr, blk, TW, RPS, rr, lane, args.thr.depth_discontinuity_threshold);
+        for (int rr = 0; rr < RPS; ++rr) {
+          if constexpr (LAYOUT == kLayoutDepth16) {
+            walk.row_depth(st * RPS + rr, reinterpret_cast<const uint16_t*>(blk), TW, rr, lane,
+                           args.thr.depth_discontinuity_threshold, static_cast<float>(cur.col0 + lane * P),
+                           static_cast<float>(cur.row0 + st * RPS + rr), args.pin);
+          } else {
+            walk.row(st * RPS + rr, blk, TW, RPS, rr, lane, args.thr.depth_discontinuity_threshold);
+          }
+        }
       }
       __syncwarp();        // every lane is done reading the slot ...
       issue_next(slot);    // ... before the async proxy refills it
@@ -364,10 +388,15 @@ template <int LAYOUT>
 bool launch_stream(const CellStatsArgs& a, cudaStream_t st, cudaError_t* err) {
   switch (a.geom.patch) {
     case 4: *err = launch_stream_p<LAYOUT, 4>(a, st); return true;
-    case 5: *err = launch_stream_p<LAYOUT, 5>(a, st); return true;
     case 6: *err = launch_stream_p<LAYOUT, 6>(a, st); return true;
     case 8: *err = launch_stream_p<LAYOUT, 8>(a, st); return true;
     case 10: *err = launch_stream_p<LAYOUT, 10>(a, st); return true;
+    case 5:
+      if constexpr (LAYOUT != kLayoutDepth16) {
+        *err = launch_stream_p<LAYOUT, 5>(a, st);
+        return true;
+      }
+      return false;
     default: return false;
   }
 }
@@ -396,10 +425,27 @@ bool cell_stats_stream_eligible(const CellStatsArgs& a) {
   return true;
 }
 
+bool cell_stats_depth_eligible(const CellStatsArgs& a) {
+  const Geometry& g = a.geom;
+  const int p = g.patch;
+  if (a.force_tile_kernel || !(p == 4 || p == 6 || p == 8 || p == 10)) return false;
+  // 2-byte samples: rows, frames and row segments must start on 16-byte boundaries and be multiples of 16 bytes
+  if (reinterpret_cast<uintptr_t>(a.depth) % 16 != 0 || g.width % 8 != 0 || g.n_points % 8 != 0) return false;
+  const int tail = g.nh % 32;
+  if ((tail * p) % 8 != 0) return false;
+  return true;
+}
+
 cudaError_t launch_cell_stats(const CellStatsArgs& args_in, cudaStream_t stream) {
   CellStatsArgs a = args_in;
   const Geometry& g = a.geom;
   if (g.n_cells == 0 || a.n_frames == 0) return cudaSuccess;
+  if (a.layout == kLayoutDepth16) {
+    if (!cell_stats_depth_eligible(a)) return cudaErrorInvalidValue;  // the caller converts to points instead
+    a.tiles_per_strip = (g.nh + 31) / 32;
+    cudaError_t err = cudaSuccess;
+    return launch_stream<kLayoutDepth16>(a, stream, &err) ? err : cudaErrorInvalidValue;
+  }
   if (cell_stats_stream_eligible(a)) {
     a.tiles_per_strip = (g.nh + 31) / 32;
     cudaError_t err = cudaSuccess;

@@ -7,7 +7,9 @@ namespace dpx {
 constexpr int kCellStatsThreads = 128;
 
 struct CellStatsArgs {
-  const float* xyz;  // device, n_frames organized clouds
+  const float* xyz;  // device, n_frames organized clouds (layouts 0/1)
+  const uint16_t* depth;  // device, n_frames raw depth images (layout kLayoutDepth16)
+  Pinhole pin;            // intrinsics for kLayoutDepth16
   int n_frames;
   int layout;
   int tile_cells;       // cells staged per CTA (from cell_stats_tile_cells)
@@ -23,5 +25,7 @@ struct CellStatsArgs {
 
 int cell_stats_tile_cells(int patch, int nh);
 cudaError_t launch_cell_stats(const CellStatsArgs& args, cudaStream_t stream);
+// whether the fused depth -> points path of the streaming kernel can take this geometry / pointer
+bool cell_stats_depth_eligible(const CellStatsArgs& args);
 
 }  // namespace dpx

@@ -67,6 +67,44 @@ struct CellWalkPacked {
     hprev = vprev = 0.f;
   }
 
+  // One pair of consecutive points (k, k + 1) of image row i: everything order-sensitive happens here.
+  // l0/l1/l2 are the same six values in the pairing of the accumulators (see s0/s1/s2 above).
+  __device__ __forceinline__ void pair(int i, int jj, float xe, float ye, float ze, float xo, float yo, float zo, u64 l0,
+                                       u64 l1, u64 l2, float disc_thr) {
+    const int k = i * P + 2 * jj;  // even point of the pair; k + 1 is in the same row and the same region
+    if (k == 0) { first[0] = xe; first[1] = ye; first[2] = ze; }
+    if (k + 1 == N - 1) { last[0] = xo; last[1] = yo; last[2] = zo; }
+    // X^T X chains, point k then point k + 1 (cell_segment_stat.cpp:32)
+    vA = add2(pk2(__fmul_rn(xe, xe), __fmul_rn(xe, ye)), vA);
+    vB = add2(pk2(__fmul_rn(xe, ze), __fmul_rn(ye, ye)), vB);
+    vC = add2(pk2(__fmul_rn(ye, ze), __fmul_rn(ze, ze)), vC);
+    vA = add2(pk2(__fmul_rn(xo, xo), __fmul_rn(xo, yo)), vA);
+    vB = add2(pk2(__fmul_rn(xo, zo), __fmul_rn(yo, yo)), vB);
+    vC = add2(pk2(__fmul_rn(yo, zo), __fmul_rn(zo, zo)), vC);
+    // column sums (cell_segment_stat.cpp:31)
+    if (k < kA2) {
+      const int m = (k & 7) >> 1;
+      s0[m] = add2(s0[m], l0); s1[m] = add2(s1[m], l1); s2[m] = add2(s2[m], l2);
+    } else {
+      const int m = (k - kA2) >> 1;
+      r0[m] = l0; r1[m] = l1; r2[m] = l2;
+    }
+    // hasValidPoints (cell_segment.cpp:57-60)
+    vv = add2(vv, pk2(valid_f(ze), valid_f(zo)));
+    // isHorizontalContinuous: indices [N/2, N/2 + P) = row P/2 (cell_segment.cpp:62-76)
+    if (i == P / 2) {
+      if (jj == 0) hprev = ze;
+      scan_step(ze, hprev, hcnt, disc_thr);
+      scan_step(zo, hprev, hcnt, disc_thr);
+    }
+    // isVerticalContinuous: column P/2 of every row (cell_segment.cpp:78-91)
+    if (2 * jj == P / 2 || 2 * jj + 1 == P / 2) {
+      const float zc = (2 * jj == P / 2) ? ze : zo;
+      if (i == 0) vprev = zc;
+      scan_step(zc, vprev, vcnt, disc_thr);
+    }
+  }
+
   // Consume image row i (compile-time after unrolling) of cell `t` from a staged block.
   // Row-major block: blk[(rr * tw + col) * 3 + a]; column-major block: blk[(a * rows + rr) * tw + col].
   __device__ __forceinline__ void row(int i, const float* blk, int tw, int rows, int rr, int t, float disc_thr) {
@@ -82,7 +120,6 @@ struct CellWalkPacked {
     }
 #pragma unroll
     for (int jj = 0; jj < P / 2; ++jj) {
-      const int k = i * P + 2 * jj;  // even point of the pair; k + 1 is in the same row and the same region
       u64 l0, l1, l2;
       float xe, ye, ze, xo, yo, zo;
       if (LAYOUT == kLayoutRowMajor) {
@@ -92,37 +129,27 @@ struct CellWalkPacked {
         l0 = p0[jj]; l1 = p1[jj]; l2 = p2[jj];
         upk2(l0, xe, xo); upk2(l1, ye, yo); upk2(l2, ze, zo);
       }
-      if (k == 0) { first[0] = xe; first[1] = ye; first[2] = ze; }
-      if (k + 1 == N - 1) { last[0] = xo; last[1] = yo; last[2] = zo; }
-      // X^T X chains, point k then point k + 1 (cell_segment_stat.cpp:32)
-      vA = add2(pk2(__fmul_rn(xe, xe), __fmul_rn(xe, ye)), vA);
-      vB = add2(pk2(__fmul_rn(xe, ze), __fmul_rn(ye, ye)), vB);
-      vC = add2(pk2(__fmul_rn(ye, ze), __fmul_rn(ze, ze)), vC);
-      vA = add2(pk2(__fmul_rn(xo, xo), __fmul_rn(xo, yo)), vA);
-      vB = add2(pk2(__fmul_rn(xo, zo), __fmul_rn(yo, yo)), vB);
-      vC = add2(pk2(__fmul_rn(yo, zo), __fmul_rn(zo, zo)), vC);
-      // column sums (cell_segment_stat.cpp:31)
-      if (k < kA2) {
-        const int m = (k & 7) >> 1;
-        s0[m] = add2(s0[m], l0); s1[m] = add2(s1[m], l1); s2[m] = add2(s2[m], l2);
-      } else {
-        const int m = (k - kA2) >> 1;
-        r0[m] = l0; r1[m] = l1; r2[m] = l2;
-      }
-      // hasValidPoints (cell_segment.cpp:57-60)
-      vv = add2(vv, pk2(valid_f(ze), valid_f(zo)));
-      // isHorizontalContinuous: indices [N/2, N/2 + P) = row P/2 (cell_segment.cpp:62-76)
-      if (i == P / 2) {
-        if (jj == 0) hprev = ze;
-        scan_step(ze, hprev, hcnt, disc_thr);
-        scan_step(zo, hprev, hcnt, disc_thr);
-      }
-      // isVerticalContinuous: column P/2 of every row (cell_segment.cpp:78-91)
-      if (2 * jj == P / 2 || 2 * jj + 1 == P / 2) {
-        const float zc = (2 * jj == P / 2) ? ze : zo;
-        if (i == 0) vprev = zc;
-        scan_step(zc, vprev, vcnt, disc_thr);
-      }
+      pair(i, jj, xe, ye, ze, xo, yo, zo, l0, l1, l2, disc_thr);
+    }
+  }
+
+  // Same, from raw depth: the staged block holds uint16 samples, blk16[rr * tw + col], and the points are
+  // DepthImage::toPointCloud's (depth_image.cpp:64-73): z = float(raw), x = ((col - cx) * z) / fx,
+  // y = ((row - cy) * z) / fy, every step rounded to fp32.  Uses the column-major pairing (LAYOUT must be
+  // kLayoutColMajor).  `colf` = image column of the cell's first pixel, `rowf` = image row, both exact in fp32.
+  __device__ __forceinline__ void row_depth(int i, const uint16_t* blk16, int tw, int rr, int t, float disc_thr, float colf,
+                                            float rowf, const Pinhole& k) {
+    const uint32_t* pz = reinterpret_cast<const uint32_t*>(blk16 + rr * tw + t * P);
+    const float ry = __fsub_rn(rowf, k.cy);
+#pragma unroll
+    for (int jj = 0; jj < P / 2; ++jj) {
+      const uint32_t w = pz[jj];
+      const float ze = static_cast<float>(w & 0xffffu), zo = static_cast<float>(w >> 16);
+      const float xe = __fdiv_rn(__fmul_rn(__fsub_rn(__fadd_rn(colf, static_cast<float>(2 * jj)), k.cx), ze), k.fx);
+      const float xo = __fdiv_rn(__fmul_rn(__fsub_rn(__fadd_rn(colf, static_cast<float>(2 * jj + 1)), k.cx), zo), k.fx);
+      const float ye = __fdiv_rn(__fmul_rn(ry, ze), k.fy);
+      const float yo = __fdiv_rn(__fmul_rn(ry, zo), k.fy);
+      pair(i, jj, xe, ye, ze, xo, yo, zo, pk2(xe, xo), pk2(ye, yo), pk2(ze, zo), disc_thr);
     }
   }
 

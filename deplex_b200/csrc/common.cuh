@@ -17,6 +17,12 @@ namespace dpx {
 
 constexpr int kLayoutColMajor = 0;
 constexpr int kLayoutRowMajor = 1;
+constexpr int kLayoutDepth16 = 2;  // raw uint16 depth + pinhole intrinsics: points are generated in registers
+
+// DepthImage::toPointCloud's inputs (depth_image.cpp:58-61)
+struct Pinhole {
+  float fx, fy, cx, cy;
+};
 
 constexpr uint8_t kFlagValid = 1;
 constexpr uint8_t kFlagPlanar = 2;

@@ -172,6 +172,45 @@ class PlaneExtractor:
                                                        stream.cuda_stream))
         return labels
 
+    # ---- raw depth in (DepthImage::toPointCloud evaluated on the device, depth_image.cpp:55-78) ------------
+    @staticmethod
+    def _intrinsics(k):
+        """dict(fx, fy, cx, cy) or a 3x3 matrix -> dpx_intrinsics (values rounded to float32 like Eigen::Matrix3f)."""
+        if isinstance(k, dict):
+            return _capi.dpx_intrinsics(k["fx"], k["fy"], k["cx"], k["cy"])
+        m = np.asarray(k, dtype=np.float32)
+        return _capi.dpx_intrinsics(m[0, 0], m[1, 1], m[0, 2], m[1, 2])
+
+    def process_depth_batch_host(self, depth, intrinsics, labels=None):
+        """depth: host uint16 array of F frames (F,H,W).  Returns (F,N) int32 labels, identical to process() on the
+        clouds DepthImage.transform_to_pcd would produce; only 2 bytes per pixel cross PCIe."""
+        d = np.ascontiguousarray(depth, dtype=np.uint16)
+        f = d.size // self.n_points if self.n_points else 0
+        assert d.size == f * self.n_points, "batch does not hold a whole number of frames"
+        if labels is None:
+            labels = np.empty((f, self.n_points), dtype=np.int32)
+        k = self._intrinsics(intrinsics)
+        self._check(self._lib.dpx_process_depth_batch_host(self._h, d.ctypes.data, f, C.byref(k), labels.ctypes.data))
+        return labels
+
+    def process_depth_batch_host_ptr(self, depth_ptr, n_frames, intrinsics, labels_ptr):
+        k = self._intrinsics(intrinsics)
+        self._check(self._lib.dpx_process_depth_batch_host(self._h, depth_ptr, n_frames, C.byref(k), labels_ptr))
+
+    def process_depth_batch_device(self, depth, intrinsics, labels=None, stream=None):
+        """depth: CUDA int16/uint16 tensor of F frames; asynchronous on `stream`."""
+        import torch
+        assert depth.is_cuda and depth.element_size() == 2 and depth.is_contiguous()
+        f = depth.numel() // self.n_points
+        if labels is None:
+            labels = torch.empty((f, self.n_points), dtype=torch.int32, device=depth.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(depth.device)
+        k = self._intrinsics(intrinsics)
+        self._check(self._lib.dpx_process_depth_batch_device(self._h, depth.data_ptr(), f, C.byref(k), labels.data_ptr(),
+                                                             stream.cuda_stream))
+        return labels
+
     # ---- tables the reference computes and discards --------------------------------------------------
     def cells(self, frame=0):
         n = self.info.n_cells

@@ -64,6 +64,12 @@ typedef struct dpx_config {
   float ransac_inliers_ratio;                 /* ransacInliersRatio */
 } dpx_config;
 
+/* Pinhole intrinsics [[fx, 0, cx], [0, fy, cy], [0, 0, 1]] as DepthImage::toPointCloud reads them
+ * (cpp/deplex/src/deplex/utils/depth_image.cpp:58-61). */
+typedef struct dpx_intrinsics {
+  float fx, fy, cx, cy;
+} dpx_intrinsics;
+
 typedef struct dpx_extractor dpx_extractor; /* opaque: PlaneExtractor::Impl's replacement */
 
 /* Geometry and capacities fixed at creation. */
@@ -133,6 +139,16 @@ DPX_API dpx_status dpx_process_batch_host(dpx_extractor* ex, const float* xyz, i
  * NULL = the legacy default stream).  d_labels: n_frames * height * width int32 in device memory. */
 DPX_API dpx_status dpx_process_batch_device(dpx_extractor* ex, const float* d_xyz, int32_t n_frames, dpx_layout layout,
                                     int32_t* d_labels, void* cuda_stream);
+
+/* ---- raw depth in: replaces DepthImage::toPointCloud (depth_image.cpp:55-78) followed by process() ----
+ * depth: n_frames * height * width uint16 samples (row-major images, raw sensor units; 0 = no measurement).
+ * The points z = float(raw), x = ((col - cx) * z) / fx, y = ((row - cy) * z) / fy are generated on the device,
+ * fused into the first kernel where the geometry allows, so 2 bytes per pixel cross PCIe / HBM instead of 12.
+ * Labels are identical to process() on the cloud toPointCloud would have produced. */
+DPX_API dpx_status dpx_process_depth_batch_host(dpx_extractor* ex, const uint16_t* depth, int32_t n_frames,
+                                        const dpx_intrinsics* k, int32_t* labels);
+DPX_API dpx_status dpx_process_depth_batch_device(dpx_extractor* ex, const uint16_t* d_depth, int32_t n_frames,
+                                          const dpx_intrinsics* k, int32_t* d_labels, void* cuda_stream);
 
 /* ---- introspection of the last batch (the reference computes these and discards them) ---- */
 DPX_API dpx_status dpx_get_cells(dpx_extractor* ex, int32_t frame, dpx_cell* out, int32_t capacity);

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, frame_cloud, to_oracle_cfg
+from conftest import GOLDEN, frame_cloud, load_frame, to_oracle_cfg
 
 pytestmark = pytest.mark.gpu
 
@@ -195,3 +195,44 @@ def test_unaligned_device_pointer(oracle_mod):
     ex = PlaneExtractor(h, w, Config())
     out = ex.process_batch_device(buf[1:], LAYOUT_ROWMAJOR).cpu().numpy()[0]
     assert np.array_equal(out, oracle_mod.process(h, w, oracle_mod.OracleConfig(), xyz))
+
+
+@pytest.mark.parametrize("hw,patch", [((480, 640), 10), ((480, 640), 4), ((480, 640), 5), ((1080, 1920), 8), ((480, 642), 6)])
+def test_depth_input_equals_point_input(oracle_mod, hw, patch):
+    """dpx_process_depth_batch_*: DepthImage::toPointCloud (depth_image.cpp:55-78) evaluated on the device -- fused into
+    the cell-stats kernel (even patch, aligned rows) or through the conversion kernel (patch 5, width 642) -- gives
+    exactly the labels of process() on the host-made cloud, and of the oracle."""
+    import torch
+    from deplex_b200 import Config, PlaneExtractor, synth, LAYOUT_ROWMAJOR
+    h, w = hw
+    F = 3
+    k = synth.intrinsics_for(h, w)
+    depth = np.stack([synth.make_depth(h, w, 900 + f, k) for f in range(F)])
+    clouds = np.stack([synth.depth_to_cloud(depth[f], k, "rowmajor") for f in range(F)])
+    cfg = Config(patch_size=patch)
+    ex = PlaneExtractor(h, w, cfg, max_batch=F)
+    want = ex.process_batch_host(clouds, LAYOUT_ROWMAJOR)
+    got = ex.process_depth_batch_host(depth, k)
+    assert np.array_equal(got, want)
+    cells_depth = ex.cells(1)
+    ex.process_batch_host(clouds, LAYOUT_ROWMAJOR)
+    cells_pts = ex.cells(1)
+    for name in ("sum", "var", "mean", "normal", "d", "mse", "bin"):
+        assert np.array_equal(cells_depth[name], cells_pts[name], equal_nan=True), name
+    dev = ex.process_depth_batch_device(torch.from_numpy(depth.view(np.int16)).cuda(), k).cpu().numpy()
+    assert np.array_equal(dev, want)
+    ref = oracle_mod.process(h, w, to_oracle_cfg(oracle_mod, cfg), clouds[0])
+    assert np.array_equal(got[0], ref)
+
+
+def test_depth_input_with_refinement_and_shipped_frames(oracle_mod):
+    from deplex_b200 import Config, PlaneExtractor
+    for name in ("tum", "icl"):
+        depth, k, ini = load_frame(name)
+        xyz, _ = frame_cloud(name)
+        for refine in (0, 1):
+            cfg = Config(ini, ransac_refinement=refine)
+            ex = PlaneExtractor(480, 640, cfg)
+            got = ex.process_depth_batch_host(depth[None], k)[0]
+            assert np.array_equal(got, ex.process(xyz))
+            assert np.array_equal(got, oracle_mod.process(480, 640, to_oracle_cfg(oracle_mod, cfg), xyz))
