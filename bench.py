@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-frames", type=int, default=0, help="frames in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the single-frame latency legs (configs[0], configs[1])")
     return ap.parse_args()
 
 
@@ -61,12 +62,19 @@ def workload_config(a, extra=None):
     return cfg
 
 
-def make_host_batch(a, rank):
+def make_host_batch(a, rank, with_depth=False):
+    """`frames` synthetic organized clouds (the first `unique` generated, then tiled); optionally also the raw
+    uint16 depth images they were back-projected from."""
     from deplex_b200 import synth
     uniq = min(a.unique, a.frames)
-    base = synth.make_batch(a.height, a.width, rank * 100000, uniq, a.layout)
+    k = synth.intrinsics_for(a.height, a.width)
+    depth = np.stack([synth.make_depth(a.height, a.width, rank * 100000 + i, k) for i in range(uniq)])
+    base = np.stack([synth.depth_to_cloud(depth[i], k, a.layout) for i in range(uniq)])
     reps = (a.frames + uniq - 1) // uniq
-    return np.concatenate([base] * reps, axis=0)[: a.frames]
+    clouds = np.concatenate([base] * reps, axis=0)[: a.frames]
+    if with_depth:
+        return clouds, np.concatenate([depth] * reps, axis=0)[: a.frames], k
+    return clouds
 
 
 class ClockSampler:
@@ -124,6 +132,63 @@ class ClockSampler:
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons), "window": window}
+
+
+def latency_mode(dev, calls=300):
+    """BASELINE.json configs[0] and configs[1]: the shipped TUM and ICL-NUIM frames (tests/golden fixtures), one
+    process() call at a time through the host-pointer API (pinned buffers, H2D + kernels + D2H per call), the way
+    examples/process_cloud.cpp and process_sequence.cpp time it: min / mean / max microseconds per frame."""
+    import torch
+    from deplex_b200 import Config, PlaneExtractor, synth, LAYOUT_ROWMAJOR
+    golden = os.path.join(ROOT, "tests", "golden")
+    out = {}
+    for name, cfgname in (("tum", "TUM_fr3_long_val"), ("icl", "ICL_living_room")):
+        try:
+            depth = np.load(os.path.join(golden, f"{name}_depth.npz"))["depth"]
+            K = np.loadtxt(os.path.join(golden, cfgname + ".K"), dtype=np.float32)
+            k = dict(fx=float(K[0, 0]), fy=float(K[1, 1]), cx=float(K[0, 2]), cy=float(K[1, 2]))
+            cfg = Config(os.path.join(golden, cfgname + ".ini"))
+            h, w = depth.shape
+            xyz = torch.from_numpy(synth.depth_to_cloud(depth, k, "rowmajor")).pin_memory()
+            lab = torch.empty(h * w, dtype=torch.int32).pin_memory()
+            ex = PlaneExtractor(h, w, cfg, device=dev.index)
+            for _ in range(10):
+                ex.process_batch_host_ptr(xyz.data_ptr(), 1, LAYOUT_ROWMAJOR, lab.data_ptr())
+            ts = []
+            for _ in range(calls):
+                t0 = time.perf_counter()
+                ex.process_batch_host_ptr(xyz.data_ptr(), 1, LAYOUT_ROWMAJOR, lab.data_ptr())
+                ts.append(time.perf_counter() - t0)
+            d_xyz = xyz.to(dev)
+            d_lab = torch.empty(1, h * w, dtype=torch.int32, device=dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(10):
+                ex.process_batch_device(d_xyz, LAYOUT_ROWMAJOR, d_lab)
+            e0.record()
+            for _ in range(calls):
+                ex.process_batch_device(d_xyz, LAYOUT_ROWMAJOR, d_lab)
+            e1.record()
+            torch.cuda.synchronize()
+            us = np.array(ts) * 1e6
+            out[name] = {"frame": f"{cfgname} ({w}x{h}, patchSize={cfg.patch_size})", "calls": calls,
+                         "host_ptr_us": {"min": float(us.min()), "mean": float(us.mean()), "max": float(us.max())},
+                         "host_ptr_fps": float(1e6 / us.mean()),
+                         "device_resident_us": float(e0.elapsed_time(e1) * 1e3 / calls),
+                         "planes": int(lab.max().item())}
+            ex.close()
+        except Exception as e:  # fixtures are optional for the bench
+            out[name] = {"error": repr(e)}
+    return out
+
+
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json, written by
+    tools/ncu_traffic.py from the same bench command); None when no capture is recorded."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return rec.get(kernel)
+    except Exception:
+        return None
 
 
 def cpu_baseline(a, host_batch, threads, sample_frames):
@@ -193,7 +258,7 @@ def run_ours(a):
         torch.cuda.synchronize()
 
     lay = LAYOUT_ROWMAJOR if a.layout == "rowmajor" else LAYOUT_COLMAJOR
-    host_np = make_host_batch(a, rank)
+    host_np, depth_np, intr = make_host_batch(a, rank, with_depth=True)
     n_px = a.height * a.width
     pin_in = torch.empty(host_np.shape, dtype=torch.float32).pin_memory()
     pin_in.copy_(torch.from_numpy(host_np))
@@ -258,7 +323,7 @@ def run_ours(a):
     value = world * a.steps * a.frames / (max_ms / 1e3)
 
     # ---- end to end: host pointers, pinned memory, H2D + D2H inside the timed region ------------------
-    e2e = None
+    e2e = e2e_depth = None
     if not a.no_e2e:
         for _ in range(2):
             ex.process_batch_host_ptr(pin_in.data_ptr(), a.frames, lay, pin_out.data_ptr())
@@ -278,6 +343,23 @@ def run_ours(a):
                "labels_checksum": int(pin_out.view(-1)[:: 997].to(torch.int64).sum().item())}
         same = bool(torch.equal(pin_out, d_lab.cpu()))
         e2e["matches_device_path"] = same
+        # the same workload entering as raw uint16 depth (toPointCloud fused on the device)
+        pin_depth = torch.from_numpy(depth_np.view(np.int16)).pin_memory()
+        pin_out2 = torch.empty_like(pin_out).pin_memory()
+        for _ in range(2):
+            ex.process_depth_batch_host_ptr(pin_depth.data_ptr(), a.frames, intr, pin_out2.data_ptr())
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            ex.process_depth_batch_host_ptr(pin_depth.data_ptr(), a.frames, intr, pin_out2.data_ptr())
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_depth = {"value": world * k_e2e * a.frames / float(t.item()), "unit": UNIT,
+                     "h2d_bytes_per_step": int(a.frames * n_px * 2), "d2h_bytes_per_step": int(a.frames * n_px * 4),
+                     "api": "dpx_process_depth_batch_host (uint16 depth + intrinsics in, same labels out)",
+                     "matches_point_path": bool(torch.equal(pin_out2, pin_out))}
 
     if rank != 0:
         if world > 1:
@@ -302,9 +384,16 @@ def run_ours(a):
         gbs = alg_bytes[k] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         stages[k] = {"ms": ms, "algorithmic_bytes": alg_bytes[k], "gbs": gbs, "frac": gbs / peak}
     dominant = max(stages, key=lambda k: stages[k]["ms"])
+    step_ms = max_ms / a.steps
+    pipeline_bytes = a.frames * n_px * 16  # 12 B/px read once + 4 B/px written once
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": stages[dominant]["gbs"], "peak": peak,
-                "unit": "GB/s", "frac": stages[dominant]["frac"], "traffic": None, "peak_source": peak_src,
-                "stages": stages}
+                "unit": "GB/s", "frac": stages[dominant]["frac"], "traffic": measured_traffic(dominant),
+                "peak_source": peak_src, "stages": stages,
+                "pipeline": {"algorithmic_bytes": pipeline_bytes, "gbs": pipeline_bytes / (step_ms * 1e-3) / 1e9,
+                             "frac": pipeline_bytes / (step_ms * 1e-3) / 1e9 / peak,
+                             "note": "whole step, 16 B/pixel/frame; the region-growing stage is latency-bound by construction"}}
+    for k in stages:
+        stages[k]["traffic"] = measured_traffic(k)
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
@@ -314,6 +403,9 @@ def run_ours(a):
     }
     if e2e:
         out["e2e"] = e2e
+        out["e2e_depth16"] = e2e_depth
+    if world == 1 and not a.no_latency:
+        out["latency"] = latency_mode(dev)
     if world == 1 and not a.no_cpu_baseline:
         n = a.cpu_sample_frames or a.frames
         reps = 4

@@ -609,12 +609,19 @@ cudaError_t launch_region_grow(const RegionArgs& args, cudaStream_t stream) {
   edge_mask_kernel<<<static_cast<unsigned>((cells + 255) / 256), 256, 0, stream>>>(args);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const CtaPlan cta = region_grow_cta_plan(args.geom, args.thr);
+  CtaPlan cta = region_grow_cta_plan(args.geom, args.thr, true);
+  const bool members_smem = cta.bytes > 0;
+  if (!members_smem) cta = region_grow_cta_plan(args.geom, args.thr, false);
   static const bool force_warp_kernel = std::getenv("DPX_REGION_KERNEL") && std::strcmp(std::getenv("DPX_REGION_KERNEL"), "warp") == 0;
   const bool all_smem = args.plan.bins_smem && args.plan.list_smem && args.plan.members_smem && args.plan.merge_smem;
   if (cta.bytes > 0 && !force_warp_kernel) {
-    cudaFuncSetAttribute(region_grow_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cta.bytes));
-    region_grow_cta_kernel<<<args.n_frames, kCtaThreads, cta.bytes, stream>>>(args, cta);
+    if (members_smem) {
+      cudaFuncSetAttribute(region_grow_cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cta.bytes));
+      region_grow_cta_kernel<true><<<args.n_frames, kCtaThreads, cta.bytes, stream>>>(args, cta);
+    } else {
+      cudaFuncSetAttribute(region_grow_cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cta.bytes));
+      region_grow_cta_kernel<false><<<args.n_frames, kCtaThreads, cta.bytes, stream>>>(args, cta);
+    }
   } else if (all_smem) {
     cudaFuncSetAttribute(region_grow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(args.plan.bytes));
     region_grow_kernel<true><<<args.n_frames, 32, args.plan.bytes, stream>>>(args);

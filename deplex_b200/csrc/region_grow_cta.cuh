@@ -35,6 +35,9 @@ struct CtaPlan {
 
 __device__ __noinline__ void fit_plane_call(const Moments& m, PlaneFit& f) { fit_plane(m, f); }
 
+// MEMBERS_SMEM = false: the member runs (and later the adjacency bit matrix) live in the global scratch table
+// `pairs` (8 bytes per cell, L2-resident) so that frames of up to ~27 000 cells keep the BFS state in shared memory.
+template <bool MEMBERS_SMEM>
 __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const RegionArgs args, const CtaPlan plan) {
   extern __shared__ float4 smem_f4[];
   const Geometry& g = args.geom;
@@ -53,8 +56,11 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
   int* run_end = reinterpret_cast<int*>(smem + plan.off_runend);             // [K] end of its still-unassigned members
   unsigned* cw = reinterpret_cast<unsigned*>(smem + plan.off_cw);            // [C] cell words; later the segment labels
   int32_t* list = reinterpret_cast<int32_t*>(smem + plan.off_list);          // [C] BFS queues = region cell lists
-  int32_t* members = reinterpret_cast<int32_t*>(smem + plan.off_members);    // [C] cell ids grouped by initial bin
-  float* msem = reinterpret_cast<float*>(smem + plan.off_msem);              // [C] their MSE, same order
+  // [C] cell ids grouped by initial bin, and [C] their MSE in the same order
+  int32_t* members = MEMBERS_SMEM ? reinterpret_cast<int32_t*>(smem + plan.off_members)
+                                  : reinterpret_cast<int32_t*>(args.tables.pairs + 2 * fc);
+  float* msem = MEMBERS_SMEM ? reinterpret_cast<float*>(smem + plan.off_msem)
+                             : reinterpret_cast<float*>(args.tables.pairs + 2 * fc + C);
   float* recs = reinterpret_cast<float*>(smem + plan.off_recs);              // [rec_cap][24]
   int32_t* merge = reinterpret_cast<int32_t*>(smem + plan.off_merge);        // [plane_cap]
   volatile int* misc = reinterpret_cast<volatile int*>(smem + plan.off_misc);
@@ -161,22 +167,32 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
       {
         const int start = bin_off[bslot], end = run_end[bslot];
         int w = start;
-        for (int i0 = start; i0 < end; i0 += 32) {
-          const int i = i0 + lane;
-          const bool in = i < end;
-          const int c = in ? members[i] : 0;
-          const float m = in ? msem[i] : 0.f;
-          const bool alive = in && (cw[c] & kAlive);
-          if (alive && (m < lm || (m == lm && c < seed))) { lm = m; seed = c; }
-          const unsigned am = __ballot_sync(kFull, alive);
-          if (am != kFull || w != i0) {
-            if (alive) {
-              const int pos = w + __popc(am & ((1u << lane) - 1u));
-              members[pos] = c;
-              msem[pos] = m;
-            }
+        // four 32-member chunks per round: their loads are independent, so a round costs one memory round trip
+        for (int i0 = start; i0 < end; i0 += 128) {
+          int c[4];
+          float m[4];
+          bool alive[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 32 * u + lane;
+            const bool in = i < end;
+            c[u] = in ? members[i] : -1;
+            m[u] = in ? msem[i] : 0.f;
           }
-          w += __popc(am);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) alive[u] = c[u] >= 0 && (cw[c[u]] & kAlive);
+          __syncwarp();  // all reads of this round precede its (possibly overlapping) compaction writes
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (alive[u] && (m[u] < lm || (m[u] == lm && c[u] < seed))) { lm = m[u]; seed = c[u]; }
+            const unsigned am = __ballot_sync(kFull, alive[u]);
+            if (alive[u] && (am != kFull || w != i0 + 32 * u)) {
+              const int pos = w + __popc(am & ((1u << lane) - 1u));
+              members[pos] = c[u];
+              msem[pos] = m[u];
+            }
+            w += __popc(am);
+          }
           __syncwarp();
         }
         if (lane == 0) run_end[bslot] = w;
@@ -534,7 +550,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
 }
 
 // Shared-memory layout of the CTA kernel; bytes == 0 means "does not fit, use the generic kernel".
-inline CtaPlan region_grow_cta_plan(const Geometry& g, const Thresholds& th) {
+inline CtaPlan region_grow_cta_plan(const Geometry& g, const Thresholds& th, bool members_smem) {
   CtaPlan p{};
   auto align16 = [](size_t v) { return (v + 15) & ~static_cast<size_t>(15); };
   const size_t B2 = static_cast<size_t>(th.histogram_bins_per_coord) * th.histogram_bins_per_coord;
@@ -547,14 +563,19 @@ inline CtaPlan region_grow_cta_plan(const Geometry& g, const Thresholds& th) {
   p.off_runend = static_cast<int>(off);  off = align16(off + B2 * 4);
   p.off_cw = static_cast<int>(off);      off = align16(off + C * 4);
   p.off_list = static_cast<int>(off);    off = align16(off + (C > B2 ? C : B2) * 4);
-  p.off_members = static_cast<int>(off); off = align16(off + C * 4);
-  p.off_msem = static_cast<int>(off);    off = align16(off + C * 4);
-  p.adj_bytes = static_cast<int>(off - p.off_members);
+  if (members_smem) {
+    p.off_members = static_cast<int>(off); off = align16(off + C * 4);
+    p.off_msem = static_cast<int>(off);    off = align16(off + C * 4);
+    p.adj_bytes = static_cast<int>(off - p.off_members);
+  } else {
+    p.adj_bytes = static_cast<int>(C * 8);  // the `pairs` scratch of this frame
+  }
   p.rec_cap = g.plane_cap < 128 ? g.plane_cap : 128;
   p.off_recs = static_cast<int>(off);    off = align16(off + static_cast<size_t>(p.rec_cap) * kRecFloats * 4);
   p.off_merge = static_cast<int>(off);   off = align16(off + static_cast<size_t>(g.plane_cap) * 4);
   p.off_misc = static_cast<int>(off);    off = align16(off + 64);
-  p.bytes = off <= 100 * 1024 ? off : 0;
+  // small frames keep several CTAs per SM; large ones may take (almost) a whole SM's shared memory
+  p.bytes = off <= (members_smem ? 100u : 220u) * 1024 ? off : 0;
   return p;
 }
 

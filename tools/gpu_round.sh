@@ -7,7 +7,7 @@ set -u
 TAG=${1:-rXX}
 OUT=gpurun_out
 mkdir -p $OUT
-BENCH_SHORT="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e"
+BENCH_SHORT="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-latency"
 
 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"; tail -3 $OUT/pytest_gpu_$TAG.log
 python __graft_entry__.py smoke > $OUT/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -2 $OUT/smoke_$TAG.log
