@@ -22,7 +22,10 @@ namespace {
 
 constexpr int kCtaThreads = 128;
 constexpr int kCtaWarps = kCtaThreads / 32;
-constexpr unsigned kAlive = 1u << 20;   // cell word: bits 0-15 bin, 16-19 edge mask, 20 alive (planar and unassigned)
+// cell word: bits 0-15 slot of the cell's initial bin in the compacted histogram, 16-19 edge mask, 20 alive (planar and
+// unassigned), 21-31 claim field (all ones while idle; see the BFS step)
+constexpr unsigned kAlive = 1u << 20;
+constexpr unsigned kClaimIdle = 0x7ffu << 21;
 constexpr int kRecFloats = kSegFloats;  // region / plane records use the segs layout
 
 struct CtaPlan {
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
   for (int c = tid; c < C; c += kCtaThreads) {
     const int b = static_cast<int>(__ldg(bin_in + c));
     const unsigned e = static_cast<unsigned>(__ldg(edge_in + c));
-    cw[c] = b >= 0 ? (static_cast<unsigned>(b) | (e << 16) | kAlive) : 0u;
+    cw[c] = b >= 0 ? (static_cast<unsigned>(b) | (e << 16) | kAlive | kClaimIdle) : 0u;
     seg_label[c] = 0;
     if (b >= 0) atomicAdd(&hist_tmp[b], 1);
   }
@@ -130,7 +133,9 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
   for (int c = tid; c < C; c += kCtaThreads) {
     const unsigned w = cw[c];
     if (w & kAlive) {
-      const int pos = atomicAdd(&run_end[binslot[w & 0xffffu]], 1);
+      const unsigned slot = static_cast<unsigned>(binslot[w & 0xffffu]);
+      cw[c] = (w & 0xffff0000u) | slot;  // from here on the word carries the histogram slot instead of the bin id
+      const int pos = atomicAdd(&run_end[slot], 1);
       members[pos] = c;
       msem[pos] = __ldg(mse_g + c);
     }
@@ -223,36 +228,38 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
       __syncwarp();
       // a seed without a single passing edge is a region of one cell: no BFS step needed
       int head = ((seed_w >> 16) & 0xfu) ? 0 : 1, tail = 1;
+      const int ent = lane >> 2;
+      const unsigned lt_mask = (1u << lane) - 1u;
+      const unsigned my_claim = static_cast<unsigned>(lane) << 21;
       while (head < tail) {
+        // straight-line step (a single warp pays every branch and every dependent instruction in full)
         const int nb = min(8, tail - head);
-        int v = 0;
+        unsigned pk = 0;
+        if (ent < nb) pk = static_cast<unsigned>(q[head + ent]);
+        const bool edge_ok = ((pk >> (24 + slot4)) & 1u) != 0;
+        const int v = static_cast<int>(pk & 0xffffffu) + delta;
         unsigned w = 0;
-        if ((lane >> 2) < nb) {
-          const unsigned pk = static_cast<unsigned>(q[head + (lane >> 2)]);
-          if ((pk >> (24 + slot4)) & 1u) {
-            v = static_cast<int>(pk & 0xffffffu) + delta;
-            w = cw[v];
-          }
-        }
+        if (edge_ok) w = cw[v];
         const bool pass = (w & kAlive) != 0;  // edge test passed, still unassigned, not yet activated
         const unsigned pm = __ballot_sync(kFull, pass);
-        unsigned wm = 0;
-        if (pm) {
-          bool win = pass;
-          // lanes of one queue entry have distinct targets: only passing lanes of different entries can clash
-          const unsigned same_entry = 0xfu << ((__ffs(pm) - 1) & ~3);
-          if (pass && (pm & ~same_entry)) {
-            const unsigned grp = __match_any_sync(pm, v);
-            win = (__ffs(grp) - 1) == lane;
-          }
-          wm = __ballot_sync(kFull, win);
-          if (win) {
-            q[tail + __popc(wm & ((1u << lane) - 1u))] = v | static_cast<int>(((w >> 16) & 0xfu) << 24);
-            cw[v] = w & ~kAlive;  // removePoint + unassigned_mask[v] = false (plane_extractor.cpp:324-325)
-            const int b = static_cast<int>(w & 0xffffu);
-            if (b == bi) ++same;
-            else atomicSub(&hkey[binslot[b]], 1u << 15);
-          }
+        // lanes of one queue entry have distinct targets: a clash needs passing lanes in two different nibbles.
+        // Then every candidate posts its lane number into the cell word's claim field with a shared-memory
+        // atomicMin (the rest of the word is identical for all of them) and the lowest lane -- the earliest in
+        // FIFO order -- finds itself there.  (match.any would do the same but costs ~250 cycles on this path.)
+        const unsigned nib = (pm | (pm >> 1) | (pm >> 2) | (pm >> 3)) & 0x11111111u;
+        bool win = pass;
+        if (nib & (nib - 1u)) {
+          if (pass) atomicMin(&cw[v], (w & ~kClaimIdle) | my_claim);
+          __syncwarp();
+          if (pass) win = (cw[v] >> 21) == static_cast<unsigned>(lane);
+        }
+        const unsigned wm = __ballot_sync(kFull, win);
+        if (win) {
+          q[tail + __popc(wm & lt_mask)] = v | static_cast<int>(((w >> 16) & 0xfu) << 24);
+          cw[v] = w & ~kAlive;  // removePoint + unassigned_mask[v] = false (plane_extractor.cpp:324-325); claim idle again
+          const unsigned sl = w & 0xffffu;
+          if (sl == static_cast<unsigned>(bslot)) ++same;
+          else atomicSub(&hkey[sl], 1u << 15);
         }
         tail += __popc(wm);
         head += nb;
