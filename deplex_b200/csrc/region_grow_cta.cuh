@@ -90,7 +90,9 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
   for (int i = tid; i < B2; i += kCtaThreads) {
     hist_tmp[i] = 0;
     binslot[i] = -1;
+    hkey[i] = 0;
   }
+  if (tid < 4) hkey[B2 + tid] = 0;  // the vectorised scan may read up to three entries past the last bin
   if (tid < 8 + kCtaWarps) misc[tid] = 0;
   __syncthreads();
   for (int c = tid; c < C; c += kCtaThreads) {
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
       if (cnt > 0) {
         const int slot = K + __popc(nz & ((1u << lane) - 1u));
         binslot[b] = static_cast<int16_t>(slot);
-        hkey[slot] = (static_cast<unsigned>(cnt) << 15) | (0x7fffu - static_cast<unsigned>(b));
+        hkey[slot] = (static_cast<unsigned>(cnt) << 15) | (0x7fffu - static_cast<unsigned>(slot));
         bin_off[slot] = run + incl - cnt;
         run_end[slot] = run + incl - cnt;
       }
@@ -156,14 +158,14 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
     const int delta = (slot4 == 0) ? -nh : (slot4 == 1) ? nh : (slot4 == 2) ? -1 : 1;
     while (remaining > 0) {
       if (prof) t_mark = clock64();
-      // most frequent bin, first maximum (normals_histogram.cpp:54-56): max key = largest count, smallest bin id
+      // most frequent bin, first maximum (normals_histogram.cpp:54-56): max key = largest count, smallest slot
+      // (slots ascend with the bin ids, so the smallest slot is the smallest bin id)
       unsigned key = 0;
       for (int i = lane; i < K; i += 32) key = max(key, hkey[i]);
       key = __reduce_max_sync(kFull, key);
-      const int bc = static_cast<int>(key >> 15), bi = static_cast<int>(0x7fffu - (key & 0x7fffu));
+      const int bc = static_cast<int>(key >> 15), bslot = static_cast<int>(0x7fffu - (key & 0x7fffu));
       const unsigned long long n_cand = bc > 0 ? static_cast<unsigned long long>(bc) : 0ull;
       if (n_cand < th.min_candidate_size) break;  // plane_extractor.cpp:305-307
-      const int bslot = binslot[bi];
 
       // seed = first strict minimum of the MSE among the bin's unassigned cells (plane_extractor.cpp:309-316);
       // the scan also compacts the bin's member run down to the cells that are still unassigned
@@ -173,6 +175,23 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
         const int start = bin_off[bslot], end = run_end[bslot];
         int w = start;
         // four 32-member chunks per round: their loads are independent, so a round costs one memory round trip
+        if (end - start <= 32) {
+          // short run (the usual case for the left-over bins that produce one-cell regions): one chunk, no unrolling
+          const int i = start + lane;
+          const bool in = i < end;
+          const int c = in ? members[i] : -1;
+          const float m = in ? msem[i] : 0.f;
+          const bool alive = in && (cw[c] & kAlive);
+          if (alive) { lm = m; seed = c; }
+          const unsigned am = __ballot_sync(kFull, alive);
+          if (alive && am != ((end - start == 32) ? kFull : ((1u << (end - start)) - 1u))) {
+            const int pos = start + __popc(am & ((1u << lane) - 1u));
+            members[pos] = c;
+            msem[pos] = m;
+          }
+          w = start + __popc(am);
+          __syncwarp();
+        } else
         for (int i0 = start; i0 < end; i0 += 128) {
           int c[4];
           float m[4];
@@ -564,7 +583,7 @@ inline CtaPlan region_grow_cta_plan(const Geometry& g, const Thresholds& th, boo
   const size_t C = static_cast<size_t>(g.n_cells);
   size_t off = 0;
   p.off_stage = static_cast<int>(off);   off = align16(off + static_cast<size_t>(kCtaWarps - 1) * 32 * 12 * 4);
-  p.off_hkey = static_cast<int>(off);    off = align16(off + B2 * 4);
+  p.off_hkey = static_cast<int>(off);    off = align16(off + (B2 + 4) * 4);
   p.off_binslot = static_cast<int>(off); off = align16(off + B2 * 2);
   p.off_binoff = static_cast<int>(off);  off = align16(off + B2 * 4);
   p.off_runend = static_cast<int>(off);  off = align16(off + B2 * 4);
