@@ -38,6 +38,65 @@ struct CtaPlan {
 
 __device__ __noinline__ void fit_plane_call(const Moments& m, PlaneFit& f) { fit_plane(m, f); }
 
+// Wide BFS step: one lane per queue entry (up to 32), each lane probes its four neighbours.  FIFO order is
+// (entry, slot) lexicographic; a cell reached more than once goes to the smallest entry * 4 + slot, posted into the
+// cell word's claim field with a shared-memory atomicMin.  Kept out of line so that the narrow step's register
+// allocation is not disturbed.  Returns {cells appended, appended cells that belong to the seed's bin}.
+constexpr int kWideThreshold = 12;
+__device__ __noinline__ int2 bfs_wide_step(int32_t* q, unsigned* cw, unsigned* hkey, int head, int tail, int lane, int nh,
+                                           int bslot) {
+  const int nbw = min(32, tail - head);
+  unsigned pk = 0;
+  if (lane < nbw) pk = static_cast<unsigned>(q[head + lane]);
+  const int u = static_cast<int>(pk & 0xffffffu);
+  int vv[4];
+  unsigned ww[4];
+  unsigned passm = 0;
+#pragma unroll
+  for (int sl4 = 0; sl4 < 4; ++sl4) {
+    const int dl = (sl4 == 0) ? -nh : (sl4 == 1) ? nh : (sl4 == 2) ? -1 : 1;
+    vv[sl4] = u + dl;
+    ww[sl4] = ((pk >> (24 + sl4)) & 1u) ? cw[vv[sl4]] : 0u;
+    if (ww[sl4] & kAlive) passm |= 1u << sl4;
+  }
+  const unsigned anyp = __ballot_sync(kFull, passm != 0);
+  unsigned winm = passm;
+  if (anyp & (anyp - 1u)) {  // at least two entries have candidates: they may clash
+#pragma unroll
+    for (int sl4 = 0; sl4 < 4; ++sl4)
+      if (passm & (1u << sl4))
+        atomicMin(&cw[vv[sl4]], (ww[sl4] & ~kClaimIdle) | (static_cast<unsigned>(lane * 4 + sl4) << 21));
+    __syncwarp();
+#pragma unroll
+    for (int sl4 = 0; sl4 < 4; ++sl4)
+      if ((passm & (1u << sl4)) && (cw[vv[sl4]] >> 21) != static_cast<unsigned>(lane * 4 + sl4)) winm &= ~(1u << sl4);
+  }
+  // append position of (lane, slot) = winners of lower lanes + own lower slots
+  const unsigned nwin = __popc(winm);
+  int incl = static_cast<int>(nwin);
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += t;
+  }
+  int pos = tail + incl - static_cast<int>(nwin);
+  int same = 0;
+#pragma unroll
+  for (int sl4 = 0; sl4 < 4; ++sl4) {
+    if (winm & (1u << sl4)) {
+      q[pos++] = vv[sl4] | static_cast<int>(((ww[sl4] >> 16) & 0xfu) << 24);
+      cw[vv[sl4]] = ww[sl4] & ~kAlive;
+      const unsigned slt = ww[sl4] & 0xffffu;
+      if (slt == static_cast<unsigned>(bslot)) ++same;
+      else atomicSub(&hkey[slt], 1u << 15);
+    }
+  }
+  const int total = __shfl_sync(kFull, incl, 31);
+  __syncwarp();
+  return make_int2(total, same);
+}
+
+
 // MEMBERS_SMEM = false: the member runs (and later the adjacency bit matrix) live in the global scratch table
 // `pairs` (8 bytes per cell, L2-resident) so that frames of up to ~27 000 cells keep the BFS state in shared memory.
 template <bool MEMBERS_SMEM>
@@ -251,6 +310,15 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
       const unsigned lt_mask = (1u << lane) - 1u;
       const unsigned my_claim = static_cast<unsigned>(lane) << 21;
       while (head < tail) {
+        // (large frames only: the instantiation for small frames keeps the narrow step's tighter code)
+        if (!MEMBERS_SMEM && tail - head > kWideThreshold) {
+          const int2 r = bfs_wide_step(q, cw, hkey, head, tail, lane, nh, bslot);
+          head += min(32, tail - head);
+          tail += r.x;
+          same += r.y;
+          ++n_steps;
+          continue;
+        }
         // straight-line step (a single warp pays every branch and every dependent instruction in full)
         const int nb = min(8, tail - head);
         unsigned pk = 0;
