@@ -20,7 +20,7 @@
 namespace dpx {
 namespace {
 
-constexpr int kCtaThreads = 128;
+constexpr int kCtaThreads = 256;
 constexpr int kCtaWarps = kCtaThreads / 32;
 // cell word: bits 0-15 slot of the cell's initial bin in the compacted histogram, 16-19 edge mask, 20 alive (planar and
 // unassigned), 21-31 claim field (all ones while idle; see the BFS step)
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
   if (warp == 0) {
     // ================= the sequential chain: createPlaneSegments (plane_extractor.cpp:302-331) ==========
     int remaining = misc[3];
-    const int K = misc[4];
+    const int K4 = (misc[4] + 3) / 4;
     int n_regions = 0, list_off = 0;
     const int slot4 = lane & 3;
     const int delta = (slot4 == 0) ? -nh : (slot4 == 1) ? nh : (slot4 == 2) ? -1 : 1;
@@ -220,7 +220,10 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
       // most frequent bin, first maximum (normals_histogram.cpp:54-56): max key = largest count, smallest slot
       // (slots ascend with the bin ids, so the smallest slot is the smallest bin id)
       unsigned key = 0;
-      for (int i = lane; i < K; i += 32) key = max(key, hkey[i]);
+      for (int i = lane; i < K4; i += 32) {  // four keys per lane and round (entries past the last bin are zero)
+        const uint4 k4 = reinterpret_cast<const uint4*>(hkey)[i];
+        key = max(max(key, max(k4.x, k4.y)), max(k4.z, k4.w));
+      }
       key = __reduce_max_sync(kFull, key);
       const int bc = static_cast<int>(key >> 15), bslot = static_cast<int>(0x7fffu - (key & 0x7fffu));
       const unsigned long long n_cand = bc > 0 ? static_cast<unsigned long long>(bc) : 0ull;
@@ -667,7 +670,7 @@ inline CtaPlan region_grow_cta_plan(const Geometry& g, const Thresholds& th, boo
   p.rec_cap = g.plane_cap < 128 ? g.plane_cap : 128;
   p.off_recs = static_cast<int>(off);    off = align16(off + static_cast<size_t>(p.rec_cap) * kRecFloats * 4);
   p.off_merge = static_cast<int>(off);   off = align16(off + static_cast<size_t>(g.plane_cap) * 4);
-  p.off_misc = static_cast<int>(off);    off = align16(off + 64);
+  p.off_misc = static_cast<int>(off);    off = align16(off + (8 + kCtaWarps) * 4);
   // small frames keep several CTAs per SM; large ones may take (almost) a whole SM's shared memory
   p.bytes = off <= (members_smem ? 100u : 220u) * 1024 ? off : 0;
   return p;
