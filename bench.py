@@ -249,6 +249,9 @@ def run_ours(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # host side of the e2e path: keep this rank's pinned buffers on the GPU's NUMA node
+    from deplex_b200 import sharding
+    numa_node = sharding.bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -337,7 +340,7 @@ def run_ours(a):
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * k_e2e * a.frames / float(t.item()), "unit": UNIT,
+        e2e = {"value": world * k_e2e * a.frames / float(t.item()), "unit": UNIT, "numa_node_rank0": numa_node,
                "h2d_bytes_per_step": int(a.frames * n_px * 12), "d2h_bytes_per_step": int(a.frames * n_px * 4),
                "steps": k_e2e, "api": "dpx_process_batch_host (pinned host buffers, chunked copy/compute overlap)",
                "labels_checksum": int(pin_out.view(-1)[:: 997].to(torch.int64).sum().item())}

@@ -99,5 +99,5 @@ def test_no_cpu_fallback_through_the_bindings(deplex_mod):
 
 
 def test_cpp_binaries_built(lib_built):
-    for exe in ("process_cloud", "test_api"):
+    for exe in ("process_cloud", "process_sequence", "test_api"):
         assert os.access(os.path.join(ROOT, "deplex_b200", "cpp", "build", exe), os.X_OK)

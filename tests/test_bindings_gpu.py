@@ -65,3 +65,20 @@ def test_cpp_class_reference_cases(tmp_path):
     r = subprocess.run([exe, png, os.path.join(GOLDEN, "TUM_fr3_long_val.K"), os.path.join(GOLDEN, "TUM_fr3_long_val.ini"), "5"],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "Number of found planes: 34" in r.stdout, r.stdout + r.stderr
+
+
+def test_cpp_process_sequence_example(tmp_path):
+    """examples/process_sequence.cpp workflow: a directory of PNGs, latency mode and raw-depth batch mode agree."""
+    cv2 = pytest.importorskip("cv2")
+    from deplex_b200 import synth
+    seq = tmp_path / "seq"
+    seq.mkdir()
+    depth, _, _ = load_frame("tum")
+    cv2.imwrite(str(seq / "000.png"), depth)
+    for i in range(1, 5):
+        cv2.imwrite(str(seq / f"{i:03d}.png"), synth.make_depth(480, 640, 60 + i))
+    exe = os.path.join(ROOT, "deplex_b200", "cpp", "build", "process_sequence")
+    r = subprocess.run([exe, str(seq), os.path.join(GOLDEN, "TUM_fr3_long_val.K"), os.path.join(GOLDEN, "TUM_fr3_long_val.ini"), "3"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "modes agree: yes" in r.stdout and "5 frames" in r.stdout
