@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
   // misc: [0] regions published, [1] growing finished, [2] scratch counter, [3] remaining planar cells, [4] K,
   //       [8..8+kCtaWarps) per-warp counts for the ordered compaction
   int* hist_tmp = reinterpret_cast<int*>(list);  // [B2] raw histogram during setup (the list is still unused)
+  int32_t* dummy = reinterpret_cast<int32_t*>(smem + plan.off_misc) + 32;  // [32] per-lane sink of the branch-free BFS tail
 
   const float4* rec_b4 = args.tables.rec_b + 3 * fc;
   const int16_t* bin_in = args.tables.bin + fc;
@@ -220,7 +221,15 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
       // most frequent bin, first maximum (normals_histogram.cpp:54-56): max key = largest count, smallest slot
       // (slots ascend with the bin ids, so the smallest slot is the smallest bin id)
       unsigned key = 0;
-      for (int i = lane; i < K4; i += 32) {  // four keys per lane and round (entries past the last bin are zero)
+      // four keys per lane and load, the first 512 slots without a branch (entries past the last bin are zero)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = lane + 32 * u;
+        uint4 k4 = make_uint4(0u, 0u, 0u, 0u);
+        if (i < K4) k4 = reinterpret_cast<const uint4*>(hkey)[i];
+        key = max(max(key, max(k4.x, k4.y)), max(k4.z, k4.w));
+      }
+      for (int i = lane + 128; i < K4; i += 32) {
         const uint4 k4 = reinterpret_cast<const uint4*>(hkey)[i];
         key = max(max(key, max(k4.x, k4.y)), max(k4.z, k4.w));
       }
@@ -238,19 +247,21 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
         int w = start;
         // four 32-member chunks per round: their loads are independent, so a round costs one memory round trip
         if (end - start <= 32) {
-          // short run (the usual case for the left-over bins that produce one-cell regions): one chunk, no unrolling
+          // short run (the usual case for the left-over bins that produce one-cell regions): one chunk, straight-line
           const int i = start + lane;
           const bool in = i < end;
-          const int c = in ? members[i] : -1;
+          const int c = in ? members[i] : 0;
           const float m = in ? msem[i] : 0.f;
-          const bool alive = in && (cw[c] & kAlive);
-          if (alive) { lm = m; seed = c; }
+          const unsigned wv = in ? cw[c] : 0u;
+          const bool alive = (wv & kAlive) != 0;
           const unsigned am = __ballot_sync(kFull, alive);
-          if (alive && am != ((end - start == 32) ? kFull : ((1u << (end - start)) - 1u))) {
-            const int pos = start + __popc(am & ((1u << lane) - 1u));
-            members[pos] = c;
-            msem[pos] = m;
-          }
+          // stable compaction; lanes without a live member write to their private sink
+          const int pos = start + __popc(am & ((1u << lane) - 1u));
+          int32_t* mdst = alive ? members + pos : dummy + lane;
+          float* sdst = alive ? msem + pos : reinterpret_cast<float*>(dummy) + lane;
+          *mdst = c;
+          *sdst = m;
+          if (alive) { lm = m; seed = c; }
           w = start + __popc(am);
           __syncwarp();
         } else
@@ -292,8 +303,9 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
         const unsigned bb = best ^ ((best >> 31) ? 0x80000000u : 0xffffffffu);
         lm = __uint_as_float(bb);
       }
-      // no candidate with mse < INT_MAX: the reference reads an uninitialised seed id here
-      if (seed == kNoSeed || !(static_cast<double>(lm) < 2147483647.0)) break;
+      // no candidate with mse < INT_MAX: the reference reads an uninitialised seed id here.  (double)lm < 2147483647.0
+      // is lm < 2^31 for a float: the largest float below 2^31 is 2^31 - 128.
+      if (seed == kNoSeed || !(lm < 2147483648.0f)) break;
       if (prof) { const long long t = clock64(); t_seed += t - t_mark; t_mark = t; ++n_seeds; }
 
       // growSeed (plane_extractor.cpp:349-392): batched FIFO BFS into list[list_off ...)
@@ -301,10 +313,12 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
       int same = 0;  // cells of the seed's bin activated by this lane (histogram is settled after the BFS)
       const unsigned seed_w = cw[seed];
       __syncwarp();
-      if (lane == 0) {
-        q[0] = seed | static_cast<int>(((seed_w >> 16) & 0xfu) << 24);
-        cw[seed] = seed_w & ~kAlive;
-        same = 1;
+      {
+        int32_t* qd = lane == 0 ? q : dummy + lane;
+        unsigned* cd = lane == 0 ? cw + seed : reinterpret_cast<unsigned*>(dummy) + lane;
+        *qd = seed | static_cast<int>(((seed_w >> 16) & 0xfu) << 24);
+        *cd = seed_w & ~kAlive;
+        same = lane == 0 ? 1 : 0;
       }
       __syncwarp();
       // a seed without a single passing edge is a region of one cell: no BFS step needed
@@ -344,13 +358,15 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
           if (pass) win = (cw[v] >> 21) == static_cast<unsigned>(lane);
         }
         const unsigned wm = __ballot_sync(kFull, win);
-        if (win) {
-          q[tail + __popc(wm & lt_mask)] = v | static_cast<int>(((w >> 16) & 0xfu) << 24);
-          cw[v] = w & ~kAlive;  // removePoint + unassigned_mask[v] = false (plane_extractor.cpp:324-325); claim idle again
-          const unsigned sl = w & 0xffffu;
-          if (sl == static_cast<unsigned>(bslot)) ++same;
-          else atomicSub(&hkey[sl], 1u << 15);
-        }
+        // branch-free tail: lanes that did not win write to a private dummy word instead of skipping
+        const unsigned sl = w & 0xffffu;
+        const bool other_bin = win && sl != static_cast<unsigned>(bslot);
+        int32_t* qdst = win ? q + tail + __popc(wm & lt_mask) : dummy + lane;
+        unsigned* cdst = win ? cw + v : reinterpret_cast<unsigned*>(dummy) + lane;
+        *qdst = v | static_cast<int>(((w >> 16) & 0xfu) << 24);
+        *cdst = w & ~kAlive;  // removePoint + unassigned_mask[v] = false (plane_extractor.cpp:324-325); claim idle again
+        same += (win && !other_bin) ? 1 : 0;
+        atomicSub(other_bin ? hkey + sl : reinterpret_cast<unsigned*>(dummy) + lane, 1u << 15);
         tail += __popc(wm);
         head += nb;
         ++n_steps;
@@ -670,7 +686,7 @@ inline CtaPlan region_grow_cta_plan(const Geometry& g, const Thresholds& th, boo
   p.rec_cap = g.plane_cap < 128 ? g.plane_cap : 128;
   p.off_recs = static_cast<int>(off);    off = align16(off + static_cast<size_t>(p.rec_cap) * kRecFloats * 4);
   p.off_merge = static_cast<int>(off);   off = align16(off + static_cast<size_t>(g.plane_cap) * 4);
-  p.off_misc = static_cast<int>(off);    off = align16(off + (8 + kCtaWarps) * 4);
+  p.off_misc = static_cast<int>(off);    off = align16(off + (32 + 32) * 4);
   // small frames keep several CTAs per SM; large ones may take (almost) a whole SM's shared memory
   p.bytes = off <= (members_smem ? 100u : 220u) * 1024 ? off : 0;
   return p;
