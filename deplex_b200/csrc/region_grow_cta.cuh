@@ -1,20 +1,30 @@
-// region_grow_cta.cuh -- stage 2 for frames whose working set fits in shared memory (every BASELINE
-// 640x480 / patch >= 6 configuration): one CTA of four warps per frame.
+// region_grow_cta.cuh -- stage 2 for frames of up to ~27 000 cells (every 640x480 configuration, 1280x720 and
+// 1920x1080 at patch 10): one CTA of eight warps per frame; a batch runs all its frames at once and lasts as long
+// as its slowest frame.
 //
-// Same algorithm and the same exactness arguments as region_grow_kernel (region_grow.cu); what changes is
-// who does what, so that only the truly sequential part sits on the critical path:
+// Same algorithm and the same exactness arguments as region_grow_kernel (region_grow.cu); what changes is who does
+// what, so that only the truly sequential part sits on the critical path:
 //
 //   warp 0      the sequential chain of createPlaneSegments (plane_extractor.cpp:302-331): most frequent bin,
-//               seed, FIFO BFS.  One 32-bit word per cell {bin, edge mask, alive} makes a BFS probe a single
-//               shared-memory read; the histogram is a compacted array of keys {count, bin} over the non-empty
-//               bins (one read + one redux for the first-max bin), decremented once per region for the seed's
-//               bin and by rare atomics for the others.
-//   warps 1-3   consume finished regions from a shared-memory ring while warp 0 keeps growing: the fp32
+//               seed, FIFO BFS.  One 32-bit word per cell {histogram slot, edge mask, alive, claim field} makes a
+//               BFS probe a single shared-memory read; the histogram is a compacted array of keys
+//               count << 15 | (0x7fff - slot) over the non-empty bins (slots ascend with the bin ids, so one integer
+//               max is the reference's first-max bin), decremented once per region for the seed's bin and by rare
+//               atomics for the others.  Two queue entries that reach the same cell in one step are ordered by a
+//               shared-memory atomicMin on the claim field (lowest lane = earliest in FIFO order).
+//               This chain is written branch-free where it can be -- predicated loads, an unrolled key scan, and
+//               per-lane dummy sinks for the stores and atomics of lanes that have nothing to write: a single
+//               warp pays every taken branch and every dependent instruction in full.
+//   warps 1-7   consume finished regions from a shared-memory ring while warp 0 keeps growing: the fp32
 //               moment chains over the region's FIFO list (plane_extractor.cpp:318-327).
 //   all warps   setup (histogram, grouping by bin), then after growing: plane fits one region per thread
 //               (:333-337), ordered compaction into segment ids, labels_map_ painting (:339-342), adjacency
 //               bit matrix (:430-453), final per-cell labels (:464-465).  findMergedLabels (:402-423) is a
 //               short sequential loop run by warp 0 on shared-memory plane records.
+//
+// MEMBERS_SMEM = false (frames above ~6 000 cells): the member runs and the adjacency matrix live in the L2-resident
+// `pairs` table, cell words and queue stay in shared memory (one CTA per SM), and wide frontiers take
+// bfs_wide_step (one lane per queue entry, 32 entries per step).
 #pragma once
 
 namespace dpx {
