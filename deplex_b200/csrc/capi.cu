@@ -423,6 +423,17 @@ dpx_status process_host_impl(dpx_extractor* ex, const void* src, size_t bytes_pe
     for (int i = 0; i < 2; ++i) DPX_CUDA(ex, cudaMalloc(&ex->d_depth[i], std::max<size_t>(16, np * sizeof(uint16_t) * chunk)));
   if (!is_depth && !ex->d_xyz[0])
     for (int i = 0; i < 2; ++i) DPX_CUDA(ex, cudaMalloc(&ex->d_xyz[i], std::max<size_t>(16, np * 3 * sizeof(float) * chunk)));
+  if (n_frames <= chunk) {
+    // latency path (a single process() call): everything on one stream, no cross-stream hand-offs
+    void* d_in = is_depth ? static_cast<void*>(ex->d_depth[0]) : static_cast<void*>(ex->d_xyz[0]);
+    DPX_CUDA(ex, cudaMemcpyAsync(d_in, src, bytes_per_frame * n_frames, cudaMemcpyHostToDevice, ex->s_run));
+    st = is_depth ? run_stages(ex, nullptr, n_frames, layout, ex->d_lab[0], ex->s_run, ex->d_depth[0], pin)
+                  : run_stages(ex, ex->d_xyz[0], n_frames, layout, ex->d_lab[0], ex->s_run);
+    if (st != DPX_OK) return st;
+    DPX_CUDA(ex, cudaMemcpyAsync(labels, ex->d_lab[0], np * sizeof(int32_t) * n_frames, cudaMemcpyDeviceToHost, ex->s_run));
+    DPX_CUDA(ex, cudaStreamSynchronize(ex->s_run));
+    return DPX_OK;
+  }
   int n_chunks = 0;
   for (int f0 = 0; f0 < n_frames; f0 += chunk, ++n_chunks) {
     const int slot = n_chunks & 1;
