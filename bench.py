@@ -376,10 +376,12 @@ def run_ours(a):
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
     n_cells = ex.info.n_cells
+    # frames whose pixels the region-growing kernel paints itself (fused stage 3): all but max(2, F/8) per batch
+    fused = (a.frames - min(a.frames, max(2, a.frames // 8))) if ex.info.fused_labeling else 0
     alg_bytes = {  # algorithmic bytes per launch
         "cell_stats": a.frames * n_px * 12,
-        "region_grow": a.frames * n_cells * 82,
-        "labeling": a.frames * n_px * 4,
+        "region_grow": a.frames * n_cells * 82 + fused * n_px * 4,
+        "labeling": (a.frames - fused) * n_px * 4,
     }
     stages = {}
     for k in ("cell_stats", "region_grow", "labeling"):
@@ -391,7 +393,7 @@ def run_ours(a):
     pipeline_bytes = a.frames * n_px * 16  # 12 B/px read once + 4 B/px written once
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": stages[dominant]["gbs"], "peak": peak,
                 "unit": "GB/s", "frac": stages[dominant]["frac"], "traffic": measured_traffic(dominant),
-                "peak_source": peak_src, "stages": stages,
+                "peak_source": peak_src, "stages": stages, "fused_label_frames": fused,
                 "pipeline": {"algorithmic_bytes": pipeline_bytes, "gbs": pipeline_bytes / (step_ms * 1e-3) / 1e9,
                              "frac": pipeline_bytes / (step_ms * 1e-3) / 1e9 / peak,
                              "note": "whole step, 16 B/pixel/frame; the region-growing stage is latency-bound by construction"}}

@@ -38,7 +38,7 @@ class dpx_intrinsics(C.Structure):
 
 class dpx_info(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("height", "width", "patch_size", "cells_x", "cells_y", "n_cells",
-                                          "plane_capacity", "max_batch", "device", "sm_count")]
+                                          "plane_capacity", "max_batch", "device", "sm_count", "fused_labeling")]
 
 
 class dpx_cell(C.Structure):

@@ -40,6 +40,7 @@ struct dpx_extractor {
   int tile_cells = 0;
   int stream_warps = 16;      // env DPX_STREAM_WARPS=8|12|16 (A/B measurement)
   int force_tile_kernel = 0;  // env DPX_CELL_KERNEL=tile (A/B measurement of the two stage-1 kernels)
+  int fuse_labeling = 1;      // env DPX_FUSE_LABELING=0: keep stage 3 as its own kernel (A/B measurement)
   RegionPlan plan{};
   uint32_t* mt_init = nullptr;       // std::mt19937 default state for the refinement stage
   long long* region_prof = nullptr;  // [max_batch][kRegionProfSlots], written while profiling is on
@@ -116,6 +117,7 @@ size_t carve_tables(const Geometry& g, int max_batch, bool bins_in_smem, char* b
   tb->queue = reinterpret_cast<int32_t*>(take(F * C * sizeof(int32_t)));
   tb->pairs = reinterpret_cast<uint32_t*>(take(F * C * 2 * sizeof(uint32_t)));
   tb->bin_work = reinterpret_cast<int16_t*>(take(bins_in_smem ? 0 : F * C * sizeof(int16_t)));
+  tb->paint_state = reinterpret_cast<int32_t*>(take((F + 2) * sizeof(int32_t)));
   tb->segs = reinterpret_cast<float*>(take(F * P * kSegFloats * sizeof(float)));
   tb->merge = reinterpret_cast<int32_t*>(take(F * P * sizeof(int32_t)));
   tb->n_planes = reinterpret_cast<int32_t*>(take(F * sizeof(int32_t)));
@@ -169,6 +171,7 @@ dpx_status run_stages(dpx_extractor* ex, const float* d_xyz, int n_frames, int l
     ++ex->launches;
   }
   if (prof) DPX_CUDA(ex, cudaEventRecord(ex->e_stage[1], st));
+  bool labels_painted = false;
   if (ex->geom.n_cells > 0) {
     RegionArgs ra{};
     ra.n_frames = n_frames;
@@ -177,16 +180,19 @@ dpx_status run_stages(dpx_extractor* ex, const float* d_xyz, int n_frames, int l
     ra.geom = ex->geom;
     ra.thr = ex->thr;
     ra.tables = ex->tb;
-    DPX_CUDA(ex, launch_region_grow(ra, st));
+    ra.labels = ex->fuse_labeling ? d_labels : nullptr;
+    DPX_CUDA(ex, launch_region_grow(ra, st, &labels_painted));
     ex->launches += 2;  // edge masks + region growing
   }
   if (prof) DPX_CUDA(ex, cudaEventRecord(ex->e_stage[2], st));
   {
+    // stage 3; frames the region-growing kernel has already painted are skipped (their flag is set)
     LabelArgs la{};
     la.n_frames = n_frames;
     la.geom = ex->geom;
     la.cell_label = ex->tb.cell_label;
     la.labels = d_labels;
+    la.todo = labels_painted ? ex->tb.paint_state + 1 : nullptr;
     DPX_CUDA(ex, launch_labeling(la, st));
     if (ex->geom.n_cells > 0) ++ex->launches;
   }
@@ -330,6 +336,7 @@ dpx_status dpx_create(int32_t height, int32_t width, const dpx_config* cfg_in, i
     ex->tile_cells = cell_stats_tile_cells(g.patch, g.nh);
     if (const char* e = std::getenv("DPX_STREAM_WARPS")) { const int w = std::atoi(e); ex->stream_warps = (w == 8 || w == 12) ? w : 16; }
     if (const char* e = std::getenv("DPX_CELL_KERNEL")) ex->force_tile_kernel = std::strcmp(e, "tile") == 0;
+    if (const char* e = std::getenv("DPX_FUSE_LABELING")) ex->fuse_labeling = std::atoi(e) != 0;
     ex->plan = region_grow_plan(g, th);
     Tables probe{};
     ex->scratch_bytes = carve_tables(g, max_batch, ex->plan.bins_smem != 0, nullptr, &probe);
@@ -392,6 +399,7 @@ dpx_status dpx_get_info(const dpx_extractor* ex, dpx_info* info) {
   info->max_batch = ex->max_batch;
   info->device = ex->device;
   info->sm_count = ex->sm_count;
+  info->fused_labeling = (ex->fuse_labeling && region_grow_uses_cta(ex->geom, ex->thr)) ? 1 : 0;
   return DPX_OK;
 }
 

@@ -25,7 +25,11 @@ __global__ void __launch_bounds__(kLabelThreads) labeling_kernel(const LabelArgs
   const int col = (blockIdx.x * kLabelThreads + threadIdx.x) * 4;
   if (col >= g.width) return;
   const int cell_row = blockIdx.y;
-  const int frame = blockIdx.z;
+  int frame = blockIdx.z;
+  if (args.todo != nullptr) {
+    if (frame >= args.todo[0]) return;
+    frame = args.todo[1 + frame];
+  }
   const int32_t* cl = args.cell_label + static_cast<long long>(frame) * g.n_cells + static_cast<long long>(cell_row) * g.nh;
   int32_t* out = args.labels + static_cast<long long>(frame) * g.n_points +
                  static_cast<long long>(cell_row) * p * g.width + col;
@@ -56,7 +60,7 @@ cudaError_t launch_labeling(const LabelArgs& args, cudaStream_t stream) {
   if (g.n_cells == 0)  // enormous patch: no cells, all labels zero (plane_extractor.cpp:230-232)
     return cudaMemsetAsync(args.labels, 0, sizeof(int32_t) * g.n_points * args.n_frames, stream);
   const int groups = (g.width + 3) / 4;
-  dim3 grid((groups + kLabelThreads - 1) / kLabelThreads, g.nv, args.n_frames);
+  dim3 grid((groups + kLabelThreads - 1) / kLabelThreads, g.nv, args.todo ? labeling_deferred_frames(args.n_frames) : args.n_frames);
   labeling_kernel<<<grid, kLabelThreads, 0, stream>>>(args);
   return cudaGetLastError();
 }

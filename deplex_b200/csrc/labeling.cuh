@@ -9,8 +9,12 @@ struct LabelArgs {
   Geometry geom;
   const int32_t* cell_label;  // [F][C]
   int32_t* labels;            // [F][H*W]
+  const int32_t* todo;        // optional {count, frame ids...}: only these frames are painted (the region-growing
+                              // kernel has painted the others); nullptr = all frames
 };
 
 cudaError_t launch_labeling(const LabelArgs& args, cudaStream_t stream);
+// frames the fused painting of region_grow_cta_kernel leaves to stage 3: the slowest eighth by finishing order
+__host__ __device__ inline int labeling_deferred_frames(int n_frames) { const int d = n_frames / 8 > 2 ? n_frames / 8 : 2; return d < n_frames ? d : n_frames; }
 
 }  // namespace dpx

@@ -89,6 +89,11 @@ __global__ void __launch_bounds__(256) edge_mask_kernel(const RegionArgs args) {
   if (idx >= total) return;
   const int c = static_cast<int>(idx % g.n_cells);
   const long long base = idx - c;  // first cell of this frame
+  if (idx == 0) {
+    // reset the fused-painting bookkeeping of this batch (region_grow_cta_kernel runs after this kernel)
+    args.tables.paint_state[0] = 0;
+    args.tables.paint_state[1] = 0;
+  }
   const int r = c / g.nh, q = c - r * g.nh;
   unsigned mask = 0;
   if (args.tables.bin[idx] >= 0) {
@@ -603,7 +608,20 @@ RegionPlan region_grow_plan(const Geometry& g, const Thresholds& th) {
   return p;
 }
 
-cudaError_t launch_region_grow(const RegionArgs& args, cudaStream_t stream) {
+namespace {
+bool force_warp_kernel_env() {
+  static const bool v = std::getenv("DPX_REGION_KERNEL") && std::strcmp(std::getenv("DPX_REGION_KERNEL"), "warp") == 0;
+  return v;
+}
+}  // namespace
+
+bool region_grow_uses_cta(const Geometry& g, const Thresholds& th) {
+  if (g.n_cells == 0 || force_warp_kernel_env()) return false;
+  return region_grow_cta_plan(g, th, true).bytes > 0 || region_grow_cta_plan(g, th, false).bytes > 0;
+}
+
+cudaError_t launch_region_grow(const RegionArgs& args, cudaStream_t stream, bool* painted) {
+  if (painted) *painted = false;
   if (args.n_frames == 0) return cudaSuccess;
   const long long cells = static_cast<long long>(args.n_frames) * args.geom.n_cells;
   edge_mask_kernel<<<static_cast<unsigned>((cells + 255) / 256), 256, 0, stream>>>(args);
@@ -612,7 +630,7 @@ cudaError_t launch_region_grow(const RegionArgs& args, cudaStream_t stream) {
   CtaPlan cta = region_grow_cta_plan(args.geom, args.thr, true);
   const bool members_smem = cta.bytes > 0;
   if (!members_smem) cta = region_grow_cta_plan(args.geom, args.thr, false);
-  static const bool force_warp_kernel = std::getenv("DPX_REGION_KERNEL") && std::strcmp(std::getenv("DPX_REGION_KERNEL"), "warp") == 0;
+  const bool force_warp_kernel = force_warp_kernel_env();
   const bool all_smem = args.plan.bins_smem && args.plan.list_smem && args.plan.members_smem && args.plan.merge_smem;
   if (cta.bytes > 0 && !force_warp_kernel) {
     if (members_smem) {
@@ -622,6 +640,7 @@ cudaError_t launch_region_grow(const RegionArgs& args, cudaStream_t stream) {
       cudaFuncSetAttribute(region_grow_cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cta.bytes));
       region_grow_cta_kernel<false><<<args.n_frames, kCtaThreads, cta.bytes, stream>>>(args, cta);
     }
+    if (painted) *painted = args.labels != nullptr;
   } else if (all_smem) {
     cudaFuncSetAttribute(region_grow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(args.plan.bytes));
     region_grow_kernel<true><<<args.n_frames, 32, args.plan.bytes, stream>>>(args);

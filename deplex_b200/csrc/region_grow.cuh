@@ -16,6 +16,7 @@ constexpr int kRegionProfSlots = 12;
 struct RegionArgs {
   int n_frames;
   long long* prof;  // optional [F][kRegionProfSlots] per-phase cycle counters, or nullptr
+  int32_t* labels;  // optional [F][H*W]: when set and the CTA kernel runs, it also paints the per-pixel labels (stage 3 fused)
   RegionPlan plan;
   Geometry geom;
   Thresholds thr;
@@ -23,6 +24,9 @@ struct RegionArgs {
 };
 
 RegionPlan region_grow_plan(const Geometry& g, const Thresholds& th);
-cudaError_t launch_region_grow(const RegionArgs& args, cudaStream_t stream);
+// whether launch_region_grow takes the CTA kernel (which can paint the pixel labels itself) for this geometry
+bool region_grow_uses_cta(const Geometry& g, const Thresholds& th);
+// *painted (optional) tells the caller whether the per-pixel labels were written, i.e. whether stage 3 is still needed
+cudaError_t launch_region_grow(const RegionArgs& args, cudaStream_t stream, bool* painted = nullptr);
 
 }  // namespace dpx

@@ -26,6 +26,7 @@
 // `pairs` table, cell words and queue stay in shared memory (one CTA per SM), and wide frontiers take
 // bfs_wide_step (one lane per queue entry, 32 entries per step).
 #pragma once
+#include "labeling.cuh"
 
 namespace dpx {
 namespace {
@@ -645,11 +646,56 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
   const long long t_merge_end = prof ? clock64() : 0;
 
   // ---- per-cell final labels (plane_extractor.cpp:464-465), plane records back to the global tables ---------
+  int32_t* final_lab = list;  // [C] the queue storage is free now
   for (int c = tid; c < C; c += kCtaThreads) {
     const int l = static_cast<int>(cw[c]);
-    cell_label[c] = (l == 0) ? 0 : merge[l - 1] + 1;
+    const int fl = (l == 0) ? 0 : merge[l - 1] + 1;
+    cell_label[c] = fl;
+    final_lab[c] = fl;
   }
   for (int i = tid; i < nseg; i += kCtaThreads) merge_out[i] = merge[i];
+  // toImageLabels (plane_extractor.cpp:455-470) fused: a frame's pixels are painted as soon as its own region growing is
+  // done, so the 4 B/pixel write stream of the faster frames overlaps the chains of the slower ones.  The slowest
+  // eighth of the batch (by finishing order) leaves its pixels to the labeling kernel that follows: one CTA writing
+  // 1.2 MB alone at the very end would only lengthen the tail.
+  if (args.labels != nullptr) {
+    if (tid == 0) misc[2] = atomicAdd(&args.tables.paint_state[0], 1);
+    __syncthreads();
+  }
+  const bool paint_here = args.labels != nullptr && misc[2] < args.n_frames - labeling_deferred_frames(args.n_frames);
+  if (args.labels != nullptr && !paint_here && tid == 0) {
+    const int slot = atomicAdd(&args.tables.paint_state[1], 1);
+    args.tables.paint_state[2 + slot] = frame;
+  }
+  if (paint_here) {
+    const int p = g.patch, width = g.width;
+    int32_t* out = args.labels + static_cast<long long>(frame) * g.n_points;
+    const int groups = (width + 3) / 4;  // groups of 4 consecutive pixels of one image row
+    const bool vec = (width & 3) == 0;
+    for (int item = tid; item < nv * groups; item += kCtaThreads) {
+      const int cr = item / groups, gi = item - cr * groups;
+      const int col = gi * 4;
+      int cq = col / p, rem = col - cq * p;
+      int lab[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        lab[i] = (col + i < width) ? final_lab[cr * nh + cq] : 0;
+        if (++rem == p) { rem = 0; ++cq; }
+      }
+      int32_t* dst = out + static_cast<long long>(cr) * p * width + col;
+      if (vec) {
+        const int4 v4 = make_int4(lab[0], lab[1], lab[2], lab[3]);
+        for (int r = 0; r < p; ++r)
+          asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(dst + static_cast<long long>(r) * width),
+                       "r"(v4.x), "r"(v4.y), "r"(v4.z), "r"(v4.w)
+                       : "memory");
+      } else {
+        for (int r = 0; r < p; ++r)
+          for (int i = 0; i < 4; ++i)
+            if (col + i < width) dst[static_cast<long long>(r) * width + i] = lab[i];
+      }
+    }
+  }
   {
     const int n_smem = min(nseg, plan.rec_cap);
     for (int i = tid; i < n_smem * kSegFloats; i += kCtaThreads) segs_g[i] = recs[i];

@@ -26,7 +26,8 @@ def test_struct_layouts_match_header(lib_built):
     assert C.sizeof(_capi.dpx_config) == 64
     assert C.sizeof(_capi.dpx_cell) == 4 * (3 + 6 + 3 + 3 + 4 + 5)
     assert C.sizeof(_capi.dpx_plane) == 4 * 11
-    assert C.sizeof(_capi.dpx_info) == 40
+    assert C.sizeof(_capi.dpx_info) == 44
+    assert C.sizeof(_capi.dpx_intrinsics) == 16
 
 
 def test_config_defaults_and_ini(lib_built, tmp_path):
