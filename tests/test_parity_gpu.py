@@ -287,3 +287,28 @@ def test_config_sweep_matches_oracle(oracle_mod, idx):
             assert exact.mean() >= 0.995
             assert np.array_equal(planes["merge_label"], dbg["merge_labels"][:n])
             assert np.array_equal(planes["n_points"], dbg["plane_npts"][:n])
+
+
+@pytest.mark.parametrize("n_frames", [1, 2, 3, 9, 40])
+def test_fused_label_painting_equals_separate_kernel(oracle_mod, n_frames, monkeypatch):
+    """Stage 3 is partly fused into the region-growing kernel (frames that finish early paint their own pixels, the
+    slowest max(2, F/8) are left to the labeling kernel).  Whatever the split, every frame's labels must be those of
+    the unfused pipeline (DPX_FUSE_LABELING=0) and of the oracle, also when the same handle is reused."""
+    from deplex_b200 import Config, PlaneExtractor, synth, LAYOUT_ROWMAJOR
+    h, w = 480, 640
+    batch = synth.make_batch(h, w, 7000, n_frames, "rowmajor")
+    fused = PlaneExtractor(h, w, Config(), max_batch=n_frames)
+    assert fused.info.fused_labeling == 1
+    monkeypatch.setenv("DPX_FUSE_LABELING", "0")
+    plain = PlaneExtractor(h, w, Config(), max_batch=n_frames)
+    monkeypatch.delenv("DPX_FUSE_LABELING")
+    assert plain.info.fused_labeling == 0
+    want = plain.process_batch_host(batch, LAYOUT_ROWMAJOR)
+    for _ in range(3):  # reuse: the painting bookkeeping is reset every batch
+        got = fused.process_batch_host(batch, LAYOUT_ROWMAJOR)
+        assert np.array_equal(got, want)
+    got = fused.process_batch_host(batch[: max(1, n_frames // 2)], LAYOUT_ROWMAJOR)  # smaller batch on the same handle
+    assert np.array_equal(got, want[: max(1, n_frames // 2)])
+    ocfg = oracle_mod.OracleConfig()
+    for f in range(min(n_frames, 3)):
+        assert np.array_equal(want[f], oracle_mod.process(h, w, ocfg, batch[f]))
