@@ -32,7 +32,7 @@ UNIT = "frames/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=256, help="frames per batch (per GPU)")
@@ -191,7 +191,7 @@ def measured_traffic(kernel):
         return None
 
 
-def cpu_baseline(a, host_batch, threads, sample_frames):
+def cpu_baseline(a, host_batch, threads, sample_frames, passes=1):
     """The oracle (a port of the reference's CPU algorithm) timed on this box's host cores."""
     import oracle
     from deplex_b200 import Config
@@ -200,9 +200,10 @@ def cpu_baseline(a, host_batch, threads, sample_frames):
     sample = host_batch[:sample_frames]
     oracle.process_batch(a.height, a.width, cfg, sample[: max(1, threads)], layout, threads)  # warm
     t0 = time.perf_counter()
-    oracle.process_batch(a.height, a.width, cfg, sample, layout, threads)
+    for _ in range(passes):
+        oracle.process_batch(a.height, a.width, cfg, sample, layout, threads)
     dt = time.perf_counter() - t0
-    return sample.shape[0] / dt, dt
+    return passes * sample.shape[0] / dt, dt
 
 
 def run_reference(a):
@@ -413,12 +414,11 @@ def run_ours(a):
         out["latency"] = latency_mode(dev)
     if world == 1 and not a.no_cpu_baseline:
         n = a.cpu_sample_frames or a.frames
-        reps = 4
-        sample = np.concatenate([host_np[:n]] * reps, axis=0)
-        v, dt = cpu_baseline(a, sample, 1, sample.shape[0])
+        reps = max(1, round(14 * (640 * 480 * 256) / (n_px * n)))  # ~10 s of single-thread work
+        v, dt = cpu_baseline(a, host_np, 1, n, passes=reps)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                               "sample": f"{sample.shape[0]} frames ({n} of this batch x{reps}), 1 thread (the reference is "
-                                         f"single-threaded by default), {dt:.1f} s; host has {os.cpu_count()} cores"}
+                               "sample": f"{n * reps} frames ({n} frames of this batch x{reps} passes), 1 thread (the reference "
+                                         f"is single-threaded by default), {dt:.1f} s; host has {os.cpu_count()} cores"}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
