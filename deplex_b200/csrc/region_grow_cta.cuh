@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
     // ================= consumers: region moments in FIFO order (plane_extractor.cpp:318-327) ================
     float* stage = stage_all + (warp - 1) * 32 * 12;
     for (int r = warp - 1;; r += kCtaWarps - 1) {
-      while (misc[0] <= r && misc[1] == 0) __nanosleep(64);
+      while (misc[0] <= r && misc[1] == 0) __nanosleep(2000);
       if (misc[0] <= r) {
         // growing may have finished between the two reads: look once more
         __threadfence_block();
