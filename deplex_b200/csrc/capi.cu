@@ -117,6 +117,7 @@ size_t carve_tables(const Geometry& g, int max_batch, bool bins_in_smem, char* b
   tb->queue = reinterpret_cast<int32_t*>(take(F * C * sizeof(int32_t)));
   tb->pairs = reinterpret_cast<uint32_t*>(take(F * C * 2 * sizeof(uint32_t)));
   tb->bin_work = reinterpret_cast<int16_t*>(take(bins_in_smem ? 0 : F * C * sizeof(int16_t)));
+  tb->cell_words = reinterpret_cast<uint32_t*>(take(F * C * sizeof(uint32_t)));
   tb->paint_state = reinterpret_cast<int32_t*>(take((F + 2) * sizeof(int32_t)));
   tb->segs = reinterpret_cast<float*>(take(F * P * kSegFloats * sizeof(float)));
   tb->merge = reinterpret_cast<int32_t*>(take(F * P * sizeof(int32_t)));

@@ -615,10 +615,28 @@ bool force_warp_kernel_env() {
 }
 }  // namespace
 
-bool region_grow_uses_cta(const Geometry& g, const Thresholds& th) {
-  if (g.n_cells == 0 || force_warp_kernel_env()) return false;
-  return region_grow_cta_plan(g, th, true).bytes > 0 || region_grow_cta_plan(g, th, false).bytes > 0;
+namespace {
+// 0 / 1 / 2 = storage mode of region_grow_cta_kernel, -1 = the generic single-warp kernels
+int cta_mode(const Geometry& g, const Thresholds& th, CtaPlan* plan) {
+  if (g.n_cells == 0 || force_warp_kernel_env()) return -1;
+  for (int mode = 0; mode <= 2; ++mode) {
+    const CtaPlan p = region_grow_cta_plan(g, th, mode);
+    if (p.bytes > 0) {
+      if (plan) *plan = p;
+      return mode;
+    }
+  }
+  return -1;
 }
+template <int MODE>
+cudaError_t launch_cta(const RegionArgs& args, const CtaPlan& plan, cudaStream_t stream) {
+  cudaFuncSetAttribute(region_grow_cta_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.bytes));
+  region_grow_cta_kernel<MODE><<<args.n_frames, kCtaThreads, plan.bytes, stream>>>(args, plan);
+  return cudaGetLastError();
+}
+}  // namespace
+
+bool region_grow_uses_cta(const Geometry& g, const Thresholds& th) { return cta_mode(g, th, nullptr) >= 0; }
 
 cudaError_t launch_region_grow(const RegionArgs& args, cudaStream_t stream, bool* painted) {
   if (painted) *painted = false;
@@ -627,21 +645,14 @@ cudaError_t launch_region_grow(const RegionArgs& args, cudaStream_t stream, bool
   edge_mask_kernel<<<static_cast<unsigned>((cells + 255) / 256), 256, 0, stream>>>(args);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  CtaPlan cta = region_grow_cta_plan(args.geom, args.thr, true);
-  const bool members_smem = cta.bytes > 0;
-  if (!members_smem) cta = region_grow_cta_plan(args.geom, args.thr, false);
-  const bool force_warp_kernel = force_warp_kernel_env();
-  const bool all_smem = args.plan.bins_smem && args.plan.list_smem && args.plan.members_smem && args.plan.merge_smem;
-  if (cta.bytes > 0 && !force_warp_kernel) {
-    if (members_smem) {
-      cudaFuncSetAttribute(region_grow_cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cta.bytes));
-      region_grow_cta_kernel<true><<<args.n_frames, kCtaThreads, cta.bytes, stream>>>(args, cta);
-    } else {
-      cudaFuncSetAttribute(region_grow_cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cta.bytes));
-      region_grow_cta_kernel<false><<<args.n_frames, kCtaThreads, cta.bytes, stream>>>(args, cta);
-    }
+  CtaPlan cta{};
+  const int mode = cta_mode(args.geom, args.thr, &cta);
+  if (mode >= 0) {
     if (painted) *painted = args.labels != nullptr;
-  } else if (all_smem) {
+    return mode == 0 ? launch_cta<0>(args, cta, stream) : mode == 1 ? launch_cta<1>(args, cta, stream) : launch_cta<2>(args, cta, stream);
+  }
+  const bool all_smem = args.plan.bins_smem && args.plan.list_smem && args.plan.members_smem && args.plan.merge_smem;
+  if (all_smem) {
     cudaFuncSetAttribute(region_grow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(args.plan.bytes));
     region_grow_kernel<true><<<args.n_frames, 32, args.plan.bytes, stream>>>(args);
   } else {

@@ -54,6 +54,7 @@ __device__ __noinline__ void fit_plane_call(const Moments& m, PlaneFit& f) { fit
 // cell word's claim field with a shared-memory atomicMin.  Kept out of line so that the narrow step's register
 // allocation is not disturbed.  Returns {cells appended, appended cells that belong to the seed's bin}.
 constexpr int kWideThreshold = 12;
+template <bool BIG_GLOBAL>
 __device__ __noinline__ int2 bfs_wide_step(int32_t* q, unsigned* cw, unsigned* hkey, int head, int tail, int lane, int nh,
                                            int bslot) {
   const int nbw = min(32, tail - head);
@@ -80,7 +81,8 @@ __device__ __noinline__ int2 bfs_wide_step(int32_t* q, unsigned* cw, unsigned* h
     __syncwarp();
 #pragma unroll
     for (int sl4 = 0; sl4 < 4; ++sl4)
-      if ((passm & (1u << sl4)) && (cw[vv[sl4]] >> 21) != static_cast<unsigned>(lane * 4 + sl4)) winm &= ~(1u << sl4);
+      if ((passm & (1u << sl4)) && ((BIG_GLOBAL ? __ldcg(cw + vv[sl4]) : cw[vv[sl4]]) >> 21) != static_cast<unsigned>(lane * 4 + sl4))
+        winm &= ~(1u << sl4);
   }
   // append position of (lane, slot) = winners of lower lanes + own lower slots
   const unsigned nwin = __popc(winm);
@@ -110,8 +112,13 @@ __device__ __noinline__ int2 bfs_wide_step(int32_t* q, unsigned* cw, unsigned* h
 
 // MEMBERS_SMEM = false: the member runs (and later the adjacency bit matrix) live in the global scratch table
 // `pairs` (8 bytes per cell, L2-resident) so that frames of up to ~27 000 cells keep the BFS state in shared memory.
-template <bool MEMBERS_SMEM>
+// MODE 0: everything in shared memory.  MODE 1: member runs / adjacency matrix in the global `pairs` table.
+// MODE 2 (frames above ~27 000 cells): cell words and queue in global memory as well (L2-resident, ~10x the latency
+// of shared memory per probe, but the same algorithmic structure instead of the single-warp fallback).
+template <int MODE>
 __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const RegionArgs args, const CtaPlan plan) {
+  constexpr bool MEMBERS_SMEM = MODE == 0;
+  constexpr bool BIG_GLOBAL = MODE == 2;
   extern __shared__ float4 smem_f4[];
   const Geometry& g = args.geom;
   const Thresholds& th = args.thr;
@@ -127,8 +134,9 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
   int16_t* binslot = reinterpret_cast<int16_t*>(smem + plan.off_binslot);    // [B2] bin -> slot in hkey (or -1)
   int* bin_off = reinterpret_cast<int*>(smem + plan.off_binoff);             // [K] start of the bin's member run
   int* run_end = reinterpret_cast<int*>(smem + plan.off_runend);             // [K] end of its still-unassigned members
-  unsigned* cw = reinterpret_cast<unsigned*>(smem + plan.off_cw);            // [C] cell words; later the segment labels
-  int32_t* list = reinterpret_cast<int32_t*>(smem + plan.off_list);          // [C] BFS queues = region cell lists
+  // [C] cell words (later the segment labels) and [C] BFS queues = region cell lists
+  unsigned* cw = BIG_GLOBAL ? args.tables.cell_words + fc : reinterpret_cast<unsigned*>(smem + plan.off_cw);
+  int32_t* list = BIG_GLOBAL ? args.tables.queue + fc : reinterpret_cast<int32_t*>(smem + plan.off_list);
   // [C] cell ids grouped by initial bin, and [C] their MSE in the same order
   int32_t* members = MEMBERS_SMEM ? reinterpret_cast<int32_t*>(smem + plan.off_members)
                                   : reinterpret_cast<int32_t*>(args.tables.pairs + 2 * fc);
@@ -340,7 +348,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
       while (head < tail) {
         // (large frames only: the instantiation for small frames keeps the narrow step's tighter code)
         if (!MEMBERS_SMEM && tail - head > kWideThreshold) {
-          const int2 r = bfs_wide_step(q, cw, hkey, head, tail, lane, nh, bslot);
+          const int2 r = bfs_wide_step<BIG_GLOBAL>(q, cw, hkey, head, tail, lane, nh, bslot);
           head += min(32, tail - head);
           tail += r.x;
           same += r.y;
@@ -366,7 +374,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
         if (nib & (nib - 1u)) {
           if (pass) atomicMin(&cw[v], (w & ~kClaimIdle) | my_claim);
           __syncwarp();
-          if (pass) win = (cw[v] >> 21) == static_cast<unsigned>(lane);
+          if (pass) win = ((BIG_GLOBAL ? __ldcg(cw + v) : cw[v]) >> 21) == static_cast<unsigned>(lane);
         }
         const unsigned wm = __ballot_sync(kFull, win);
         // branch-free tail: lanes that did not win write to a private dummy word instead of skipping
@@ -719,7 +727,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
 }
 
 // Shared-memory layout of the CTA kernel; bytes == 0 means "does not fit, use the generic kernel".
-inline CtaPlan region_grow_cta_plan(const Geometry& g, const Thresholds& th, bool members_smem) {
+inline CtaPlan region_grow_cta_plan(const Geometry& g, const Thresholds& th, int mode) {
   CtaPlan p{};
   auto align16 = [](size_t v) { return (v + 15) & ~static_cast<size_t>(15); };
   const size_t B2 = static_cast<size_t>(th.histogram_bins_per_coord) * th.histogram_bins_per_coord;
@@ -730,9 +738,11 @@ inline CtaPlan region_grow_cta_plan(const Geometry& g, const Thresholds& th, boo
   p.off_binslot = static_cast<int>(off); off = align16(off + B2 * 2);
   p.off_binoff = static_cast<int>(off);  off = align16(off + B2 * 4);
   p.off_runend = static_cast<int>(off);  off = align16(off + B2 * 4);
-  p.off_cw = static_cast<int>(off);      off = align16(off + C * 4);
-  p.off_list = static_cast<int>(off);    off = align16(off + (C > B2 ? C : B2) * 4);
-  if (members_smem) {
+  if (mode <= 1) {
+    p.off_cw = static_cast<int>(off);      off = align16(off + C * 4);
+    p.off_list = static_cast<int>(off);    off = align16(off + (C > B2 ? C : B2) * 4);
+  }
+  if (mode == 0) {
     p.off_members = static_cast<int>(off); off = align16(off + C * 4);
     p.off_msem = static_cast<int>(off);    off = align16(off + C * 4);
     p.adj_bytes = static_cast<int>(off - p.off_members);
@@ -744,7 +754,9 @@ inline CtaPlan region_grow_cta_plan(const Geometry& g, const Thresholds& th, boo
   p.off_merge = static_cast<int>(off);   off = align16(off + static_cast<size_t>(g.plane_cap) * 4);
   p.off_misc = static_cast<int>(off);    off = align16(off + (32 + 32) * 4);
   // small frames keep several CTAs per SM; large ones may take (almost) a whole SM's shared memory
-  p.bytes = off <= (members_smem ? 100u : 220u) * 1024 ? off : 0;
+  p.bytes = off <= (mode == 0 ? 100u : 220u) * 1024 ? off : 0;
+  // mode 2 keeps the queue in global memory, where the raw histogram of the setup needs B2 words (C >= B2 or not)
+  if (mode == 2 && C < B2) p.bytes = 0;
   return p;
 }
 
