@@ -22,9 +22,8 @@
 //               bit matrix (:430-453), final per-cell labels (:464-465).  findMergedLabels (:402-423) is a
 //               short sequential loop run by warp 0 on shared-memory plane records.
 //
-// MEMBERS_SMEM = false (frames above ~6 000 cells): the member runs and the adjacency matrix live in the L2-resident
-// `pairs` table, cell words and queue stay in shared memory (one CTA per SM), and wide frontiers take
-// bfs_wide_step (one lane per queue entry, 32 entries per step).
+// Storage modes (template parameter, chosen by the frame size): see region_grow_cta_kernel.  Frames above ~6 000 cells
+// take bfs_wide_step (one lane per queue entry, 32 entries per step) when the frontier is wide.
 #pragma once
 #include "labeling.cuh"
 
@@ -110,9 +109,9 @@ __device__ __noinline__ int2 bfs_wide_step(int32_t* q, unsigned* cw, unsigned* h
 }
 
 
-// MEMBERS_SMEM = false: the member runs (and later the adjacency bit matrix) live in the global scratch table
-// `pairs` (8 bytes per cell, L2-resident) so that frames of up to ~27 000 cells keep the BFS state in shared memory.
-// MODE 0: everything in shared memory.  MODE 1: member runs / adjacency matrix in the global `pairs` table.
+// MODE 0: everything in shared memory (frames of up to ~6 000 cells, several CTAs per SM).
+// MODE 1: member runs (and later the adjacency bit matrix) in the global scratch table `pairs` (8 bytes per cell,
+// L2-resident), so that frames of up to ~27 000 cells keep the BFS state -- cell words and queue -- in shared memory.
 // MODE 2 (frames above ~27 000 cells): cell words and queue in global memory as well (L2-resident, ~10x the latency
 // of shared memory per probe, but the same algorithmic structure instead of the single-warp fallback).
 template <int MODE>
@@ -129,7 +128,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
   const long long fc = static_cast<long long>(frame) * C;
 
   char* smem = reinterpret_cast<char*>(smem_f4);
-  float* stage_all = reinterpret_cast<float*>(smem + plan.off_stage);        // [3 warps][32][12]
+  float* stage_all = reinterpret_cast<float*>(smem + plan.off_stage);        // [kCtaWarps - 1][32][12]
   unsigned* hkey = reinterpret_cast<unsigned*>(smem + plan.off_hkey);        // [K] count << 15 | (0x7fff - bin), non-empty bins
   int16_t* binslot = reinterpret_cast<int16_t*>(smem + plan.off_binslot);    // [B2] bin -> slot in hkey (or -1)
   int* bin_off = reinterpret_cast<int*>(smem + plan.off_binoff);             // [K] start of the bin's member run
@@ -715,7 +714,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
     o[1] = t_init;                     // setup
     o[2] = t_seed;                     // bin argmax + seed search (all seeds)
     o[3] = t_bfs;                      // BFS (all seeds)
-    o[4] = 0;                          // moment accumulation runs concurrently on warps 1-3
+    o[4] = 0;                          // moment accumulation runs concurrently on the other warps
     o[5] = t_fit_end - t_grow_end;     // plane fits + label painting
     o[6] = t_merge_end - t_fit_end;    // adjacency + merging
     o[7] = t_end - t_merge_end;        // final labels
