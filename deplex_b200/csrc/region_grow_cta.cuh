@@ -54,8 +54,8 @@ __device__ __noinline__ void fit_plane_call(const Moments& m, PlaneFit& f) { fit
 // allocation is not disturbed.  Returns {cells appended, appended cells that belong to the seed's bin}.
 constexpr int kWideThreshold = 12;
 template <bool BIG_GLOBAL>
-__device__ __noinline__ int2 bfs_wide_step(int32_t* q, unsigned* cw, unsigned* hkey, int head, int tail, int lane, int nh,
-                                           int bslot) {
+__device__ __noinline__ int2 bfs_wide_step(int32_t* q, unsigned* cw, unsigned* hkey, int32_t* sink, int head, int tail, int lane,
+                                           int nh, int bslot) {
   const int nbw = min(32, tail - head);
   unsigned pk = 0;
   if (lane < nbw) pk = static_cast<unsigned>(q[head + lane]);
@@ -83,27 +83,28 @@ __device__ __noinline__ int2 bfs_wide_step(int32_t* q, unsigned* cw, unsigned* h
       if ((passm & (1u << sl4)) && ((BIG_GLOBAL ? __ldcg(cw + vv[sl4]) : cw[vv[sl4]]) >> 21) != static_cast<unsigned>(lane * 4 + sl4))
         winm &= ~(1u << sl4);
   }
-  // append position of (lane, slot) = winners of lower lanes + own lower slots
+  // append position of (lane, slot) = winners of lower lanes + own lower slots.  A lane has 0..4 winners: the prefix
+  // over the lanes comes from three ballots on the bits of that count instead of a five-round shuffle scan.
   const unsigned nwin = __popc(winm);
-  int incl = static_cast<int>(nwin);
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(kFull, incl, o);
-    if (lane >= o) incl += t;
-  }
-  int pos = tail + incl - static_cast<int>(nwin);
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned b0 = __ballot_sync(kFull, nwin & 1u), b1 = __ballot_sync(kFull, nwin & 2u), b2 = __ballot_sync(kFull, nwin & 4u);
+  int pos = tail + __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
+  const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
   int same = 0;
+  // branch-free: slots that did not win write to a private sink (see the narrow step)
 #pragma unroll
   for (int sl4 = 0; sl4 < 4; ++sl4) {
-    if (winm & (1u << sl4)) {
-      q[pos++] = vv[sl4] | static_cast<int>(((ww[sl4] >> 16) & 0xfu) << 24);
-      cw[vv[sl4]] = ww[sl4] & ~kAlive;
-      const unsigned slt = ww[sl4] & 0xffffu;
-      if (slt == static_cast<unsigned>(bslot)) ++same;
-      else atomicSub(&hkey[slt], 1u << 15);
-    }
+    const bool won = (winm >> sl4) & 1u;
+    const unsigned slt = ww[sl4] & 0xffffu;
+    const bool other_bin = won && slt != static_cast<unsigned>(bslot);
+    int32_t* qdst = won ? q + pos : sink + lane;
+    unsigned* cdst = won ? cw + vv[sl4] : reinterpret_cast<unsigned*>(sink) + lane;
+    *qdst = vv[sl4] | static_cast<int>(((ww[sl4] >> 16) & 0xfu) << 24);
+    *cdst = ww[sl4] & ~kAlive;
+    pos += won ? 1 : 0;
+    same += (won && !other_bin) ? 1 : 0;
+    atomicSub(other_bin ? hkey + slt : reinterpret_cast<unsigned*>(sink) + lane, 1u << 15);
   }
-  const int total = __shfl_sync(kFull, incl, 31);
   __syncwarp();
   return make_int2(total, same);
 }
@@ -282,33 +283,48 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
           if (alive) { lm = m; seed = c; }
           w = start + __popc(am);
           __syncwarp();
-        } else
-        for (int i0 = start; i0 < end; i0 += 128) {
-          int c[4];
-          float m[4];
-          bool alive[4];
+        } else {
+          // long run: four 32-member chunks per round; the loads of the next round are issued before this round is
+          // processed, so that a round costs its processing and not a memory round trip (member runs of large
+          // frames live in global memory)
+          int cn[4];
+          float mn[4];
+          auto fetch = [&](int i0) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = i0 + 32 * u + lane;
-            const bool in = i < end;
-            c[u] = in ? members[i] : -1;
-            m[u] = in ? msem[i] : 0.f;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) alive[u] = c[u] >= 0 && (cw[c[u]] & kAlive);
-          __syncwarp();  // all reads of this round precede its (possibly overlapping) compaction writes
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (alive[u] && (m[u] < lm || (m[u] == lm && c[u] < seed))) { lm = m[u]; seed = c[u]; }
-            const unsigned am = __ballot_sync(kFull, alive[u]);
-            if (alive[u] && (am != kFull || w != i0 + 32 * u)) {
-              const int pos = w + __popc(am & ((1u << lane) - 1u));
-              members[pos] = c[u];
-              msem[pos] = m[u];
+            for (int u = 0; u < 4; ++u) {
+              const int i = i0 + 32 * u + lane;
+              const bool in = i < end;
+              cn[u] = in ? members[i] : -1;
+              mn[u] = in ? msem[i] : 0.f;
             }
-            w += __popc(am);
+          };
+          fetch(start);
+          for (int i0 = start; i0 < end; i0 += 128) {
+            int c[4];
+            float m[4];
+            bool alive[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              c[u] = cn[u];
+              m[u] = mn[u];
+            }
+            if (i0 + 128 < end) fetch(i0 + 128);  // reads entries the compaction below cannot reach
+#pragma unroll
+            for (int u = 0; u < 4; ++u) alive[u] = c[u] >= 0 && (cw[c[u]] & kAlive);
+            __syncwarp();  // all reads of this round precede its (possibly overlapping) compaction writes
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (alive[u] && (m[u] < lm || (m[u] == lm && c[u] < seed))) { lm = m[u]; seed = c[u]; }
+              const unsigned am = __ballot_sync(kFull, alive[u]);
+              if (alive[u] && (am != kFull || w != i0 + 32 * u)) {
+                const int pos = w + __popc(am & ((1u << lane) - 1u));
+                members[pos] = c[u];
+                msem[pos] = m[u];
+              }
+              w += __popc(am);
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
         if (lane == 0) run_end[bslot] = w;
       }
@@ -347,7 +363,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
       while (head < tail) {
         // (large frames only: the instantiation for small frames keeps the narrow step's tighter code)
         if (!MEMBERS_SMEM && tail - head > kWideThreshold) {
-          const int2 r = bfs_wide_step<BIG_GLOBAL>(q, cw, hkey, head, tail, lane, nh, bslot);
+          const int2 r = bfs_wide_step<BIG_GLOBAL>(q, cw, hkey, dummy, head, tail, lane, nh, bslot);
           head += min(32, tail - head);
           tail += r.x;
           same += r.y;
