@@ -61,6 +61,10 @@ int main(int argc, char** argv) {
     for (int64_t i = 0; i < n; ++i)
       for (int a = 0; a < 3; ++a) cm[a * n + i] = points[3 * i + a];
     CHECK(algorithm.process(cm.data(), n, PointLayout::ColMajor) == labels);
+    // raw depth in (toPointCloud evaluated on the device) gives the same labels
+    std::vector<int32_t> from_depth(static_cast<size_t>(n));
+    algorithm.processDepthBatch(image.data(), 1, k[0], k[4], k[2], k[5], from_depth.data());
+    CHECK(from_depth == labels);
     // move operations keep the extractor usable
     PlaneExtractor moved(std::move(algorithm));
     CHECK(moved.process(points.data(), n, PointLayout::RowMajor) == labels);
