@@ -8,7 +8,8 @@
 //   std::mt19937 (default seed 5489, one generator per process() call, shared across the labels) and
 //   libstdc++'s std::uniform_int_distribution<int> (GCC >= 11: Lemire's multiply-shift with rejection)
 //
-// One CTA per frame.  The reference's loop is sequential twice over -- labels share one random stream, and each
+// One thread-block cluster (8 CTAs of 512 threads, distributed shared memory) per frame; CTA 0 of the cluster leads.
+// The reference's loop is sequential twice over -- labels share one random stream, and each
 // label's iterations stop as soon as a hypothesis reaches the target inlier ratio -- so the CTA walks the labels in
 // order and evaluates the next 32 hypotheses of the current label speculatively and at once:
 //   warp 0     draws the sample ranks of 32 hypotheses from the generator (state in shared memory, twist done by
@@ -16,13 +17,16 @@
 //   96 threads turn (hypothesis, sample) ranks into pixels: the k-th pixel of a label in image order follows
 //              from the label's cells sorted by cell id (cells are painted whole), no per-pixel index lists;
 //   32 threads build the plane models (fp32, the reference's expression order);
-//   all warps  score: a warp stages 32 points in shared memory, then lane g scores hypothesis g on each of them
-//              (the loss is a count, so the order of the points is free);
+//   all warps  of all 8 CTAs score: a warp stages 32 points in shared memory, then lane g scores hypothesis g on each
+//              of them (the loss is a count, so the order of the points is free); per-warp counts go to the leader's
+//              shared memory with distributed-shared-memory atomics;
 //   thread 0   replays the reference's sequential loop over the 32 losses (best-so-far, IsContinued) and reports how
 //              many hypotheses were really consumed; warp 0 rewinds the generator to exactly that point.
 // FindInliers + the relabelling loop (which stops at the last inlier, plane_extractor.cpp:500-507) become two
 // passes: the largest inlier pixel index, then "non-inlier before it -> 0".
 #include "refine.cuh"
+
+#include <cooperative_groups.h>
 
 #include "exact_math.cuh"
 
@@ -32,6 +36,8 @@ namespace {
 constexpr int kRefThreads = 512;
 constexpr int kRefWarps = kRefThreads / 32;
 constexpr int kHyp = 32;  // hypotheses evaluated per round = lanes of a warp
+constexpr int kRefCluster = 8;  // CTAs per frame (portable cluster size limit)
+namespace cg = cooperative_groups;
 constexpr unsigned kFullMask = 0xffffffffu;
 
 struct RefShared {
@@ -149,13 +155,17 @@ __device__ __forceinline__ float plane_error(const float (&m)[4], float x, float
 template <int LAYOUT>
 __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs args) {
   __shared__ RefShared s;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned crank = cluster.block_rank();
+  const bool leader = crank == 0;
+  RefShared* lead = cluster.map_shared_rank(&s, 0);  // the leader CTA's copy (distributed shared memory)
   const Geometry& g = args.geom;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int frame = blockIdx.x;
+  const int frame = blockIdx.x / kRefCluster;
   const int C = g.n_cells, p = g.patch, p2 = p * p, nh = g.nh;
   const long long fc = static_cast<long long>(frame) * C;
   const int nseg = args.tables.n_planes[frame];
-  if (nseg <= 0) return;  // no plane: nothing is labelled (plane_extractor.cpp:230-232)
+  if (nseg <= 0) return;  // no plane: nothing is labelled (plane_extractor.cpp:230-232); the whole cluster leaves
 
   const int32_t* cell_label = args.tables.cell_label + fc;
   int32_t* lab_cells = args.tables.queue + fc;                               // [C] cells sorted by (label, cell id)
@@ -164,53 +174,58 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
   int32_t* labels = args.labels + static_cast<long long>(frame) * g.n_points;
   const double thr = static_cast<double>(args.threshold);      // SetParamThreshold(double) <- float config value
   const double ratio = static_cast<double>(args.inliers_ratio);
+  // this thread's share of a label's points: chunks of 32 points, dealt round-robin over the cluster's warps
+  const int gwarp = static_cast<int>(crank) * kRefWarps + warp;
+  constexpr int kStride = kRefCluster * kRefThreads;
 
-  // ---- labels_indices (plane_extractor.cpp:473-478), per cell instead of per pixel ---------------------
-  for (int i = tid; i < nseg; i += kRefThreads) lab_end[i] = 0;
-  for (int i = tid; i < kMtN; i += kRefThreads) s.mt[i] = args.mt_init[i];
-  int mt_idx = kMtN, mt_idx_bak = kMtN;  // meaningful in warp 0 only
-  __syncthreads();
-  for (int c = tid; c < C; c += kRefThreads) {
-    const int l = cell_label[c];
-    if (l > 0) atomicAdd(&lab_end[l - 1], 1);
-  }
-  __syncthreads();
-  if (warp == 0) {
-    // exclusive scan of the counts -> run starts (kept as running cursors), then a stable fill in ascending cell id
-    int run = 0;
-    for (int b0 = 0; b0 < nseg; b0 += 32) {
-      const int i = b0 + lane;
-      const int cnt = i < nseg ? lab_end[i] : 0;
-      int incl = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(kFullMask, incl, o);
-        if (lane >= o) incl += t;
-      }
-      if (i < nseg) lab_end[i] = run + incl - cnt;
-      run += __shfl_sync(kFullMask, incl, 31);
+  int mt_idx = kMtN, mt_idx_bak = kMtN;  // generator position; meaningful in warp 0 of the leader only
+  if (leader) {
+    // ---- labels_indices (plane_extractor.cpp:473-478), per cell instead of per pixel ---------------------
+    for (int i = tid; i < nseg; i += kRefThreads) lab_end[i] = 0;
+    for (int i = tid; i < kMtN; i += kRefThreads) s.mt[i] = args.mt_init[i];
+    __syncthreads();
+    for (int c = tid; c < C; c += kRefThreads) {
+      const int l = cell_label[c];
+      if (l > 0) atomicAdd(&lab_end[l - 1], 1);
     }
-    __syncwarp();
-    for (int c0 = 0; c0 < C; c0 += 32) {
-      const int c = c0 + lane;
-      const int l = c < C ? cell_label[c] : 0;
-      const unsigned act = __ballot_sync(kFullMask, l > 0);
-      if (l > 0) {
-        const unsigned grp = __match_any_sync(act, l);
-        const int leader = __ffs(grp) - 1;
-        int base = 0;
-        if (lane == leader) {
-          base = lab_end[l - 1];
-          lab_end[l - 1] = base + __popc(grp);
+    __syncthreads();
+    if (warp == 0) {
+      // exclusive scan of the counts -> run starts (kept as running cursors), then a stable fill in ascending cell id
+      int run = 0;
+      for (int b0 = 0; b0 < nseg; b0 += 32) {
+        const int i = b0 + lane;
+        const int cnt = i < nseg ? lab_end[i] : 0;
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(kFullMask, incl, o);
+          if (lane >= o) incl += t;
         }
-        base = __shfl_sync(grp, base, leader);
-        lab_cells[base + __popc(grp & ((1u << lane) - 1u))] = c;
+        if (i < nseg) lab_end[i] = run + incl - cnt;
+        run += __shfl_sync(kFullMask, incl, 31);
       }
       __syncwarp();
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        const int c = c0 + lane;
+        const int l = c < C ? cell_label[c] : 0;
+        const unsigned act = __ballot_sync(kFullMask, l > 0);
+        if (l > 0) {
+          const unsigned grp = __match_any_sync(act, l);
+          const int ldr = __ffs(grp) - 1;
+          int base = 0;
+          if (lane == ldr) {
+            base = lab_end[l - 1];
+            lab_end[l - 1] = base + __popc(grp);
+          }
+          base = __shfl_sync(grp, base, ldr);
+          lab_cells[base + __popc(grp & ((1u << lane) - 1u))] = c;
+        }
+        __syncwarp();
+      }
     }
+    __threadfence();
   }
-  __threadfence_block();
-  __syncthreads();
+  cluster.sync();  // the label runs (global memory) are visible to the whole cluster
 
   // ---- one label after the other (plane_extractor.cpp:486-508) ----------------------------------------------
   for (int L = 0; L < nseg; ++L) {
@@ -218,74 +233,78 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
     LabelCells lc;
     lc.cells = lab_cells + start;
     lc.count = lab_end[L] - start;
-    if (lc.count == 0) continue;  // labels_indices[label].size() == 0
+    if (lc.count == 0) continue;  // labels_indices[label].size() == 0 (the same decision in every CTA)
     const int n = lc.count * p2;
 
-    if (tid == 0) {
+    if (leader && tid == 0) {
       s.best[0] = s.best[1] = s.best[2] = s.best[3] = 0.f;  // Eigen::Vector4f::Zero()
       s.bestloss = HUGE_VAL;
       s.iteration = 0;
+      s.max_inlier_pix = -1;
       // IsContinued(0, N - HUGE_VAL, N): int(-inf) is INT_MIN on x86-64
       s.go_on = (0 < args.max_iterations) && (static_cast<double>(INT_MIN) < ratio * n);
     }
-    __syncthreads();
+    cluster.sync();
+    int go_on = lead->go_on;
 
     // ---- FindBest (RANSAC.hpp:25-51), 32 hypotheses per round -------------------------------------------------
-    while (s.go_on) {
-      if (warp == 0) {
-        // remember the generator, then draw the samples of 32 consecutive iterations (RANSAC.hpp:81-87)
-        for (int i = lane; i < kMtN; i += 32) s.mt_bak[i] = s.mt[i];
-        mt_idx_bak = mt_idx;
-        __syncwarp();
-        int draws = 0;
-        for (int h = 0; h < kHyp; ++h) {
-          int a = -1, b = -1, c = -1, cnt = 0;  // the std::set<int>, kept sorted
-          while (cnt < 3) {
-            const int v = uniform_below_warp(s, lane, mt_idx, static_cast<uint32_t>(n), draws);
-            if (v == a || v == b || v == c) continue;
-            if (cnt == 0) a = v;
-            else if (cnt == 1) { if (v < a) { b = a; a = v; } else b = v; }
-            else {
-              if (v < a) { c = b; b = a; a = v; }
-              else if (v < b) { c = b; b = v; }
-              else c = v;
+    while (go_on) {
+      if (leader) {
+        if (warp == 0) {
+          // remember the generator, then draw the samples of 32 consecutive iterations (RANSAC.hpp:81-87)
+          for (int i = lane; i < kMtN; i += 32) s.mt_bak[i] = s.mt[i];
+          mt_idx_bak = mt_idx;
+          __syncwarp();
+          int draws = 0;
+          for (int h = 0; h < kHyp; ++h) {
+            int a = -1, b = -1, c = -1, cnt = 0;  // the std::set<int>, kept sorted
+            while (cnt < 3) {
+              const int v = uniform_below_warp(s, lane, mt_idx, static_cast<uint32_t>(n), draws);
+              if (v == a || v == b || v == c) continue;
+              if (cnt == 0) a = v;
+              else if (cnt == 1) { if (v < a) { b = a; a = v; } else b = v; }
+              else {
+                if (v < a) { c = b; b = a; a = v; }
+                else if (v < b) { c = b; b = v; }
+                else c = v;
+              }
+              ++cnt;
             }
-            ++cnt;
-          }
-          if (lane == 0) {
-            s.rank[h][0] = a; s.rank[h][1] = b; s.rank[h][2] = c;
-            s.draws_cum[h] = draws;
+            if (lane == 0) {
+              s.rank[h][0] = a; s.rank[h][1] = b; s.rank[h][2] = c;
+              s.draws_cum[h] = draws;
+            }
           }
         }
+        if (tid < kHyp) s.loss[tid] = 0;
+        __syncthreads();
+        if (tid < kHyp * 3) s.pix[tid / 3][tid % 3] = kth_pixel(lc, s.rank[tid / 3][tid % 3], p, nh, g.width);
+        __syncthreads();
+        if (tid < kHyp) {
+          // PlaneEstimator::ComputeModel (Plane.hpp:13-43), fp32 in the reference's expression order
+          float x0, y0, z0, x1, y1, z1, x2, y2, z2;
+          load_point<LAYOUT>(xyz, g.n_points, s.pix[tid][0], x0, y0, z0);
+          load_point<LAYOUT>(xyz, g.n_points, s.pix[tid][1], x1, y1, z1);
+          load_point<LAYOUT>(xyz, g.n_points, s.pix[tid][2], x2, y2, z2);
+          const f32 X0(x0), X1(x1), X2(x2), Y0(y0), Y1(y1), Y2(y2), Z0(z0), Z1(z1), Z2(z2);
+          const f32 D = X0 * Y1 - X1 * Y0 - X0 * Y2 + X2 * Y0 + X1 * Y2 - X2 * Y1;
+          const f32 a = (Z0 * (Y1 - Y2)) / D - (Z1 * (Y0 - Y2)) / D + (Z2 * (Y0 - Y1)) / D;
+          const f32 b = (Z1 * (X0 - X2)) / D - (Z0 * (X1 - X2)) / D - (Z2 * (X0 - X1)) / D;
+          const f32 d = (Z2 * (X0 * Y1 - X1 * Y0)) / D - (Z1 * (X0 * Y2 - X2 * Y0)) / D + (Z0 * (X1 * Y2 - X2 * Y1)) / D;
+          const f32 c(-1.0f);
+          // `sqrt(float)` in Plane.hpp:36 resolves to ::sqrt(double): double square root, rounded to float on assignment
+          const f32 l(__double2float_rn(__dsqrt_rn(static_cast<double>((a * a + b * b + c * c).v))));
+          s.model[tid][0] = (a / l).v; s.model[tid][1] = (b / l).v; s.model[tid][2] = (c / l).v; s.model[tid][3] = (d / l).v;
+        }
       }
-      if (tid < kHyp) s.loss[tid] = 0;
-      __syncthreads();
-      if (tid < kHyp * 3) s.pix[tid / 3][tid % 3] = kth_pixel(lc, s.rank[tid / 3][tid % 3], p, nh, g.width);
-      __syncthreads();
-      if (tid < kHyp) {
-        // PlaneEstimator::ComputeModel (Plane.hpp:13-43), fp32 in the reference's expression order
-        float x0, y0, z0, x1, y1, z1, x2, y2, z2;
-        load_point<LAYOUT>(xyz, g.n_points, s.pix[tid][0], x0, y0, z0);
-        load_point<LAYOUT>(xyz, g.n_points, s.pix[tid][1], x1, y1, z1);
-        load_point<LAYOUT>(xyz, g.n_points, s.pix[tid][2], x2, y2, z2);
-        const f32 X0(x0), X1(x1), X2(x2), Y0(y0), Y1(y1), Y2(y2), Z0(z0), Z1(z1), Z2(z2);
-        const f32 D = X0 * Y1 - X1 * Y0 - X0 * Y2 + X2 * Y0 + X1 * Y2 - X2 * Y1;
-        const f32 a = (Z0 * (Y1 - Y2)) / D - (Z1 * (Y0 - Y2)) / D + (Z2 * (Y0 - Y1)) / D;
-        const f32 b = (Z1 * (X0 - X2)) / D - (Z0 * (X1 - X2)) / D - (Z2 * (X0 - X1)) / D;
-        const f32 d = (Z2 * (X0 * Y1 - X1 * Y0)) / D - (Z1 * (X0 * Y2 - X2 * Y0)) / D + (Z0 * (X1 * Y2 - X2 * Y1)) / D;
-        const f32 c(-1.0f);
-        // `sqrt(float)` in Plane.hpp:36 resolves to ::sqrt(double): double square root, rounded to float on assignment
-        const f32 l(__double2float_rn(__dsqrt_rn(static_cast<double>((a * a + b * b + c * c).v))));
-        s.model[tid][0] = (a / l).v; s.model[tid][1] = (b / l).v; s.model[tid][2] = (c / l).v; s.model[tid][3] = (d / l).v;
-      }
-      __syncthreads();
+      cluster.sync();  // (1) the 32 models and the zeroed losses are in the leader's shared memory
       {
         // EvaluateModel (RANSAC.hpp:89-98): lane g scores hypothesis g; loss += (fabs(error) >= threshold)
         float m[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) m[k] = s.model[lane][k];
+        for (int k = 0; k < 4; ++k) m[k] = lead->model[lane][k];
         unsigned loss = 0;
-        for (int e0 = warp * 32; e0 < n; e0 += kRefThreads) {
+        for (int e0 = gwarp * 32; e0 < n; e0 += kStride) {
           const int e = e0 + lane;
           float x = 0.f, y = 0.f, z = 0.f;
           if (e < n) {
@@ -305,55 +324,56 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
           }
           __syncwarp();
         }
-        atomicAdd(&s.loss[lane], loss);
+        if (loss) atomicAdd(&lead->loss[lane], loss);
       }
-      __syncthreads();
-      if (tid == 0) {
-        // the reference's sequential loop over these hypotheses (RANSAC.hpp:33-46)
-        int consumed = 0;
-        bool go = true;
-        for (int h = 0; h < kHyp; ++h) {
-          const int inl = ::isinf(s.bestloss) ? INT_MIN : static_cast<int>(n - s.bestloss);
-          go = (s.iteration < args.max_iterations) && (static_cast<double>(inl) < ratio * n);
-          if (!go) break;
-          ++s.iteration;
-          ++consumed;
-          const double loss = static_cast<double>(s.loss[h]);
-          if (loss < s.bestloss) {
-            s.best[0] = s.model[h][0]; s.best[1] = s.model[h][1]; s.best[2] = s.model[h][2]; s.best[3] = s.model[h][3];
-            s.bestloss = loss;
+      cluster.sync();  // (2) every CTA's counts are in
+      if (leader) {
+        if (tid == 0) {
+          // the reference's sequential loop over these hypotheses (RANSAC.hpp:33-46)
+          int consumed = 0;
+          bool go = true;
+          for (int h = 0; h < kHyp; ++h) {
+            const int inl = ::isinf(s.bestloss) ? INT_MIN : static_cast<int>(n - s.bestloss);
+            go = (s.iteration < args.max_iterations) && (static_cast<double>(inl) < ratio * n);
+            if (!go) break;
+            ++s.iteration;
+            ++consumed;
+            const double loss = static_cast<double>(s.loss[h]);
+            if (loss < s.bestloss) {
+              s.best[0] = s.model[h][0]; s.best[1] = s.model[h][1]; s.best[2] = s.model[h][2]; s.best[3] = s.model[h][3];
+              s.bestloss = loss;
+            }
           }
+          if (go) {
+            const int inl = ::isinf(s.bestloss) ? INT_MIN : static_cast<int>(n - s.bestloss);
+            go = (s.iteration < args.max_iterations) && (static_cast<double>(inl) < ratio * n);
+          }
+          s.consumed = consumed;
+          s.go_on = go ? 1 : 0;
         }
-        if (go) {
-          const int inl = ::isinf(s.bestloss) ? INT_MIN : static_cast<int>(n - s.bestloss);
-          go = (s.iteration < args.max_iterations) && (static_cast<double>(inl) < ratio * n);
+        __syncthreads();
+        if (warp == 0 && s.consumed < kHyp) {
+          // rewind the generator to just after the last iteration the reference would have run
+          for (int i = lane; i < kMtN; i += 32) s.mt[i] = s.mt_bak[i];
+          mt_idx = mt_idx_bak;
+          __syncwarp();
+          const int redo = s.consumed > 0 ? s.draws_cum[s.consumed - 1] : 0;
+          for (int k = 0; k < redo; ++k) (void)mt_next_warp(s, lane, mt_idx);
         }
-        s.consumed = consumed;
-        s.go_on = go ? 1 : 0;
       }
-      __syncthreads();
-      if (warp == 0 && s.consumed < kHyp) {
-        // rewind the generator to just after the last iteration the reference would have run
-        for (int i = lane; i < kMtN; i += 32) s.mt[i] = s.mt_bak[i];
-        mt_idx = mt_idx_bak;
-        __syncwarp();
-        const int redo = s.consumed > 0 ? s.draws_cum[s.consumed - 1] : 0;
-        for (int k = 0; k < redo; ++k) (void)mt_next_warp(s, lane, mt_idx);
-      }
-      __syncthreads();
+      cluster.sync();  // (3) the decision is visible
+      go_on = lead->go_on;
     }
 
     // ---- FindInliers + relabelling (RANSAC.hpp:53-62, plane_extractor.cpp:498-507) ---------------------------
-    if (tid == 0) s.max_inlier_pix = -1;
-    __syncthreads();
     float m[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) m[k] = s.best[k];
+    for (int k = 0; k < 4; ++k) m[k] = lead->best[k];
     for (int pass = 0; pass < 2; ++pass) {
-      const int last = s.max_inlier_pix;
-      if (pass == 1 && last < 0) break;  // no inlier at all: the relabelling loop never runs
+      const int last = pass ? lead->max_inlier_pix : -1;
+      if (pass == 1 && last < 0) break;  // no inlier at all: the relabelling loop never runs (same in every CTA)
       int local_max = -1;
-      for (int e = tid; e < n; e += kRefThreads) {
+      for (int e = gwarp * 32 + lane; e < n; e += kStride - 0) {
         const int t = e / p2, in = e - t * p2;
         const int cell = lc.cells[t];
         const int r = cell / nh, q = cell - r * nh;
@@ -370,12 +390,13 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
       }
       if (pass == 0) {
         local_max = __reduce_max_sync(kFullMask, local_max);
-        if (lane == 0 && local_max >= 0) atomicMax(&s.max_inlier_pix, local_max);
+        if (lane == 0 && local_max >= 0) atomicMax(&lead->max_inlier_pix, local_max);
+        cluster.sync();  // the largest inlier pixel of the whole label is known
       }
-      __syncthreads();
     }
-    __syncthreads();
+    cluster.sync();  // nobody still reads this label's state when the leader resets it for the next one
   }
+  cluster.sync();  // no CTA leaves while another may still touch its shared memory
 }
 
 }  // namespace
@@ -387,11 +408,20 @@ void mt19937_default_state(uint32_t out[kMtN]) {
 
 cudaError_t launch_refine(const RefineArgs& args, cudaStream_t stream) {
   if (args.n_frames == 0 || args.geom.n_cells == 0) return cudaSuccess;
-  if (args.layout == kLayoutRowMajor)
-    refine_kernel<kLayoutRowMajor><<<args.n_frames, kRefThreads, 0, stream>>>(args);
-  else
-    refine_kernel<kLayoutColMajor><<<args.n_frames, kRefThreads, 0, stream>>>(args);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(args.n_frames) * kRefCluster, 1, 1);
+  cfg.blockDim = dim3(kRefThreads, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kRefCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (args.layout == kLayoutRowMajor) return cudaLaunchKernelEx(&cfg, refine_kernel<kLayoutRowMajor>, args);
+  return cudaLaunchKernelEx(&cfg, refine_kernel<kLayoutColMajor>, args);
 }
 
 }  // namespace dpx
