@@ -37,6 +37,8 @@ constexpr int kRefThreads = 512;
 constexpr int kRefWarps = kRefThreads / 32;
 constexpr int kHyp = 32;  // hypotheses evaluated per round = lanes of a warp
 constexpr int kRefCluster = 8;  // CTAs per frame (portable cluster size limit)
+constexpr int kTape = 128;      // generator outputs prepared per round (32 hypotheses x 3 draws + slack)
+constexpr int kMaxRows = 1023;  // cell rows the per-label row table can hold
 namespace cg = cooperative_groups;
 constexpr unsigned kFullMask = 0xffffffffu;
 
@@ -50,9 +52,11 @@ struct RefShared {
   long long pix[kHyp][3];     // their pixels
   float best[4];
   double bestloss;            // HUGE_VAL until a hypothesis has been accepted
-  int iteration, consumed, go_on;
+  int iteration, consumed, go_on, fast_round;
   int max_inlier_pix;
   float4 stage[kRefWarps][32];
+  uint32_t tape[kTape];       // tempered generator outputs of this round, in draw order
+  int rowstart[kMaxRows + 1]; // per label: index of the first of its cells in each cell row (cells are sorted)
 };
 
 // ---- std::mt19937, executed by warp 0 (all lanes compute the same values; lane 0 owns the stores) ----------
@@ -84,18 +88,21 @@ __device__ __forceinline__ void mt_twist_warp(uint32_t* mt, int lane) {
   }
 }
 
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= y >> 18;
+  return y;
+}
+
 // `idx` is the generator's position, held in a register by every lane of warp 0 (all lanes agree)
 __device__ __forceinline__ uint32_t mt_next_warp(RefShared& s, int lane, int& idx) {
   if (idx >= kMtN) {
     mt_twist_warp(s.mt, lane);
     idx = 0;
   }
-  uint32_t y = s.mt[idx++];
-  y ^= y >> 11;
-  y ^= (y << 7) & 0x9d2c5680u;
-  y ^= (y << 15) & 0xefc60000u;
-  y ^= y >> 18;
-  return y;
+  return mt_temper(s.mt[idx++]);
 }
 
 // std::uniform_int_distribution<int>(0, n - 1)(gen) for a 32-bit generator, libstdc++ >= 11 (bits/uniform_int_dist.h,
@@ -122,13 +129,21 @@ struct LabelCells {
 
 // The k-th pixel (image order) among the pixels of a label whose cells are `lc` (plane_extractor.cpp:473-478 builds
 // this list explicitly).  A cell row holding m of the label's cells contributes p image rows of m*p pixels each.
-__device__ __forceinline__ long long kth_pixel(const LabelCells& lc, int k, int p, int nh, int width) {
+// rowstart[r] = index of the label's first cell in cell row r (rowstart[nv] = count), or nullptr to search.
+__device__ __forceinline__ long long kth_pixel(const LabelCells& lc, const int* rowstart, int k, int p, int nh, int width) {
   const int p2 = p * p;
   const int t = k / p2;
   const int r = lc.cells[t] / nh;  // cell row containing rank k
-  int s = t, e = t + 1;
-  while (s > 0 && lc.cells[s - 1] / nh == r) --s;
-  while (e < lc.count && lc.cells[e] / nh == r) ++e;
+  int s, e;
+  if (rowstart) {
+    s = rowstart[r];
+    e = rowstart[r + 1];
+  } else {
+    s = t;
+    e = t + 1;
+    while (s > 0 && lc.cells[s - 1] / nh == r) --s;
+    while (e < lc.count && lc.cells[e] / nh == r) ++e;
+  }
   const int m = e - s;
   const int kk = k - s * p2;
   const int i = kk / (p * m), rem = kk - i * (p * m);
@@ -236,6 +251,21 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
     if (lc.count == 0) continue;  // labels_indices[label].size() == 0 (the same decision in every CTA)
     const int n = lc.count * p2;
 
+    const bool rows_ok = g.nv <= kMaxRows;
+    if (leader && rows_ok) {
+      // first cell of the label in every cell row (lower bound over the sorted cell list): ranks -> pixels become
+      // two table reads instead of a walk along the row
+      for (int r = tid; r <= g.nv; r += kRefThreads) {
+        int lo = 0, hi = lc.count;
+        const int key = r * nh;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (lc.cells[mid] < key) lo = mid + 1;
+          else hi = mid;
+        }
+        s.rowstart[r] = lo;
+      }
+    }
     if (leader && tid == 0) {
       s.best[0] = s.best[1] = s.best[2] = s.best[3] = 0.f;  // Eigen::Vector4f::Zero()
       s.bestloss = HUGE_VAL;
@@ -251,34 +281,83 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
     while (go_on) {
       if (leader) {
         if (warp == 0) {
-          // remember the generator, then draw the samples of 32 consecutive iterations (RANSAC.hpp:81-87)
-          for (int i = lane; i < kMtN; i += 32) s.mt_bak[i] = s.mt[i];
-          mt_idx_bak = mt_idx;
-          __syncwarp();
-          int draws = 0;
-          for (int h = 0; h < kHyp; ++h) {
-            int a = -1, b = -1, c = -1, cnt = 0;  // the std::set<int>, kept sorted
-            while (cnt < 3) {
-              const int v = uniform_below_warp(s, lane, mt_idx, static_cast<uint32_t>(n), draws);
-              if (v == a || v == b || v == c) continue;
-              if (cnt == 0) a = v;
-              else if (cnt == 1) { if (v < a) { b = a; a = v; } else b = v; }
-              else {
-                if (v < a) { c = b; b = a; a = v; }
-                else if (v < b) { c = b; b = v; }
-                else c = v;
+          // The samples of 32 consecutive iterations (RANSAC.hpp:81-87).  Almost always every iteration takes exactly
+          // three draws (a rejection in the distribution or a repeated sample has probability ~3/n), so the next 96
+          // generator outputs are tempered in parallel and lane h takes outputs 3h..3h+2; any lane that sees a
+          // rejection or a repeat sends the whole round down the sequential path.
+          const int idx0 = mt_idx;
+          bool twisted = false;
+          if (idx0 + kTape > kMtN) {
+            // the tape runs into the next block of the generator: keep the current one for a possible rewind
+            for (int i = lane; i < kMtN; i += 32) s.mt_bak[i] = s.mt[i];
+            __syncwarp();
+          }
+          {
+            const int avail = max(0, min(kTape, kMtN - idx0));
+            for (int j = lane; j < avail; j += 32) s.tape[j] = mt_temper(s.mt[idx0 + j]);
+            if (avail < kTape) {
+              __syncwarp();
+              mt_twist_warp(s.mt, lane);
+              twisted = true;
+              for (int j = avail + lane; j < kTape; j += 32) s.tape[j] = mt_temper(s.mt[j - avail]);
+            }
+            __syncwarp();
+          }
+          const uint32_t un = static_cast<uint32_t>(n);
+          const uint32_t threshold = (0u - un) % un;
+          int v[3];
+          bool clean = true;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const unsigned long long product = static_cast<unsigned long long>(s.tape[3 * lane + i]) * un;
+            const uint32_t low = static_cast<uint32_t>(product);
+            if (low < un && low < threshold) clean = false;  // the distribution would draw again
+            v[i] = static_cast<int>(product >> 32);
+          }
+          if (v[0] == v[1] || v[0] == v[2] || v[1] == v[2]) clean = false;  // std::set would need another draw
+          if (__all_sync(kFullMask, clean)) {
+            const int a = min(v[0], min(v[1], v[2])), c = max(v[0], max(v[1], v[2]));
+            const int b = v[0] + v[1] + v[2] - a - c;
+            s.rank[lane][0] = a; s.rank[lane][1] = b; s.rank[lane][2] = c;
+            s.draws_cum[lane] = 3 * (lane + 1);
+            if (lane == 0) s.fast_round = 1 | (twisted ? 2 : 0);
+            mt_idx_bak = idx0;  // position before this round; the position after it is settled once `consumed` is known
+          } else {
+            // sequential path from the state at the start of the round
+            if (twisted) {
+              for (int i = lane; i < kMtN; i += 32) s.mt[i] = s.mt_bak[i];
+              __syncwarp();
+            }
+            mt_idx = idx0;
+            for (int i = lane; i < kMtN; i += 32) s.mt_bak[i] = s.mt[i];
+            mt_idx_bak = mt_idx;
+            __syncwarp();
+            int draws = 0;
+            for (int h = 0; h < kHyp; ++h) {
+              int a = -1, b = -1, c = -1, cnt = 0;  // the std::set<int>, kept sorted
+              while (cnt < 3) {
+                const int vv = uniform_below_warp(s, lane, mt_idx, un, draws);
+                if (vv == a || vv == b || vv == c) continue;
+                if (cnt == 0) a = vv;
+                else if (cnt == 1) { if (vv < a) { b = a; a = vv; } else b = vv; }
+                else {
+                  if (vv < a) { c = b; b = a; a = vv; }
+                  else if (vv < b) { c = b; b = vv; }
+                  else c = vv;
+                }
+                ++cnt;
               }
-              ++cnt;
+              if (lane == 0) {
+                s.rank[h][0] = a; s.rank[h][1] = b; s.rank[h][2] = c;
+                s.draws_cum[h] = draws;
+              }
             }
-            if (lane == 0) {
-              s.rank[h][0] = a; s.rank[h][1] = b; s.rank[h][2] = c;
-              s.draws_cum[h] = draws;
-            }
+            if (lane == 0) s.fast_round = 0;
           }
         }
         if (tid < kHyp) s.loss[tid] = 0;
         __syncthreads();
-        if (tid < kHyp * 3) s.pix[tid / 3][tid % 3] = kth_pixel(lc, s.rank[tid / 3][tid % 3], p, nh, g.width);
+        if (tid < kHyp * 3) s.pix[tid / 3][tid % 3] = kth_pixel(lc, rows_ok ? s.rowstart : nullptr, s.rank[tid / 3][tid % 3], p, nh, g.width);
         __syncthreads();
         if (tid < kHyp) {
           // PlaneEstimator::ComputeModel (Plane.hpp:13-43), fp32 in the reference's expression order
@@ -352,13 +431,28 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
           s.go_on = go ? 1 : 0;
         }
         __syncthreads();
-        if (warp == 0 && s.consumed < kHyp) {
-          // rewind the generator to just after the last iteration the reference would have run
-          for (int i = lane; i < kMtN; i += 32) s.mt[i] = s.mt_bak[i];
-          mt_idx = mt_idx_bak;
-          __syncwarp();
+        if (warp == 0) {
+          // leave the generator just after the last iteration the reference would have run
           const int redo = s.consumed > 0 ? s.draws_cum[s.consumed - 1] : 0;
-          for (int k = 0; k < redo; ++k) (void)mt_next_warp(s, lane, mt_idx);
+          if (s.fast_round & 1) {
+            const bool twisted = (s.fast_round & 2) != 0;
+            if (mt_idx_bak + redo <= kMtN) {
+              // the consumed draws end inside the block the round started in
+              if (twisted) {
+                for (int i = lane; i < kMtN; i += 32) s.mt[i] = s.mt_bak[i];
+                __syncwarp();
+              }
+              mt_idx = mt_idx_bak + redo;
+            } else {
+              // they run into the next block, which the tape has already generated (kTape >= 96 draws)
+              mt_idx = mt_idx_bak + redo - kMtN;
+            }
+          } else if (s.consumed < kHyp) {
+            for (int i = lane; i < kMtN; i += 32) s.mt[i] = s.mt_bak[i];
+            mt_idx = mt_idx_bak;
+            __syncwarp();
+            for (int k = 0; k < redo; ++k) (void)mt_next_warp(s, lane, mt_idx);
+          }
         }
       }
       cluster.sync();  // (3) the decision is visible
