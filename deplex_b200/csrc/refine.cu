@@ -46,7 +46,8 @@ struct RefShared {
   uint32_t mt[kMtN];
   uint32_t mt_bak[kMtN];
   float model[kHyp][4];
-  unsigned loss[kHyp];
+  unsigned loss[kHyp];        // leader: the cluster's totals
+  unsigned loss_cta[kHyp];    // this CTA's share of a round
   int draws_cum[kHyp];        // generator draws used up to and including hypothesis g
   int rank[kHyp][3];          // sample ranks, ascending (std::set order)
   long long pix[kHyp][3];     // their pixels
@@ -194,6 +195,8 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
   constexpr int kStride = kRefCluster * kRefThreads;
 
   int mt_idx = kMtN, mt_idx_bak = kMtN;  // generator position; meaningful in warp 0 of the leader only
+  if (tid < kHyp) s.loss_cta[tid] = 0;
+  __syncthreads();
   if (leader) {
     // ---- labels_indices (plane_extractor.cpp:473-478), per cell instead of per pixel ---------------------
     for (int i = tid; i < nseg; i += kRefThreads) lab_end[i] = 0;
@@ -403,32 +406,61 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
           }
           __syncwarp();
         }
-        if (loss) atomicAdd(&lead->loss[lane], loss);
+        // per-warp counts -> this CTA's totals -> one distributed-shared-memory atomic per hypothesis and CTA
+        // (128 warps adding straight into the leader's 32 counters serialise there)
+        if (loss) atomicAdd(&s.loss_cta[lane], loss);
+        __syncthreads();
+        if (warp == 0) {
+          const unsigned v = s.loss_cta[lane];
+          s.loss_cta[lane] = 0;
+          if (v) atomicAdd(&lead->loss[lane], v);
+        }
       }
       cluster.sync();  // (2) every CTA's counts are in
       if (leader) {
-        if (tid == 0) {
-          // the reference's sequential loop over these hypotheses (RANSAC.hpp:33-46)
-          int consumed = 0;
-          bool go = true;
-          for (int h = 0; h < kHyp; ++h) {
-            const int inl = ::isinf(s.bestloss) ? INT_MIN : static_cast<int>(n - s.bestloss);
-            go = (s.iteration < args.max_iterations) && (static_cast<double>(inl) < ratio * n);
-            if (!go) break;
-            ++s.iteration;
-            ++consumed;
-            const double loss = static_cast<double>(s.loss[h]);
-            if (loss < s.bestloss) {
-              s.best[0] = s.model[h][0]; s.best[1] = s.model[h][1]; s.best[2] = s.model[h][2]; s.best[3] = s.model[h][3];
-              s.bestloss = loss;
+        if (warp == 1) {
+          // The reference's sequential loop over these hypotheses (RANSAC.hpp:33-46), evaluated by one warp: lane h owns
+          // hypothesis h.  The best-so-far loss before hypothesis h is a prefix minimum; the loop runs while IsContinued
+          // holds, which is monotone (the best loss only falls, the iteration count only grows), so the number of
+          // iterations really run is the number of hypotheses whose check passes.
+          const double inf = HUGE_VAL;
+          const double best0 = s.bestloss;
+          const int iter0 = s.iteration;
+          const double mine = static_cast<double>(s.loss[lane]);
+          double incl = mine;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= o) incl = ::fmin(incl, t);
+          }
+          double before = __shfl_up_sync(kFullMask, incl, 1);
+          if (lane == 0) before = inf;
+          before = ::fmin(before, best0);
+          const int inl = ::isinf(before) ? INT_MIN : static_cast<int>(n - before);
+          const bool go_h = (iter0 + lane < args.max_iterations) && (static_cast<double>(inl) < ratio * n);
+          const int consumed = __popc(__ballot_sync(kFullMask, go_h));
+          // best loss over the iterations really run, and the first of them that reaches it (strict '<' updates)
+          double best = lane < consumed ? mine : inf;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) best = ::fmin(best, __shfl_xor_sync(kFullMask, best, o));
+          const unsigned hit = __ballot_sync(kFullMask, lane < consumed && mine == best);
+          if (lane == 0) {
+            double bl = best0;
+            if (hit && best < best0) {
+              const int winner = __ffs(hit) - 1;
+              s.best[0] = s.model[winner][0]; s.best[1] = s.model[winner][1]; s.best[2] = s.model[winner][2]; s.best[3] = s.model[winner][3];
+              bl = best;
             }
+            s.bestloss = bl;
+            s.iteration = iter0 + consumed;
+            bool go = consumed == kHyp;
+            if (go) {
+              const int inl2 = ::isinf(bl) ? INT_MIN : static_cast<int>(n - bl);
+              go = (s.iteration < args.max_iterations) && (static_cast<double>(inl2) < ratio * n);
+            }
+            s.consumed = consumed;
+            s.go_on = go ? 1 : 0;
           }
-          if (go) {
-            const int inl = ::isinf(s.bestloss) ? INT_MIN : static_cast<int>(n - s.bestloss);
-            go = (s.iteration < args.max_iterations) && (static_cast<double>(inl) < ratio * n);
-          }
-          s.consumed = consumed;
-          s.go_on = go ? 1 : 0;
         }
         __syncthreads();
         if (warp == 0) {
