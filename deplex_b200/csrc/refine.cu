@@ -12,16 +12,18 @@
 // The reference's loop is sequential twice over -- labels share one random stream, and each
 // label's iterations stop as soon as a hypothesis reaches the target inlier ratio -- so the CTA walks the labels in
 // order and evaluates the next 32 hypotheses of the current label speculatively and at once:
-//   warp 0     draws the sample ranks of 32 hypotheses from the generator (state in shared memory, twist done by
-//              the warp), remembering how many draws each one took;
+//   warp 0     (leader) draws the sample ranks of 32 hypotheses: the next generator outputs are tempered in parallel
+//              into a tape and lane h takes outputs 3h..3h+2; a rejection or a repeated sample sends the round down the
+//              exact sequential path.  The draws each hypothesis took are remembered;
 //   96 threads turn (hypothesis, sample) ranks into pixels: the k-th pixel of a label in image order follows
 //              from the label's cells sorted by cell id (cells are painted whole), no per-pixel index lists;
 //   32 threads build the plane models (fp32, the reference's expression order);
 //   all warps  of all 8 CTAs score: a warp stages 32 points in shared memory, then lane g scores hypothesis g on each
 //              of them (the loss is a count, so the order of the points is free); per-warp counts go to the leader's
 //              shared memory with distributed-shared-memory atomics;
-//   thread 0   replays the reference's sequential loop over the 32 losses (best-so-far, IsContinued) and reports how
-//              many hypotheses were really consumed; warp 0 rewinds the generator to exactly that point.
+//   one warp   replays the reference's sequential loop over the 32 losses as a prefix minimum (best-so-far,
+//              IsContinued) and reports how many hypotheses were really consumed; warp 0 leaves the generator at
+//              exactly that point.
 // FindInliers + the relabelling loop (which stops at the last inlier, plane_extractor.cpp:500-507) become two
 // passes: the largest inlier pixel index, then "non-inlier before it -> 0".
 #include "refine.cuh"
