@@ -160,8 +160,9 @@ DPX_API dpx_status dpx_get_planes(dpx_extractor* ex, int32_t frame, dpx_plane* o
 DPX_API dpx_status dpx_set_profiling(dpx_extractor* ex, int32_t enabled);
 DPX_API dpx_status dpx_get_stage_ms(dpx_extractor* ex, float ms[DPX_N_STAGES]);
 /* SM-cycle counters of the region-growing stage for one frame of the last profiled batch:
- * [0] whole frame, [1] histogram + grouping, [2] seed selection, [3] BFS, [4] moment accumulation, [5] plane fits,
- * [6] adjacency + merging, [7] final labels, [8] #seeds, [9] #BFS steps, [10] #regions fitted, [11] #segments. */
+ * [0] whole frame, [1] histogram + grouping, [2] seed selection, [3] BFS, [4] moment accumulation (0 when the helper
+ * warps do it concurrently), [5] plane fits, [6] adjacency + merging, [7] final labels (+ fused pixel painting),
+ * [8] #seeds, [9] #BFS steps, [10] #regions fitted, [11] #segments. */
 #define DPX_REGION_PROFILE_SLOTS 12
 DPX_API dpx_status dpx_get_region_profile(dpx_extractor* ex, int32_t frame, int64_t out[DPX_REGION_PROFILE_SLOTS]);
 /* Number of kernels launched by this handle since creation. */
