@@ -181,6 +181,39 @@ def latency_mode(dev, calls=300):
     return out
 
 
+def fhd_stress(dev, frames=8, steps=5):
+    """BASELINE.json configs[3]: synthetic 1920x1080 clouds, default patch and a finer grid; device-resident, per-stage
+    CUDA-event times (stress test for the cell-stats and labeling bandwidth; region growing dominates on noisy fine grids)."""
+    import torch
+    from deplex_b200 import Config, PlaneExtractor, synth, LAYOUT_ROWMAJOR
+    h, w = 1080, 1920
+    out = {}
+    try:
+        base = synth.make_batch(h, w, 900000, 2, "rowmajor")
+        d_xyz = torch.from_numpy(np.concatenate([base] * (frames // 2), axis=0)).to(dev)
+        d_lab = torch.empty((frames, h * w), dtype=torch.int32, device=dev)
+        for patch in (10, 8):
+            ex = PlaneExtractor(h, w, Config(patch_size=patch), max_batch=frames, device=dev.index)
+            for _ in range(2):
+                ex.process_batch_device(d_xyz, LAYOUT_ROWMAJOR, d_lab)
+            torch.cuda.synchronize()
+            ex.set_profiling(True)
+            acc = {}
+            for _ in range(steps):
+                ex.process_batch_device(d_xyz, LAYOUT_ROWMAJOR, d_lab)
+                torch.cuda.synchronize()
+                for k, v in ex.stage_ms().items():
+                    acc[k] = acc.get(k, 0.0) + v / steps
+            total = sum(acc.values())
+            out[f"patch{patch}"] = {"cells": int(ex.info.n_cells), "frames": frames, "stage_ms": {k: round(v, 4) for k, v in acc.items()},
+                                    "frames_per_s": frames / (total * 1e-3),
+                                    "cell_stats_gbs": frames * h * w * 12 / (acc["cell_stats"] * 1e-3) / 1e9}
+            ex.close()
+    except Exception as e:
+        out["error"] = repr(e)
+    return out
+
+
 def measured_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json, written by
     tools/ncu_traffic.py from the same bench command); None when no capture is recorded."""
@@ -412,6 +445,7 @@ def run_ours(a):
         out["e2e_depth16"] = e2e_depth
     if world == 1 and not a.no_latency:
         out["latency"] = latency_mode(dev)
+        out["fhd_stress"] = fhd_stress(dev)
     if world == 1 and not a.no_cpu_baseline:
         n = a.cpu_sample_frames or a.frames
         reps = max(1, round(14 * (640 * 480 * 256) / (n_px * n)))  # ~10 s of single-thread work
