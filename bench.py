@@ -410,8 +410,8 @@ def run_ours(a):
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
     n_cells = ex.info.n_cells
-    # frames whose pixels the region-growing kernel paints itself (fused stage 3): all but max(2, F/8) per batch
-    fused = (a.frames - min(a.frames, max(2, a.frames // 8))) if ex.info.fused_labeling else 0
+    # frames whose pixels the region-growing kernel paints itself (fused stage 3): all but max(2, F/16) per batch
+    fused = (a.frames - min(a.frames, max(2, a.frames // 16))) if ex.info.fused_labeling else 0
     alg_bytes = {  # algorithmic bytes per launch
         "cell_stats": a.frames * n_px * 12,
         "region_grow": a.frames * n_cells * 82 + fused * n_px * 4,

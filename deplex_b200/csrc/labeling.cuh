@@ -14,7 +14,7 @@ struct LabelArgs {
 };
 
 cudaError_t launch_labeling(const LabelArgs& args, cudaStream_t stream);
-// frames the fused painting of region_grow_cta_kernel leaves to stage 3: the slowest eighth by finishing order
-__host__ __device__ inline int labeling_deferred_frames(int n_frames) { const int d = n_frames / 8 > 2 ? n_frames / 8 : 2; return d < n_frames ? d : n_frames; }
+// frames the fused painting of region_grow_cta_kernel leaves to stage 3: the slowest sixteenth by finishing order
+__host__ __device__ inline int labeling_deferred_frames(int n_frames) { const int d = n_frames / 16 > 2 ? n_frames / 16 : 2; return d < n_frames ? d : n_frames; }
 
 }  // namespace dpx

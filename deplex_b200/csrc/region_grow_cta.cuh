@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
   for (int i = tid; i < nseg; i += kCtaThreads) merge_out[i] = merge[i];
   // toImageLabels (plane_extractor.cpp:455-470) fused: a frame's pixels are painted as soon as its own region growing is
   // done, so the 4 B/pixel write stream of the faster frames overlaps the chains of the slower ones.  The slowest
-  // eighth of the batch (by finishing order) leaves its pixels to the labeling kernel that follows: one CTA writing
+  // sixteenth of the batch (by finishing order) leaves its pixels to the labeling kernel that follows: one CTA writing
   // 1.2 MB alone at the very end would only lengthen the tail.
   if (args.labels != nullptr) {
     if (tid == 0) misc[2] = atomicAdd(&args.tables.paint_state[0], 1);

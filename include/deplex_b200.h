@@ -83,7 +83,7 @@ typedef struct dpx_info {
   int32_t device;
   int32_t sm_count;
   int32_t fused_labeling;  /* 1: the region-growing kernel also paints the pixels of the frames that finish early (all but
-                              max(2, n_frames / 8) per batch); stage DPX_STAGE_LABELING then covers only the rest */
+                              max(2, n_frames / 16) per batch); stage DPX_STAGE_LABELING then covers only the rest */
 } dpx_info;
 
 /* Per-cell record returned by dpx_get_cells (one per cell of one frame of the last batch). */

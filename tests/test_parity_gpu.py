@@ -292,7 +292,7 @@ def test_config_sweep_matches_oracle(oracle_mod, idx):
 @pytest.mark.parametrize("n_frames", [1, 2, 3, 9, 40])
 def test_fused_label_painting_equals_separate_kernel(oracle_mod, n_frames, monkeypatch):
     """Stage 3 is partly fused into the region-growing kernel (frames that finish early paint their own pixels, the
-    slowest max(2, F/8) are left to the labeling kernel).  Whatever the split, every frame's labels must be those of
+    slowest max(2, F/16) are left to the labeling kernel).  Whatever the split, every frame's labels must be those of
     the unfused pipeline (DPX_FUSE_LABELING=0) and of the oracle, also when the same handle is reused."""
     from deplex_b200 import Config, PlaneExtractor, synth, LAYOUT_ROWMAJOR
     h, w = 480, 640
