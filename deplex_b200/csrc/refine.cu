@@ -310,21 +310,50 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
           }
           const uint32_t un = static_cast<uint32_t>(n);
           const uint32_t threshold = (0u - un) % un;
-          int v[3];
-          bool clean = true;
+          // Lane h consumes tape entries from 3h + (extra draws of the hypotheses before it) until it holds three distinct
+          // accepted values.  The extra draws (a rejection in the distribution, a repeated sample: probability ~3/n per
+          // hypothesis) shift everything behind them, so the offsets are iterated to a fixed point: a prefix sum of the
+          // lanes' extra draws per pass, normally one pass, one more per anomaly in a row.
+          int off = 0, extra = 0, a = 0, b = 0, c = 0;
+          bool ok = false;
+          for (int pass = 0; pass < 6; ++pass) {
+            int pos = 3 * lane + off, cnt = 0;
+            a = b = c = -1;
+            while (cnt < 3 && pos < kTape) {
+              const unsigned long long product = static_cast<unsigned long long>(s.tape[pos++]) * un;
+              const uint32_t low = static_cast<uint32_t>(product);
+              if (low < un && low < threshold) continue;  // the distribution draws again
+              const int vv = static_cast<int>(product >> 32);
+              if (vv == a || vv == b || vv == c) continue;  // std::set already holds it
+              if (cnt == 0) a = vv;
+              else if (cnt == 1) { if (vv < a) { b = a; a = vv; } else b = vv; }
+              else {
+                if (vv < a) { c = b; b = a; a = vv; }
+                else if (vv < b) { c = b; b = vv; }
+                else c = vv;
+              }
+              ++cnt;
+            }
+            const bool complete = cnt == 3;
+            extra = pos - (3 * lane + off) - 3;
+            int incl = extra;
 #pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const unsigned long long product = static_cast<unsigned long long>(s.tape[3 * lane + i]) * un;
-            const uint32_t low = static_cast<uint32_t>(product);
-            if (low < un && low < threshold) clean = false;  // the distribution would draw again
-            v[i] = static_cast<int>(product >> 32);
+            for (int o = 1; o < 32; o <<= 1) {
+              const int t = __shfl_up_sync(kFullMask, incl, o);
+              if (lane >= o) incl += t;
+            }
+            const int new_off = incl - extra;
+            const bool stable = __all_sync(kFullMask, complete && new_off == off);
+            off = new_off;
+            if (stable) {
+              ok = true;
+              break;
+            }
+            if (!__all_sync(kFullMask, complete)) break;  // ran off the tape: take the sequential path
           }
-          if (v[0] == v[1] || v[0] == v[2] || v[1] == v[2]) clean = false;  // std::set would need another draw
-          if (__all_sync(kFullMask, clean)) {
-            const int a = min(v[0], min(v[1], v[2])), c = max(v[0], max(v[1], v[2]));
-            const int b = v[0] + v[1] + v[2] - a - c;
+          if (ok) {
             s.rank[lane][0] = a; s.rank[lane][1] = b; s.rank[lane][2] = c;
-            s.draws_cum[lane] = 3 * (lane + 1);
+            s.draws_cum[lane] = 3 * (lane + 1) + off + extra;
             if (lane == 0) s.fast_round = 1 | (twisted ? 2 : 0);
             mt_idx_bak = idx0;  // position before this round; the position after it is settled once `consumed` is known
           } else {
