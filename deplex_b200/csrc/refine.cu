@@ -41,6 +41,7 @@ constexpr int kHyp = 32;  // hypotheses evaluated per round = lanes of a warp
 constexpr int kRefCluster = 8;  // CTAs per frame (portable cluster size limit)
 constexpr int kTape = 128;      // generator outputs prepared per round (32 hypotheses x 3 draws + slack)
 constexpr int kMaxRows = 1023;  // cell rows the per-label row table can hold
+constexpr int kCellCache = 4096;  // cells of one label cached in shared memory (larger labels read the global list)
 namespace cg = cooperative_groups;
 constexpr unsigned kFullMask = 0xffffffffu;
 
@@ -60,6 +61,7 @@ struct RefShared {
   float4 stage[kRefWarps][32];
   uint32_t tape[kTape];       // tempered generator outputs of this round, in draw order
   int rowstart[kMaxRows + 1]; // per label: index of the first of its cells in each cell row (cells are sorted)
+  int32_t cells[kCellCache];  // per label, every CTA: a copy of the label's sorted cell list when it fits
 };
 
 // ---- std::mt19937, executed by warp 0 (all lanes compute the same values; lane 0 owns the stores) ----------
@@ -255,6 +257,13 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
     lc.count = lab_end[L] - start;
     if (lc.count == 0) continue;  // labels_indices[label].size() == 0 (the same decision in every CTA)
     const int n = lc.count * p2;
+    // the label's cell list is read by every rank -> pixel lookup and by every scored point: keep it in shared memory
+    __syncthreads();  // (the previous label's last readers of the cache are done)
+    if (lc.count <= kCellCache) {
+      for (int i = tid; i < lc.count; i += kRefThreads) s.cells[i] = lc.cells[i];
+      lc.cells = s.cells;
+    }
+    __syncthreads();
 
     const bool rows_ok = g.nv <= kMaxRows;
     if (leader && rows_ok) {
