@@ -247,7 +247,9 @@ def run_reference(a):
         return
     threads = os.cpu_count() or 1
     host_batch = make_host_batch(a, 0)
-    per_step = min(a.frames, max(threads, 16 * threads))
+    # a bounded sample per step, so that K steps + W warm-ups stay within ~20 s of wall clock at ~4 000 frames/s
+    budget = max(threads, 80000 // max(1, a.steps + a.warmup))
+    per_step = min(a.frames, max(threads, (budget // threads) * threads))
     per_step = min(per_step, host_batch.shape[0])
     import oracle
     from deplex_b200 import Config
