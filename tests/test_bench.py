@@ -25,3 +25,27 @@ def test_reference_arm_other_ranks_do_nothing(oracle_mod):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
                        capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_gpu_arm_prints_the_contract_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "5", "--warmup", "3", "--frames", "16",
+                        "--unique", "4", "--cpu-sample-frames", "4"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in line, key
+    assert line["n_gpus"] == 1 and line["steps"] == 5 and line["scaling"] == "weak" and line["vs_baseline"] is None
+    assert line["gpu_launches"] >= 3 * 5 and line["value"] > 0
+    rf = line["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert set(rf["stages"]) == {"cell_stats", "region_grow", "labeling"}
+    e2e = line["e2e"]
+    assert e2e["h2d_bytes_per_step"] == 16 * 480 * 640 * 12 and e2e["d2h_bytes_per_step"] == 16 * 480 * 640 * 4
+    assert e2e["matches_device_path"] is True and line["e2e_depth16"]["matches_point_path"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1
+    assert line["latency"]["tum"]["planes"] == 34
