@@ -223,7 +223,9 @@ dpx_status run_stages(dpx_extractor* ex, const float* d_xyz, int n_frames, int l
 
 dpx_status ensure_host_path(dpx_extractor* ex) {
   if (ex->s_run) return DPX_OK;
-  ex->host_chunk = std::max(1, std::min(ex->max_batch, 32));
+  int hc = 16;  // frames per pipelined chunk of the host-pointer path (env DPX_HOST_CHUNK for A/B measurements)
+  if (const char* e = std::getenv("DPX_HOST_CHUNK")) hc = std::max(1, std::atoi(e));
+  ex->host_chunk = std::max(1, std::min(ex->max_batch, hc));
   const size_t np = static_cast<size_t>(ex->geom.n_points);
   for (int i = 0; i < 2; ++i) {
     DPX_CUDA(ex, cudaMalloc(&ex->d_lab[i], std::max<size_t>(16, np * sizeof(int32_t) * ex->host_chunk)));
