@@ -43,6 +43,8 @@ struct CtaPlan {
       off_misc;
   int rec_cap;       // region / plane records held in shared memory (the rest spill to the global segs table)
   int adj_bytes;     // bytes available to the adjacency bit matrix (the member runs' storage)
+  int cache_cap;     // modes 1/2: member-run entries of small bins kept in shared memory (positions below it)
+  int off_cmem, off_cmse;
   size_t bytes;
 };
 
@@ -137,11 +139,17 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
   // [C] cell words (later the segment labels) and [C] BFS queues = region cell lists
   unsigned* cw = BIG_GLOBAL ? args.tables.cell_words + fc : reinterpret_cast<unsigned*>(smem + plan.off_cw);
   int32_t* list = BIG_GLOBAL ? args.tables.queue + fc : reinterpret_cast<int32_t*>(smem + plan.off_list);
-  // [C] cell ids grouped by initial bin, and [C] their MSE in the same order
+  // [C] cell ids grouped by initial bin, and [C] their MSE in the same order.  Run positions below `cap` index the
+  // shared-memory arrays, the others the global ones (modes 1/2: only the small bins' runs fit in shared memory).
   int32_t* members = MEMBERS_SMEM ? reinterpret_cast<int32_t*>(smem + plan.off_members)
                                   : reinterpret_cast<int32_t*>(args.tables.pairs + 2 * fc);
   float* msem = MEMBERS_SMEM ? reinterpret_cast<float*>(smem + plan.off_msem)
                              : reinterpret_cast<float*>(args.tables.pairs + 2 * fc + C);
+  const int cap = MEMBERS_SMEM ? 0x7fffffff : plan.cache_cap;
+  int32_t* cmem = MEMBERS_SMEM ? members : reinterpret_cast<int32_t*>(smem + plan.off_cmem);
+  float* cmse = MEMBERS_SMEM ? msem : reinterpret_cast<float*>(smem + plan.off_cmse);
+  int32_t* gmem = MEMBERS_SMEM ? members : members - cap;  // indexed with positions >= cap
+  float* gmse = MEMBERS_SMEM ? msem : msem - cap;
   float* recs = reinterpret_cast<float*>(smem + plan.off_recs);              // [rec_cap][24]
   int32_t* merge = reinterpret_cast<int32_t*>(smem + plan.off_merge);        // [plane_cap]
   volatile int* misc = reinterpret_cast<volatile int*>(smem + plan.off_misc);
@@ -184,29 +192,40 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
   __syncthreads();
   // compact the non-empty bins and lay out their member runs (warp 0; ascending bin order)
   if (warp == 0) {
-    int K = 0, run = 0;
+    int K = 0, run = 0, crun = 0, total = 0;
+    auto scan = [&](int v) {
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, v, o);
+        if (lane >= o) v += t;
+      }
+      return v;
+    };
     for (int b0 = 0; b0 < B2; b0 += 32) {
       const int b = b0 + lane;
       const int cnt = b < B2 ? hist_tmp[b] : 0;
       const unsigned nz = __ballot_sync(kFull, cnt > 0);
-      int incl = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(kFull, incl, o);
-        if (lane >= o) incl += t;
-      }
+      // small bins go to the shared-memory position space while it has room (always, in mode 0), the rest behind it
+      const bool small = MEMBERS_SMEM || (cnt > 0 && cnt <= 32);
+      const int incl_s = scan(small ? cnt : 0);
+      const bool cached = MEMBERS_SMEM || (small && crun + incl_s <= cap);
+      const int incl_c = MEMBERS_SMEM ? incl_s : scan(cached ? cnt : 0);
+      const int incl_g = MEMBERS_SMEM ? 0 : scan(cached ? 0 : cnt);
       if (cnt > 0) {
         const int slot = K + __popc(nz & ((1u << lane) - 1u));
         binslot[b] = static_cast<int16_t>(slot);
         hkey[slot] = (static_cast<unsigned>(cnt) << 15) | (0x7fffu - static_cast<unsigned>(slot));
-        bin_off[slot] = run + incl - cnt;
-        run_end[slot] = run + incl - cnt;
+        const int pos = cached ? crun + incl_c - cnt : cap + run + incl_g - cnt;
+        bin_off[slot] = pos;
+        run_end[slot] = pos;
       }
       K += __popc(nz);
-      run += __shfl_sync(kFull, incl, 31);
+      crun += __shfl_sync(kFull, incl_c, 31);
+      run += __shfl_sync(kFull, incl_g, 31);
+      total += __shfl_sync(kFull, scan(cnt), 31);
     }
     if (lane == 0) {
-      misc[3] = run;
+      misc[3] = total;
       misc[4] = K;
     }
   }
@@ -217,8 +236,14 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
       const unsigned slot = static_cast<unsigned>(binslot[w & 0xffffu]);
       cw[c] = (w & 0xffff0000u) | slot;  // from here on the word carries the histogram slot instead of the bin id
       const int pos = atomicAdd(&run_end[slot], 1);
-      members[pos] = c;
-      msem[pos] = __ldg(mse_g + c);
+      const float mse = __ldg(mse_g + c);
+      if (pos < cap) {
+        cmem[pos] = c;
+        cmse[pos] = mse;
+      } else {
+        gmem[pos] = c;
+        gmse[pos] = mse;
+      }
     }
   }
   __syncthreads();  // (hist_tmp aliases the list: nobody touches the list before this barrier)
@@ -264,20 +289,22 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
       {
         const int start = bin_off[bslot], end = run_end[bslot];
         int w = start;
+        int32_t* mp = start < cap ? cmem : gmem;  // a run lies entirely in one of the two position spaces
+        float* sp = start < cap ? cmse : gmse;
         // four 32-member chunks per round: their loads are independent, so a round costs one memory round trip
         if (end - start <= 32) {
           // short run (the usual case for the left-over bins that produce one-cell regions): one chunk, straight-line
           const int i = start + lane;
           const bool in = i < end;
-          const int c = in ? members[i] : 0;
-          const float m = in ? msem[i] : 0.f;
+          const int c = in ? mp[i] : 0;
+          const float m = in ? sp[i] : 0.f;
           const unsigned wv = in ? cw[c] : 0u;
           const bool alive = (wv & kAlive) != 0;
           const unsigned am = __ballot_sync(kFull, alive);
           // stable compaction; lanes without a live member write to their private sink
           const int pos = start + __popc(am & ((1u << lane) - 1u));
-          int32_t* mdst = alive ? members + pos : dummy + lane;
-          float* sdst = alive ? msem + pos : reinterpret_cast<float*>(dummy) + lane;
+          int32_t* mdst = alive ? mp + pos : dummy + lane;
+          float* sdst = alive ? sp + pos : reinterpret_cast<float*>(dummy) + lane;
           *mdst = c;
           *sdst = m;
           if (alive) { lm = m; seed = c; }
@@ -294,8 +321,8 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
             for (int u = 0; u < 4; ++u) {
               const int i = i0 + 32 * u + lane;
               const bool in = i < end;
-              cn[u] = in ? members[i] : -1;
-              mn[u] = in ? msem[i] : 0.f;
+              cn[u] = in ? mp[i] : -1;
+              mn[u] = in ? sp[i] : 0.f;
             }
           };
           fetch(start);
@@ -318,8 +345,8 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
               const unsigned am = __ballot_sync(kFull, alive[u]);
               if (alive[u] && (am != kFull || w != i0 + 32 * u)) {
                 const int pos = w + __popc(am & ((1u << lane) - 1u));
-                members[pos] = c[u];
-                msem[pos] = m[u];
+                mp[pos] = c[u];
+                sp[pos] = m[u];
               }
               w += __popc(am);
             }
@@ -764,10 +791,21 @@ inline CtaPlan region_grow_cta_plan(const Geometry& g, const Thresholds& th, int
   } else {
     p.adj_bytes = static_cast<int>(C * 8);  // the `pairs` scratch of this frame
   }
+  p.cache_cap = 0;
   p.rec_cap = g.plane_cap < 128 ? g.plane_cap : 128;
   p.off_recs = static_cast<int>(off);    off = align16(off + static_cast<size_t>(p.rec_cap) * kRecFloats * 4);
   p.off_merge = static_cast<int>(off);   off = align16(off + static_cast<size_t>(g.plane_cap) * 4);
   p.off_misc = static_cast<int>(off);    off = align16(off + (32 + 32) * 4);
+  if (mode != 0) {
+    // whatever shared memory is left (up to 8 bytes per cell) caches the member runs of the small bins: the one-cell
+    // regions that dominate noisy frames are seeded from those, and their searches then stay out of global memory
+    const size_t limit = 220u * 1024;
+    const size_t room = off + 64 < limit ? (limit - off - 64) / 8 : 0;
+    const size_t cap = room < C ? (room / 32) * 32 : C;
+    p.cache_cap = static_cast<int>(cap);
+    p.off_cmem = static_cast<int>(off);  off = align16(off + cap * 4);
+    p.off_cmse = static_cast<int>(off);  off = align16(off + cap * 4);
+  }
   // small frames keep several CTAs per SM; large ones may take (almost) a whole SM's shared memory
   p.bytes = off <= (mode == 0 ? 100u : 220u) * 1024 ? off : 0;
   // mode 2 keeps the queue in global memory, where the raw histogram of the setup needs B2 words (C >= B2 or not)
