@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
       K += __popc(nz);
       crun += __shfl_sync(kFull, incl_c, 31);
       run += __shfl_sync(kFull, incl_g, 31);
-      total += __shfl_sync(kFull, scan(cnt), 31);
+      total += __shfl_sync(kFull, MEMBERS_SMEM ? incl_s : scan(cnt), 31);
     }
     if (lane == 0) {
       misc[3] = total;
