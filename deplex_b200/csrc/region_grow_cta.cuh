@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
 
   char* smem = reinterpret_cast<char*>(smem_f4);
   float* stage_all = reinterpret_cast<float*>(smem + plan.off_stage);        // [kCtaWarps - 1][32][12]
-  unsigned* hkey = reinterpret_cast<unsigned*>(smem + plan.off_hkey);        // [K] count << 15 | (0x7fff - bin), non-empty bins
+  unsigned* hkey = reinterpret_cast<unsigned*>(smem + plan.off_hkey);        // [K] count << 15 | (0x7fff - slot), non-empty bins
   int16_t* binslot = reinterpret_cast<int16_t*>(smem + plan.off_binslot);    // [B2] bin -> slot in hkey (or -1)
   int* bin_off = reinterpret_cast<int*>(smem + plan.off_binoff);             // [K] start of the bin's member run
   int* run_end = reinterpret_cast<int*>(smem + plan.off_runend);             // [K] end of its still-unassigned members
