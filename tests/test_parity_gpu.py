@@ -312,3 +312,32 @@ def test_fused_label_painting_equals_separate_kernel(oracle_mod, n_frames, monke
     ocfg = oracle_mod.OracleConfig()
     for f in range(min(n_frames, 3)):
         assert np.array_equal(want[f], oracle_mod.process(h, w, ocfg, batch[f]))
+
+
+def test_generic_region_kernel_fallback(tmp_path):
+    """The single-warp region_grow_kernel is only reached when the histogram does not fit the CTA kernel's shared memory;
+    force it (DPX_REGION_KERNEL=warp is read once per process, hence the subprocess) and check it against the oracle."""
+    import subprocess
+    import sys
+    code = r'''
+import os, sys
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+import numpy as np, oracle
+from conftest import frame_cloud, to_oracle_cfg
+from deplex_b200 import Config, PlaneExtractor, synth
+for name in ("tum", "icl"):
+    xyz, ini = frame_cloud(name)
+    cfg = Config(ini)
+    ex = PlaneExtractor(480, 640, cfg)
+    assert ex.info.fused_labeling == 0
+    assert np.array_equal(ex.process(xyz), oracle.process(480, 640, to_oracle_cfg(oracle, cfg), xyz)), name
+cfg = Config(patch_size=8)
+ex = PlaneExtractor(720, 1280, cfg)
+xyz = synth.make_cloud(720, 1280, 11)
+assert np.array_equal(ex.process(xyz), oracle.process(720, 1280, to_oracle_cfg(oracle, cfg), xyz))
+print("fallback ok")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DPX_REGION_KERNEL="warp")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=root, env=env)
+    assert r.returncode == 0 and "fallback ok" in r.stdout, r.stdout + r.stderr
