@@ -341,3 +341,30 @@ print("fallback ok")
     env = dict(os.environ, DPX_REGION_KERNEL="warp")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=root, env=env)
     assert r.returncode == 0 and "fallback ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_capi_argument_errors_on_device():
+    """Misuse is an error code with a message, never a crash: batch larger than max_batch, null pointers, bad layout,
+    table queries outside the last batch, depth entry without intrinsics."""
+    import ctypes as C
+    import torch
+    from deplex_b200 import Config, PlaneExtractor, _capi, synth, LAYOUT_ROWMAJOR
+    lib = _capi.load()
+    ex = PlaneExtractor(480, 640, Config(), max_batch=2)
+    xyz = torch.from_numpy(synth.make_batch(480, 640, 0, 3, "rowmajor")).cuda()
+    lab = torch.empty((3, 480 * 640), dtype=torch.int32, device="cuda")
+    st = lib.dpx_process_batch_device(ex._h, xyz.data_ptr(), 3, LAYOUT_ROWMAJOR, lab.data_ptr(), None)
+    assert st == _capi.DPX_ERR_ARGUMENT and b"max_batch" in lib.dpx_last_error(ex._h)
+    assert lib.dpx_process_batch_device(ex._h, None, 1, LAYOUT_ROWMAJOR, lab.data_ptr(), None) == _capi.DPX_ERR_ARGUMENT
+    assert lib.dpx_process_batch_device(ex._h, xyz.data_ptr(), 1, 7, lab.data_ptr(), None) == _capi.DPX_ERR_ARGUMENT
+    assert lib.dpx_process_batch_device(ex._h, xyz.data_ptr(), 0, LAYOUT_ROWMAJOR, lab.data_ptr(), None) == _capi.DPX_OK
+    assert lib.dpx_process_depth_batch_device(ex._h, xyz.data_ptr(), 1, None, lab.data_ptr(), None) == _capi.DPX_ERR_ARGUMENT
+    assert lib.dpx_process_batch_device(ex._h, xyz.data_ptr(), 2, LAYOUT_ROWMAJOR, lab.data_ptr(), None) == _capi.DPX_OK
+    torch.cuda.synchronize()
+    cells = (_capi.dpx_cell * ex.info.n_cells)()
+    assert lib.dpx_get_cells(ex._h, 2, cells, ex.info.n_cells) == _capi.DPX_ERR_ARGUMENT     # frame outside the last batch
+    assert lib.dpx_get_cells(ex._h, 1, cells, ex.info.n_cells - 1) == _capi.DPX_ERR_ARGUMENT  # capacity too small
+    assert lib.dpx_get_cells(ex._h, 1, cells, ex.info.n_cells) == _capi.DPX_OK
+    ms = (C.c_float * _capi.N_STAGES)()
+    assert lib.dpx_get_stage_ms(ex._h, C.byref(ms)) == _capi.DPX_ERR_ARGUMENT                 # profiling was never enabled
+    assert lib.dpx_process_host(None, None, 0, LAYOUT_ROWMAJOR, None) == _capi.DPX_ERR_ARGUMENT
