@@ -101,3 +101,31 @@ def test_no_cpu_fallback_through_the_bindings(deplex_mod):
 def test_cpp_binaries_built(lib_built):
     for exe in ("process_cloud", "process_sequence", "test_api"):
         assert os.access(os.path.join(ROOT, "deplex_b200", "cpp", "build", exe), os.X_OK)
+
+
+def test_wheel_is_self_contained(deplex_mod, tmp_path):
+    """python/setup.py gathers the module and both native libraries into one wheel (reference: python/setup.py);
+    installed on its own, `import deplex` resolves all three from the wheel, not from this tree."""
+    import glob
+    import subprocess
+    import zipfile
+    dist, site = tmp_path / "dist", tmp_path / "site"
+    r = subprocess.run([sys.executable, "setup.py", "-q", "bdist_wheel", "--dist-dir", str(dist), "--bdist-dir",
+                        str(tmp_path / "bdist"), "build", "--build-base", str(tmp_path / "build"), "egg_info",
+                        "--egg-base", str(tmp_path)], cwd=PYPKG, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    (wheel,) = glob.glob(str(dist / "deplex-*.whl"))
+    names = zipfile.ZipFile(wheel).namelist()
+    assert "deplex/libdeplex.so" in names and "deplex/libdeplex_b200.so" in names
+    assert any(n.startswith("deplex/pybind.") and n.endswith(".so") for n in names)
+    zipfile.ZipFile(wheel).extractall(site)
+    probe = ("import deplex; c = deplex.Config(); assert c.patch_size == 10\n"
+             "print([l.split()[-1] for l in open('/proc/self/maps') if 'deplex' in l])")
+    env = {k: v for k, v in os.environ.items() if k not in ("PYTHONPATH", "LD_LIBRARY_PATH")}
+    env["PYTHONPATH"] = str(site)
+    r = subprocess.run([sys.executable, "-c", probe], cwd=str(tmp_path), env=env, capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    loaded = set(eval(r.stdout.strip().splitlines()[-1]))
+    assert loaded and all(p.startswith(str(site)) for p in loaded), loaded
+    assert len({os.path.basename(p) for p in loaded}) == 3
