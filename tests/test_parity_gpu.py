@@ -184,6 +184,31 @@ def test_batch_equals_single_and_is_idempotent(oracle_mod):
     assert ex.kernel_launches() > 0
 
 
+@pytest.mark.parametrize("lanes", [1, 2, 3])
+def test_pipelined_lanes_match_oracle(oracle_mod, lanes):
+    """PipelinedExtractor: batches in flight on several extractors / streams at once (the next batch's cell-stats kernel
+    overlapping the previous batch's region growing) give the labels of the oracle, batch by batch, for cloud and
+    raw-depth input; join() orders the current stream behind all of them."""
+    import torch
+    from deplex_b200 import Config, PipelinedExtractor, synth, LAYOUT_ROWMAJOR
+    h, w, F, B = 480, 640, 24, 7
+    k = synth.intrinsics_for(h, w)
+    pipe = PipelinedExtractor(h, w, Config(), max_batch=F, lanes=lanes)
+    ocfg = oracle_mod.OracleConfig()
+    depth = np.stack([synth.make_depth(h, w, 7000 + i, k) for i in range(F * B)]).reshape(B, F, h, w)
+    clouds = np.stack([synth.depth_to_cloud(d, k, "rowmajor") for d in depth.reshape(-1, h, w)]).reshape(B, F, h * w, 3)
+    d_clouds = torch.from_numpy(clouds).cuda()
+    d_depth = torch.from_numpy(depth.view(np.int16)).cuda()
+    outs = [pipe.submit(d_clouds[b], LAYOUT_ROWMAJOR) if b % 2 == 0 else pipe.submit_depth(d_depth[b], k)
+            for b in range(B)]
+    pipe.join()
+    got = torch.stack(outs).cpu().numpy()          # on the current stream, i.e. behind the join
+    ref = oracle_mod.process_batch(h, w, ocfg, clouds.reshape(B * F, h * w, 3), 1, os.cpu_count() or 1)
+    assert np.array_equal(got.reshape(B * F, -1), ref)
+    assert pipe.kernel_launches() >= 3 * B
+    pipe.close()
+
+
 def test_unaligned_device_pointer(oracle_mod):
     """A device pointer that is only 4-byte aligned takes the scalar loader and still matches."""
     import torch
