@@ -79,9 +79,11 @@ def test_no_cpu_fallback(lib_built):
     import torch
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")
-    from deplex_b200 import CudaError, PlaneExtractor
+    from deplex_b200 import CudaError, PipelinedExtractor, PlaneExtractor
     with pytest.raises(CudaError):
         PlaneExtractor(480, 640)
+    with pytest.raises(CudaError):
+        PipelinedExtractor(480, 640, lanes=2)
 
 
 def test_product_does_not_touch_the_oracle():
