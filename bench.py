@@ -267,14 +267,14 @@ def run_reference(a):
     dt = time.perf_counter() - t0
     value = a.steps * per_step / dt
     sample_desc = f"{per_step} frames/step of the same batch, {threads} threads, frame-parallel"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 def run_ours(a):
@@ -485,13 +485,31 @@ def run_ours(a):
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                "sample": f"{n * reps} frames ({n} frames of this batch x{reps} passes), 1 thread (the reference "
                                          f"is single-threaded by default), {dt:.1f} s; host has {os.cpu_count()} cores"}
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(obj):
+    """The one JSON line of this run, on the process's original stdout."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, line)
+
+
 def main():
+    global _RESULT_FD
     a = parse_args()
+    # libraries print to stdout too (NCCL's version banner under torchrun): keep fd 1 for the result line only
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:
