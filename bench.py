@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--patch", type=int, default=10)
     ap.add_argument("--layout", default="rowmajor", choices=["rowmajor", "colmajor"])
-    ap.add_argument("--lanes", type=int, default=2,
+    ap.add_argument("--lanes", type=int, default=3,
                     help="extractors (each on its own stream) the device-resident leg feeds round-robin; 1 = strictly serial steps")
     ap.add_argument("--cpu-sample-frames", type=int, default=0, help="frames in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -15,7 +15,7 @@
 //               This chain is written branch-free where it can be -- predicated loads, an unrolled key scan, and
 //               per-lane dummy sinks for the stores and atomics of lanes that have nothing to write: a single
 //               warp pays every taken branch and every dependent instruction in full.
-//   warps 1-7   consume finished regions from a shared-memory ring while warp 0 keeps growing: the fp32
+//   warps 1..   consume finished regions from a shared-memory ring while warp 0 keeps growing: the fp32
 //               moment chains over the region's FIFO list (plane_extractor.cpp:318-327).
 //   all warps   setup (histogram, grouping by bin), then after growing: plane fits one region per thread
 //               (:333-337), ordered compaction into segment ids, labels_map_ painting (:339-342), adjacency
@@ -30,7 +30,10 @@
 namespace dpx {
 namespace {
 
-constexpr int kCtaThreads = 256;
+#ifndef DPX_CTA_THREADS
+#define DPX_CTA_THREADS 128  // A/B at build time: 256 (twice the helper warps, two CTAs per SM instead of three)
+#endif
+constexpr int kCtaThreads = DPX_CTA_THREADS;
 constexpr int kCtaWarps = kCtaThreads / 32;
 // cell word: bits 0-15 slot of the cell's initial bin in the compacted histogram, 16-19 edge mask, 20 alive (planar and
 // unassigned), 21-31 claim field (all ones while idle; see the BFS step)

@@ -257,15 +257,16 @@ class PipelinedExtractor:
     """`lanes` PlaneExtractor handles, each on its own CUDA stream, fed round-robin (an addition; the reference has no
     batch API).  Within one batch the HBM-bound cell-stats kernel and the latency-bound region growing run back to
     back, and the region-growing kernel's tail -- a few long frames on a few SMs -- leaves most of the GPU idle.  With
-    two batches in flight the block scheduler starts the next batch's cell-stats CTAs on every SM that region growing
-    has already left, so the tail is filled (measured on the 256-frame VGA batch: 0.364 -> 0.284 ms per batch).
+    several batches in flight the block scheduler starts the next batch's cell-stats CTAs on every SM that region growing
+    has already left, so the tail is filled (measured on the 256-frame VGA batch: 0.366 ms per batch with one lane,
+    0.277 with two, 0.259 with three).
 
     submit*() is asynchronous: the lane's stream first waits for the work already queued on torch's current stream (the
     producer of the input), and nothing after the call on the current stream is ordered behind the batch until join().
     Each lane owns its device tables, so results are independent of the lane count; C callers get the same effect with
-    two dpx_extractor handles and two streams."""
+    several dpx_extractor handles and streams."""
 
-    def __init__(self, image_height, image_width, config=None, *, max_batch=1, device=-1, lanes=2):
+    def __init__(self, image_height, image_width, config=None, *, max_batch=1, device=-1, lanes=3):
         import torch
         assert lanes >= 1
         self.lanes = [PlaneExtractor(image_height, image_width, config, max_batch=max_batch, device=device)

@@ -8,6 +8,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def child(frames, steps, lanes, split):
     sys.path.insert(0, ROOT)
     import numpy as np, torch
+    if os.environ.get("DPX_LIB"):
+        import deplex_b200._capi as _c
+        _c.LIB_PATH = os.environ["DPX_LIB"]
     from deplex_b200 import Config, PlaneExtractor, synth, LAYOUT_ROWMAJOR
     h, w = 480, 640
     dev = torch.device("cuda", 0)
@@ -43,7 +46,7 @@ def child(frames, steps, lanes, split):
     ms = e0.elapsed_time(e1) / steps
     ref = exs[0].process_batch_device(d_xyz[:per], LAYOUT_ROWMAJOR).cpu()
     ok = bool(torch.equal(ref, d_lab[:per].cpu()))
-    print(json.dumps({"warps": os.environ.get("DPX_STREAM_WARPS", "16"), "lanes": lanes, "split": split,
+    print(json.dumps({"lib": os.path.basename(os.environ.get("DPX_LIB", "default")), "warps": os.environ.get("DPX_STREAM_WARPS", "16"), "lanes": lanes, "split": split,
                       "ms_per_step": round(ms, 4), "frames_per_s": round(frames / ms * 1e3), "labels_equal": ok}))
 
 
@@ -53,7 +56,10 @@ if __name__ == "__main__":
         sys.exit(0)
     frames = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 300
-    for warps, combos in (("16", ((1, 1), (2, 1))), ("12", ((1, 1), (2, 1))), ("8", ((1, 1), (2, 1), (2, 2), (2, 4), (3, 1)))):
+    plan = (("16", ((1, 1), (2, 1), (3, 1))),)
+    if os.environ.get("OVERLAP_FULL"):
+        plan += (("12", ((1, 1), (2, 1))), ("8", ((1, 1), (2, 1), (2, 2), (2, 4), (3, 1))))
+    for warps, combos in plan:
         for lanes, split in combos:
             env = dict(os.environ, DPX_STREAM_WARPS=warps)
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", str(frames), str(steps), str(lanes), str(split)],
