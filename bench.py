@@ -280,7 +280,6 @@ def run_reference(a):
 def run_ours(a):
     import torch
     import torch.distributed as dist
-    import deplex_b200
     from deplex_b200 import Config, PipelinedExtractor, LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR
 
     rank = int(os.environ.get("RANK", "0"))

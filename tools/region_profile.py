@@ -1,4 +1,4 @@
-import sys, json, numpy as np, torch
+import sys, numpy as np, torch
 sys.path.insert(0, '.')
 import bench
 from deplex_b200 import Config, PlaneExtractor, LAYOUT_ROWMAJOR

@@ -6,7 +6,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import oracle
-from deplex_b200 import Config, PlaneExtractor, synth, LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR
+from deplex_b200 import Config, PlaneExtractor, synth, LAYOUT_COLMAJOR
 
 THREADS = os.cpu_count() or 1
 
