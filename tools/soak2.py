@@ -9,6 +9,7 @@ import oracle
 from deplex_b200 import Config, PlaneExtractor, synth, LAYOUT_COLMAJOR
 
 THREADS = os.cpu_count() or 1
+SCALE = float(os.environ.get("SOAK_SCALE", "1"))  # fraction of the frame counts below (short re-runs)
 
 
 def compare(tag, got, ref, first):
@@ -80,13 +81,15 @@ for name, fn, args in [
     ("720p p10 depth16 x100", run_depth, (720, 1280, Config(), 1300000, 100, 50)),
     ("1080p p10 colmajor x24", run_points, (1080, 1920, Config(), 1400000, 24, 12)),
 ]:
+    args = args[:4] + (max(args[5], int(args[4] * SCALE)) if SCALE < 1 else args[4], args[5])
     b = fn(*args)
     total += b
     frames += args[4]
     print(f"{name}: {b} mismatching frames  ({time.time() - t0:.0f} s)", flush=True)
 
 rng = np.random.default_rng(20261018)
-for i in range(40):
+N_CONFIGS = max(4, int(40 * SCALE))
+for i in range(N_CONFIGS):
     refine = i % 4 == 3
     cfg = random_config(rng, refine)
     n = 12 if refine else 40
@@ -96,6 +99,6 @@ for i in range(40):
     frames += n
     if b:
         print("  config:", cfg.as_dict(), flush=True)
-print(f"40 random configs: cumulative {total} mismatching frames  ({time.time() - t0:.0f} s)", flush=True)
+print(f"{N_CONFIGS} random configs: cumulative {total} mismatching frames  ({time.time() - t0:.0f} s)", flush=True)
 print(f"TOTAL mismatching frames: {total} of {frames}")
 sys.exit(1 if total else 0)
