@@ -1,3 +1,5 @@
+"""SM-cycle counters of the region-growing phases for the frames of the bench batch (mean, max, slowest frames):
+    python tools/region_profile.py   (from the repo root, on the GPU box)"""
 import sys, numpy as np, torch
 sys.path.insert(0, '.')
 import bench
