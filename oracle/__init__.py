@@ -5,4 +5,5 @@ import this package.  Nothing under deplex_b200/ does.
 """
 from .oracle import (  # noqa: F401
     OracleConfig, OracleError, build, depth_to_cloud, eig3, load_ini, process, process_batch, ref_dsyev_path,
+    set_sum_variant,
 )

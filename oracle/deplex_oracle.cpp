@@ -246,7 +246,24 @@ bool eig3_hybrid(const Sym3& A, double Q[9], double w[3]) {
 // DenseBase::sum() over a contiguous float column of length n whose first 16-byte-aligned element
 // is index `s` -- Eigen/src/Core/Redux.h, redux_impl<..., LinearVectorizedTraversal, NoUnrolling>,
 // SSE2 Packet4f, predux = (a0+a2)+(a1+a3).  Call site: cell_segment_stat.cpp:31.
+// Sensitivity switch, for tools/order_sensitivity.py only: how the three Eigen reductions are evaluated.
+//   0  the restated Eigen 3.4 orders (default; the order parity is judged against)
+//   1  plain left-to-right fp32 sums, fixed-size dot as (p0 + p1) + p2
+//   2  fp64 accumulation rounded once to fp32 (an order-free reference point)
+// It answers one question: would the labels change if Eigen's real orders differed from the restatement?
+static int g_sum_variant = 0;
+
 float eigen_sum_f32(const float* p, long n, long s) {
+  if (g_sum_variant == 1) {
+    float r = p[0];
+    for (long i = 1; i < n; ++i) r = r + p[i];
+    return r;
+  }
+  if (g_sum_variant == 2) {
+    double r = 0.0;
+    for (long i = 0; i < n; ++i) r += static_cast<double>(p[i]);
+    return static_cast<float>(r);
+  }
   const long ps = 4;
   if (s > n) s = n;
   const long aligned_size2 = ((n - s) / (2 * ps)) * (2 * ps);
@@ -278,6 +295,9 @@ float eigen_sum_f32(const float* p, long n, long s) {
 
 // Fixed-size-3 dot product: a0*b0 + (a1*b1 + a2*b2)  (redux_novec_unroller<0,3>).
 inline float dot3(const float* a, const float* b) {
+  if (g_sum_variant == 2)
+    return static_cast<float>(static_cast<double>(a[0]) * b[0] + static_cast<double>(a[1]) * b[1] + static_cast<double>(a[2]) * b[2]);
+  if (g_sum_variant == 1) return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2];
   const float p0 = a[0] * b[0];
   const float p1 = a[1] * b[1];
   const float p2 = a[2] * b[2];
@@ -409,7 +429,13 @@ void build_cell(const float* x, const float* y, const float* z, long N, const dp
       float c = 0.f;
       const float* a = col[i];
       const float* b = col[j];
-      for (long k = 0; k < N; ++k) c = a[k] * b[k] + c;
+      if (g_sum_variant == 2) {
+        double cd = 0.0;
+        for (long k = 0; k < N; ++k) cd += static_cast<double>(a[k]) * static_cast<double>(b[k]);
+        c = static_cast<float>(cd);
+      } else {
+        for (long k = 0; k < N; ++k) c = a[k] * b[k] + c;
+      }
       st.V[3 * i + j] = c;
     }
   const float fn = static_cast<float>(st.n);
@@ -898,6 +924,8 @@ int dpxo_process_batch(int32_t h, int32_t w, const dpxo_config* cfg, const float
     }
   return 0;
 }
+
+void dpxo_set_sum_variant(int v) { g_sum_variant = (v == 1 || v == 2) ? v : 0; }
 
 int dpxo_eig3(const double* A, double* Q, double* w) {
   Sym3 S{A[0], A[1], A[2], A[4], A[5], A[8]};

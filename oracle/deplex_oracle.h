@@ -86,6 +86,10 @@ int dpxo_process_batch(int32_t h, int32_t w, const dpxo_config* cfg, const float
                        int32_t n_frames, int layout, int32_t* labels, int32_t n_threads,
                        char* err, int errlen);
 
+/* Sensitivity switch for tools/order_sensitivity.py: 0 = restated Eigen 3.4 reduction orders (default), 1 = plain
+ * left-to-right fp32, 2 = fp64 accumulation rounded once.  Process-global; parity is always judged against 0. */
+void dpxo_set_sum_variant(int variant);
+
 /* The oracle's own restatement of Kopp's hybrid 3x3 symmetric eigensolver (row-major 3x3 in/out).
  * Returns 1 if the QL branch was taken, else 0. */
 int dpxo_eig3(const double* A, double* Q, double* w);

@@ -83,10 +83,18 @@ def _load():
         lib.dpxo_process_batch.argtypes = [C.c_int32, C.c_int32, C.POINTER(OracleConfig), C.c_void_p, C.c_int32,
                                            C.c_int, C.c_void_p, C.c_int32, C.c_char_p, C.c_int]
         lib.dpxo_eig3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.dpxo_set_sum_variant.argtypes = [C.c_int]
+        lib.dpxo_set_sum_variant.restype = None
         lib.dpxo_depth_to_cloud.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float,
                                             C.c_float, C.c_void_p]
         _lib = lib
     return _lib
+
+
+def set_sum_variant(variant):
+    """0 = the restated Eigen 3.4 reduction orders (default, what parity is judged against); 1 = plain left-to-right
+    fp32; 2 = fp64 accumulation rounded once.  Process-global; only tools/order_sensitivity.py changes it."""
+    _load().dpxo_set_sum_variant(int(variant))
 
 
 def load_ini(path):

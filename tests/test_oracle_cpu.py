@@ -114,6 +114,26 @@ def test_golden_fixture_regression(oracle_mod, name):
         assert (dbg["n_seeds"], dbg["n_ql_fallback"], int(dbg["cell_planar"].sum())) == (53, 571, 18527)
 
 
+def test_summation_order_switch_is_off_by_default_and_matters(oracle_mod):
+    """tools/order_sensitivity.py's switch: other summation orders change per-cell moments (the labels depend on the order
+    the reference's Eigen build uses), and setting it back restores the committed fixture bit for bit."""
+    xyz, ini = frame_cloud("tum")
+    cfg = oracle_mod.load_ini(ini)
+    gold = np.load(os.path.join(GOLDEN, "oracle_tum.npz"))
+    try:
+        for variant in (1, 2):
+            oracle_mod.set_sum_variant(variant)
+            labels, dbg = oracle_mod.process(480, 640, cfg, xyz, debug=True)
+            assert not np.array_equal(dbg["cell_sum"].view(np.uint32), gold["cell_sum"].view(np.uint32))
+            assert int(labels.max()) == 34          # the reference's golden value does not discriminate between orders
+            assert 0 < int((labels != gold["labels"]).sum())
+    finally:
+        oracle_mod.set_sum_variant(0)
+    labels, dbg = oracle_mod.process(480, 640, cfg, xyz, debug=True)
+    assert np.array_equal(labels, gold["labels"])
+    assert np.array_equal(dbg["cell_sum"].view(np.uint32), gold["cell_sum"].view(np.uint32))
+
+
 def test_layouts_agree(oracle_mod):
     xyz, ini = frame_cloud("tum")
     cfg = oracle_mod.load_ini(ini)
