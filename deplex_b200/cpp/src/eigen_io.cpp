@@ -1,7 +1,9 @@
 // eigen_io.cpp -- text I/O helpers (reference: cpp/deplex/src/deplex/utils/eigen_io.cpp:22-60).
 #include "deplex/utils/eigen_io.h"
 
+#include <cstdlib>
 #include <fstream>
+#include <iterator>
 #include <iomanip>
 #include <limits>
 #include <sstream>
@@ -10,13 +12,25 @@
 namespace deplex {
 namespace utils {
 
+// One pass over the whole file with strtof: fields are separated by `delimiter`, records by newlines.  Same contract as
+// the reference reader (eigen_io.cpp:24-40): every field is a float, the total must be a multiple of three.
 std::vector<float> readPointCloudCSV(std::string const& path, char delimiter) {
+  std::ifstream file(path, std::ios::binary);
+  std::string text((std::istreambuf_iterator<char>(file)), std::istreambuf_iterator<char>());
   std::vector<float> points;
-  std::ifstream file(path);
-  std::string row, entry;
-  while (std::getline(file, row)) {
-    std::stringstream ss(row);
-    while (std::getline(ss, entry, delimiter)) points.push_back(std::stof(entry));
+  points.reserve(text.size() / 6);
+  const char* cur = text.c_str();
+  const char* const end = cur + text.size();
+  while (cur < end) {
+    if (*cur == delimiter || *cur == '\n' || *cur == '\r' || *cur == ' ' || *cur == '\t') {
+      ++cur;
+      continue;
+    }
+    char* after = nullptr;
+    const float value = std::strtof(cur, &after);
+    if (after == cur) throw std::invalid_argument("stof");  // what std::stof throws on a non-numeric field
+    points.push_back(value);
+    cur = after;
   }
   if (points.size() % 3 != 0) throw std::runtime_error("Error reading file: Invalid points shape");
   return points;

@@ -129,3 +129,44 @@ def test_wheel_is_self_contained(deplex_mod, tmp_path):
     loaded = set(eval(r.stdout.strip().splitlines()[-1]))
     assert loaded and all(p.startswith(str(site)) for p in loaded), loaded
     assert len({os.path.basename(p) for p in loaded}) == 3
+
+
+def test_cpp_text_io_roundtrip(lib_built, tmp_path):
+    """deplex::utils::{save,read}PointCloudCSV and readIntrinsics (reference: utils/eigen_io.cpp:22-60) through libdeplex.so:
+    float-exact round trip, the reference's error texts."""
+    import subprocess
+    src = tmp_path / "io_check.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include <fstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "deplex/utils/eigen_io.h"
+int main(int argc, char** argv) {
+  using namespace deplex::utils;
+  const std::string dir = argv[1];
+  std::vector<float> pts = {0.1f, -2.5e-7f, 46655.f, 1.f / 3.f, 3.4028235e38f, 0.f, 7.f, 8.f, 9.f};
+  savePointCloudCSV(pts, dir + "/cloud.csv");
+  if (readPointCloudCSV(dir + "/cloud.csv", ',') != pts) return 1;
+  { std::ofstream f(dir + "/bad.csv"); f << "1,2,3\n4,5\n"; }
+  try { readPointCloudCSV(dir + "/bad.csv", ','); return 2; }
+  catch (std::runtime_error const& e) { if (std::string(e.what()) != "Error reading file: Invalid points shape") return 3; }
+  { std::ofstream f(dir + "/k.K"); f << "525.0 0 319.5\n0 525.0 239.5\n0 0 1\n"; }
+  const auto k = readIntrinsics(dir + "/k.K");
+  if (k[0] != 525.0f || k[2] != 319.5f || k[4] != 525.0f || k[5] != 239.5f || k[8] != 1.0f) return 4;
+  try { readIntrinsics(dir + "/missing.K"); return 5; }
+  catch (std::runtime_error const& e) {
+    if (std::string(e.what()) != "Error: Couldn't open intrinsics file " + dir + "/missing.K") return 6;
+  }
+  std::puts("io ok");
+  return 0;
+}
+''')
+    pkg = os.path.join(ROOT, "deplex_b200")
+    exe = tmp_path / "io_check"
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-DDEPLEX_NO_EIGEN", f"-I{pkg}/cpp/include", f"-I{ROOT}/include", str(src), "-o",
+                        str(exe), f"-L{pkg}", "-ldeplex", "-ldeplex_b200", f"-Wl,-rpath,{pkg}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "io ok" in r.stdout, (r.returncode, r.stderr[-500:])
