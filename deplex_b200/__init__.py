@@ -8,6 +8,6 @@ C-ABI in include/deplex_b200.h.  There is no CPU fallback: importing works witho
 configuration and host logic can be tested), creating an extractor does not.
 """
 from ._capi import LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR, LIB_PATH, load  # noqa: F401
-from .extractor import Config, CudaError, PipelinedExtractor, PlaneExtractor, UnsupportedError  # noqa: F401
+from .extractor import Config, CudaError, PipelinedExtractor, PlaneExtractor, SequenceExtractor, UnsupportedError  # noqa: F401
 
-__all__ = ["Config", "PlaneExtractor", "PipelinedExtractor", "UnsupportedError", "CudaError", "LAYOUT_COLMAJOR", "LAYOUT_ROWMAJOR"]
+__all__ = ["Config", "PlaneExtractor", "PipelinedExtractor", "SequenceExtractor", "UnsupportedError", "CudaError", "LAYOUT_COLMAJOR", "LAYOUT_ROWMAJOR"]

@@ -16,7 +16,15 @@ EXPORTS = (
     "dpx_process_host", "dpx_process_batch_host", "dpx_process_batch_device", "dpx_process_depth_batch_host",
     "dpx_process_depth_batch_device", "dpx_get_cells", "dpx_get_planes",
     "dpx_set_profiling", "dpx_get_stage_ms", "dpx_get_region_profile", "dpx_kernel_launches", "dpx_host_alloc", "dpx_host_free", "dpx_version",
+    "dpx_set_label_transport",
+    "dpx_pipeline_create", "dpx_pipeline_destroy", "dpx_pipeline_last_error", "dpx_pipeline_lanes", "dpx_pipeline_lane",
+    "dpx_pipeline_submit_device", "dpx_pipeline_submit_depth_device", "dpx_pipeline_join", "dpx_pipeline_synchronize",
+    "dpx_pipeline_kernel_launches",
+    "dpx_sequence_create", "dpx_sequence_destroy", "dpx_sequence_last_error", "dpx_sequence_devices", "dpx_sequence_range",
+    "dpx_sequence_process_host", "dpx_sequence_process_depth_host", "dpx_sequence_process_device",
+    "dpx_device_count", "dpx_device_alloc", "dpx_device_free", "dpx_memcpy_to_device", "dpx_memcpy_to_host",
 )
+LABELS_AUTO, LABELS_I32, LABELS_U16 = 0, 1, 2
 
 
 class dpx_config(C.Structure):
@@ -92,6 +100,30 @@ def load():
         "dpx_host_alloc": (C.c_int, [C.POINTER(vp), C.c_size_t]),
         "dpx_host_free": (None, [vp]),
         "dpx_version": (i32, []),
+        "dpx_set_label_transport": (C.c_int, [vp, i32]),
+        "dpx_pipeline_create": (C.c_int, [i32, i32, C.POINTER(dpx_config), i32, i32, i32, C.POINTER(vp)]),
+        "dpx_pipeline_destroy": (None, [vp]),
+        "dpx_pipeline_last_error": (C.c_char_p, [vp]),
+        "dpx_pipeline_lanes": (i32, [vp]),
+        "dpx_pipeline_lane": (vp, [vp, i32]),
+        "dpx_pipeline_submit_device": (C.c_int, [vp, vp, i32, C.c_int, vp, vp]),
+        "dpx_pipeline_submit_depth_device": (C.c_int, [vp, vp, i32, C.POINTER(dpx_intrinsics), vp, vp]),
+        "dpx_pipeline_join": (C.c_int, [vp, vp]),
+        "dpx_pipeline_synchronize": (C.c_int, [vp]),
+        "dpx_pipeline_kernel_launches": (i64, [vp]),
+        "dpx_sequence_create": (C.c_int, [i32, i32, C.POINTER(dpx_config), C.POINTER(i32), i32, i32, C.POINTER(vp)]),
+        "dpx_sequence_destroy": (None, [vp]),
+        "dpx_sequence_last_error": (C.c_char_p, [vp]),
+        "dpx_sequence_devices": (i32, [vp]),
+        "dpx_sequence_range": (None, [vp, i64, i32, C.POINTER(i64), C.POINTER(i64)]),
+        "dpx_sequence_process_host": (C.c_int, [vp, vp, i64, C.c_int, vp]),
+        "dpx_sequence_process_depth_host": (C.c_int, [vp, vp, i64, C.POINTER(dpx_intrinsics), vp]),
+        "dpx_sequence_process_device": (C.c_int, [vp, C.POINTER(vp), i64, C.c_int, C.POINTER(vp), i32, C.POINTER(C.c_float)]),
+        "dpx_device_count": (i32, []),
+        "dpx_device_alloc": (C.c_int, [i32, C.POINTER(vp), C.c_size_t]),
+        "dpx_device_free": (None, [i32, vp]),
+        "dpx_memcpy_to_device": (C.c_int, [i32, vp, vp, C.c_size_t]),
+        "dpx_memcpy_to_host": (C.c_int, [i32, vp, vp, C.c_size_t]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

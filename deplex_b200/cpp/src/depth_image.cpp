@@ -3,8 +3,10 @@
 // Reference: cpp/deplex/src/deplex/utils/depth_image.cpp:30-78, which decodes through the vendored
 // stb_image (`stbi_load_16(path, &w, &h, &channels, STBI_grey)`).  This reader is written against the PNG
 // specification (RFC 2083) over zlib's inflate and produces what that call produces for the files deplex
-// is used with: 8-bit samples are widened as v * 257, colour is reduced to luma as (77 r + 150 g + 29 b) >> 8,
-// alpha is dropped.  Interlaced and palette PNGs are rejected (depth maps are neither).
+// is used with, in stb's order of operations: colour is reduced to luma as (77 r + 150 g + 29 b) >> 8 at the file's own
+// sample width FIRST, and an 8-bit result is then widened as v * 257; alpha is dropped; grey samples of 1, 2 and 4 bits
+// are scaled to 8 bits (x 255, 85, 17) and palette images are expanded through PLTE before that.  Interlaced (Adam7)
+// PNGs are rejected with the reference's "Couldn't read image" error (stb decodes them; depth maps are never interlaced).
 #include "deplex/utils/depth_image.h"
 
 #include <zlib.h>
@@ -40,7 +42,7 @@ bool decode_png_grey16(std::string const& path, std::vector<uint16_t>* out, int3
   size_t pos = 8;
   uint32_t w = 0, h = 0;
   int depth = 0, color = -1, interlace = 0;
-  std::vector<unsigned char> idat;
+  std::vector<unsigned char> idat, plte;
   bool seen_end = false;
   while (!seen_end && pos + 12 <= file.size()) {
     const uint32_t len = be32(&file[pos]);
@@ -55,6 +57,8 @@ bool decode_png_grey16(std::string const& path, std::vector<uint16_t>* out, int3
       color = body[9];
       if (body[10] != 0 || body[11] != 0) return false;
       interlace = body[12];
+    } else if (std::memcmp(type, "PLTE", 4) == 0) {
+      plte.assign(body, body + len);
     } else if (std::memcmp(type, "IDAT", 4) == 0) {
       idat.insert(idat.end(), body, body + len);
     } else if (std::memcmp(type, "IEND", 4) == 0) {
@@ -64,17 +68,21 @@ bool decode_png_grey16(std::string const& path, std::vector<uint16_t>* out, int3
   }
   if (w == 0 || h == 0 || w > (1u << 24) || h > (1u << 24) || idat.empty()) return false;
   if (interlace != 0) return false;
-  if (depth != 8 && depth != 16) return false;
   int channels;
   switch (color) {
     case 0: channels = 1; break;
     case 2: channels = 3; break;
+    case 3: channels = 1; break;  // palette indices
     case 4: channels = 2; break;
     case 6: channels = 4; break;
     default: return false;
   }
-  const size_t bpp = static_cast<size_t>(channels) * (depth / 8);  // bytes per pixel
-  const size_t stride = bpp * w;
+  // legal sample widths (RFC 2083 section 3.1.1)
+  const bool sub_byte = depth == 1 || depth == 2 || depth == 4;
+  if (!(depth == 8 || (depth == 16 && color != 3) || (sub_byte && (color == 0 || color == 3)))) return false;
+  if (color == 3 && (plte.empty() || plte.size() % 3 != 0)) return false;
+  const size_t bpp = sub_byte ? 1 : static_cast<size_t>(channels) * (depth / 8);  // filter distance in bytes
+  const size_t stride = (static_cast<size_t>(w) * channels * depth + 7) / 8;
   std::vector<unsigned char> raw((stride + 1) * h);
   uLongf raw_len = static_cast<uLongf>(raw.size());
   if (uncompress(raw.data(), &raw_len, idat.data(), static_cast<uLong>(idat.size())) != Z_OK) return false;
@@ -106,15 +114,38 @@ bool decode_png_grey16(std::string const& path, std::vector<uint16_t>* out, int3
   }
 
   out->resize(static_cast<size_t>(w) * h);
-  for (size_t p = 0; p < out->size(); ++p) {
-    uint32_t ch[4] = {0, 0, 0, 0};
-    for (int c = 0; c < channels; ++c) {
-      const unsigned char* s = &img[p * bpp + static_cast<size_t>(c) * (depth / 8)];
-      ch[c] = depth == 16 ? static_cast<uint32_t>((s[0] << 8) | s[1]) : static_cast<uint32_t>(s[0]) * 257u;
+  const uint32_t scale = depth == 1 ? 0xffu : depth == 2 ? 0x55u : depth == 4 ? 0x11u : 1u;  // stb's depth_scale_table
+  for (uint32_t y = 0; y < h; ++y) {
+    const unsigned char* row = &img[stride * y];
+    for (uint32_t x = 0; x < w; ++x) {
+      uint32_t ch[4] = {0, 0, 0, 0};
+      int n_ch = channels, bits = depth;
+      if (depth < 8 || color == 3) {
+        uint32_t v = row[x];
+        if (depth < 8) {
+          const size_t bit = static_cast<size_t>(x) * depth;
+          v = (row[bit >> 3] >> (8 - depth - (bit & 7))) & ((1u << depth) - 1u);
+        }
+        bits = 8;
+        if (color == 3) {
+          if (static_cast<size_t>(v) * 3 + 2 >= plte.size()) return false;
+          ch[0] = plte[3 * v]; ch[1] = plte[3 * v + 1]; ch[2] = plte[3 * v + 2];
+          n_ch = 3;
+        } else {
+          ch[0] = v * scale;
+        }
+      } else {
+        for (int c = 0; c < channels; ++c) {
+          const unsigned char* s = row + static_cast<size_t>(x) * channels * (depth / 8) + static_cast<size_t>(c) * (depth / 8);
+          ch[c] = depth == 16 ? static_cast<uint32_t>((s[0] << 8) | s[1]) : static_cast<uint32_t>(s[0]);
+        }
+      }
+      // stb: reduce to grey at the file's sample width (stbi__compute_y / _16), then widen 8 -> 16 bits as v * 257
+      uint32_t grey = ch[0];
+      if (n_ch >= 3) grey = (ch[0] * 77u + ch[1] * 150u + ch[2] * 29u) >> 8;
+      if (bits == 8) grey = (grey & 0xffu) * 257u;
+      (*out)[static_cast<size_t>(y) * w + x] = static_cast<uint16_t>(grey);
     }
-    uint32_t grey = ch[0];
-    if (channels >= 3) grey = (ch[0] * 77u + ch[1] * 150u + ch[2] * 29u) >> 8;
-    (*out)[p] = static_cast<uint16_t>(grey);
   }
   *width = static_cast<int32_t>(w);
   *height = static_cast<int32_t>(h);

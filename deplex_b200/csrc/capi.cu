@@ -11,12 +11,15 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "cell_stats.cuh"
 #include "depth_points.cuh"
 #include "error_state.h"
+#include "host_pool.h"
 #include "labeling.cuh"
 #include "refine.cuh"
 #include "region_grow.cuh"
@@ -30,6 +33,9 @@ const char* thread_error() { return g_thread_error.c_str(); }
 }  // namespace dpx
 
 using namespace dpx;
+
+constexpr int kHostSlots = 4;     // chunks in flight on the host-pointer path
+constexpr int kHostLookahead = 2; // chunks queued behind the one whose labels the host is waiting for
 
 struct dpx_extractor {
   dpx_config cfg;
@@ -46,15 +52,22 @@ struct dpx_extractor {
   long long* region_prof = nullptr;  // [max_batch][kRegionProfSlots], written while profiling is on
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
-  // host-pointer path: double-buffered staging + three streams
-  int host_chunk = 0;
-  float* d_xyz[2] = {nullptr, nullptr};
-  uint16_t* d_depth[2] = {nullptr, nullptr};  // staging of the raw-depth host path
-  float* d_conv = nullptr;                    // points generated from depth when the fused path cannot run
+  // host-pointer path: kHostSlots staging buffers in flight on three streams (copy in, kernels, copy out)
+  int host_chunk_xyz = 0, host_chunk_depth = 0;  // frames per pipelined chunk (sized by bytes, see ensure_host_path)
+  float* d_xyz[kHostSlots] = {};
+  uint16_t* d_depth[kHostSlots] = {};  // staging of the raw-depth host path
+  float* d_conv = nullptr;             // points generated from depth when the fused path cannot run
   size_t d_conv_frames = 0;
-  int32_t* d_lab[2] = {nullptr, nullptr};
+  int32_t* d_lab[kHostSlots] = {};
+  int lab_chunk = 0;                   // frames d_lab[] / d_nar[] / h_nar[] are sized for
+  // narrow label transport: labels cross PCIe as uint16 and are widened into the caller's int32 buffer by host threads
+  int label_transport = DPX_LABELS_AUTO;
+  uint16_t* d_nar[kHostSlots] = {};
+  uint16_t* h_nar[kHostSlots] = {};    // pinned
+  uint64_t widen_ticket[kHostSlots] = {};
+  std::unique_ptr<HostPool> pool;
   cudaStream_t s_h2d = nullptr, s_run = nullptr, s_d2h = nullptr;
-  cudaEvent_t e_h2d[2] = {nullptr, nullptr}, e_run[2] = {nullptr, nullptr}, e_d2h[2] = {nullptr, nullptr};
+  cudaEvent_t e_h2d[kHostSlots] = {}, e_run[kHostSlots] = {}, e_d2h[kHostSlots] = {};
   // measurement
   bool profiling = false;
   cudaEvent_t e_stage[DPX_N_STAGES + 1] = {};
@@ -141,10 +154,10 @@ dpx_status run_stages(dpx_extractor* ex, const float* d_xyz, int n_frames, int l
     if (ex->cfg.ransac_refinement || !cell_stats_depth_eligible(probe)) {
       // materialise the points once (row-major) and continue on the ordinary path
       if (ex->d_conv_frames < static_cast<size_t>(n_frames)) {
-        if (ex->d_conv) DPX_CUDA(ex, cudaFree(ex->d_conv));
-        ex->d_conv = nullptr;
-        ex->d_conv_frames = 0;
-        DPX_CUDA(ex, cudaMalloc(&ex->d_conv, static_cast<size_t>(ex->max_batch) * ex->geom.n_points * 3 * sizeof(float)));
+        // first use only, stream-ordered (cudaMallocAsync does not synchronise the device, so the call stays
+        // asynchronous on the caller's stream); the buffer is kept for the life of the handle
+        DPX_CUDA(ex, cudaMallocAsync(reinterpret_cast<void**>(&ex->d_conv),
+                                     static_cast<size_t>(ex->max_batch) * ex->geom.n_points * 3 * sizeof(float), st));
         ex->d_conv_frames = static_cast<size_t>(ex->max_batch);
       }
       DPX_CUDA(ex, launch_depth_to_points(d_depth, n_frames, ex->geom, ph, ex->d_conv, st));
@@ -182,6 +195,7 @@ dpx_status run_stages(dpx_extractor* ex, const float* d_xyz, int n_frames, int l
     ra.thr = ex->thr;
     ra.tables = ex->tb;
     ra.labels = ex->fuse_labeling ? d_labels : nullptr;
+    ra.labels_vec_ok = labels_vec_ok(ex->geom, d_labels) ? 1 : 0;
     DPX_CUDA(ex, launch_region_grow(ra, st, &labels_painted));
     ex->launches += 2;  // edge masks + region growing
   }
@@ -194,6 +208,7 @@ dpx_status run_stages(dpx_extractor* ex, const float* d_xyz, int n_frames, int l
     la.cell_label = ex->tb.cell_label;
     la.labels = d_labels;
     la.todo = labels_painted ? ex->tb.paint_state + 1 : nullptr;
+    la.vec_ok = labels_vec_ok(ex->geom, d_labels) ? 1 : 0;
     DPX_CUDA(ex, launch_labeling(la, st));
     if (ex->geom.n_cells > 0) ++ex->launches;
   }
@@ -221,14 +236,26 @@ dpx_status run_stages(dpx_extractor* ex, const float* d_xyz, int n_frames, int l
   return DPX_OK;
 }
 
+int env_int(const char* name, int fallback) {
+  const char* e = std::getenv(name);
+  return e && *e ? std::atoi(e) : fallback;
+}
+
+// Streams, events and chunk sizes of the host-pointer path (first host call only).
 dpx_status ensure_host_path(dpx_extractor* ex) {
   if (ex->s_run) return DPX_OK;
-  int hc = 16;  // frames per pipelined chunk of the host-pointer path (env DPX_HOST_CHUNK for A/B measurements)
-  if (const char* e = std::getenv("DPX_HOST_CHUNK")) hc = std::max(1, std::atoi(e));
-  ex->host_chunk = std::max(1, std::min(ex->max_batch, hc));
-  const size_t np = static_cast<size_t>(ex->geom.n_points);
-  for (int i = 0; i < 2; ++i) {
-    DPX_CUDA(ex, cudaMalloc(&ex->d_lab[i], std::max<size_t>(16, np * sizeof(int32_t) * ex->host_chunk)));
+  // A chunk is what one H2D copy moves: about 64 MB, so that the copy engine works in long transfers while the kernels of
+  // the previous chunk run (640x480: 16 frames of points, 64 frames of raw depth).  DPX_HOST_CHUNK overrides (A/B).
+  const size_t np = std::max<size_t>(1, static_cast<size_t>(ex->geom.n_points));
+  const size_t target = 64u << 20;
+  const int forced = env_int("DPX_HOST_CHUNK", 0);
+  auto sized = [&](size_t bytes_per_frame) {
+    const int c = forced > 0 ? forced : static_cast<int>(std::min<size_t>(64, std::max<size_t>(1, target / bytes_per_frame)));
+    return std::max(1, std::min(ex->max_batch, c));
+  };
+  ex->host_chunk_xyz = sized(np * 3 * sizeof(float));
+  ex->host_chunk_depth = sized(np * sizeof(uint16_t));
+  for (int i = 0; i < kHostSlots; ++i) {
     DPX_CUDA(ex, cudaEventCreateWithFlags(&ex->e_h2d[i], cudaEventDisableTiming));
     DPX_CUDA(ex, cudaEventCreateWithFlags(&ex->e_run[i], cudaEventDisableTiming));
     DPX_CUDA(ex, cudaEventCreateWithFlags(&ex->e_d2h[i], cudaEventDisableTiming));
@@ -237,6 +264,58 @@ dpx_status ensure_host_path(dpx_extractor* ex) {
   DPX_CUDA(ex, cudaStreamCreateWithFlags(&ex->s_d2h, cudaStreamNonBlocking));
   DPX_CUDA(ex, cudaStreamCreateWithFlags(&ex->s_run, cudaStreamNonBlocking));
   return DPX_OK;
+}
+
+// Device label staging for chunks of up to `chunk` frames (grown on demand: the depth path uses larger chunks).
+dpx_status ensure_label_staging(dpx_extractor* ex, int chunk, bool narrow) {
+  const size_t np = static_cast<size_t>(ex->geom.n_points);
+  if (chunk > ex->lab_chunk) {
+    DPX_CUDA(ex, cudaDeviceSynchronize());
+    for (int i = 0; i < kHostSlots; ++i) {
+      if (ex->d_lab[i]) DPX_CUDA(ex, cudaFree(ex->d_lab[i]));
+      if (ex->d_nar[i]) DPX_CUDA(ex, cudaFree(ex->d_nar[i]));
+      if (ex->h_nar[i]) DPX_CUDA(ex, cudaFreeHost(ex->h_nar[i]));
+      ex->d_lab[i] = nullptr; ex->d_nar[i] = nullptr; ex->h_nar[i] = nullptr;
+      DPX_CUDA(ex, cudaMalloc(&ex->d_lab[i], std::max<size_t>(16, np * sizeof(int32_t) * chunk)));
+    }
+    ex->lab_chunk = chunk;
+  }
+  if (narrow && !ex->d_nar[0]) {
+    for (int i = 0; i < kHostSlots; ++i) {
+      DPX_CUDA(ex, cudaMalloc(&ex->d_nar[i], std::max<size_t>(16, np * sizeof(uint16_t) * ex->lab_chunk)));
+      DPX_CUDA(ex, cudaHostAlloc(reinterpret_cast<void**>(&ex->h_nar[i]), std::max<size_t>(16, np * sizeof(uint16_t) * ex->lab_chunk),
+                                 cudaHostAllocDefault));
+    }
+  }
+  if (narrow && !ex->pool) {
+    // widening threads: DPX_HOST_THREADS, else the host's hardware threads shared among the visible GPUs, at most 8
+    int n_dev = 1;
+    cudaGetDeviceCount(&n_dev);
+    const int hw = static_cast<int>(std::thread::hardware_concurrency());
+    const int n = env_int("DPX_HOST_THREADS", std::max(1, std::min(8, hw / std::max(1, n_dev))));
+    ex->pool.reset(new HostPool(std::max(1, n)));
+  }
+  return DPX_OK;
+}
+
+// Chunk sizes of one host batch: a short ramp up (the first kernels start after a small copy), full chunks, and a ramp
+// down (the last labels come back after a small copy), so that the unoverlapped head and tail of the three-stage pipeline
+// cost a couple of frames' worth of PCIe time instead of a full chunk's.
+std::vector<int> chunk_schedule(int n_frames, int chunk) {
+  std::vector<int> up, down, out;
+  int ramp = 0;
+  for (int c = std::max(1, chunk / 8); c < chunk; c *= 2) { up.push_back(c); ramp += c; }
+  down.assign(up.rbegin(), up.rend());
+  if (n_frames < 2 * ramp + chunk) {  // too short to taper: equal chunks
+    for (int f = 0; f < n_frames; f += chunk) out.push_back(std::min(chunk, n_frames - f));
+    return out;
+  }
+  out = up;
+  int middle = n_frames - 2 * ramp;
+  for (; middle >= chunk; middle -= chunk) out.push_back(chunk);
+  if (middle > 0) out.push_back(middle);
+  out.insert(out.end(), down.begin(), down.end());
+  return out;
 }
 
 }  // namespace
@@ -340,6 +419,8 @@ dpx_status dpx_create(int32_t height, int32_t width, const dpx_config* cfg_in, i
     if (const char* e = std::getenv("DPX_STREAM_WARPS")) { const int w = std::atoi(e); ex->stream_warps = (w == 8 || w == 12) ? w : 16; }
     if (const char* e = std::getenv("DPX_CELL_KERNEL")) ex->force_tile_kernel = std::strcmp(e, "tile") == 0;
     if (const char* e = std::getenv("DPX_FUSE_LABELING")) ex->fuse_labeling = std::atoi(e) != 0;
+    if (const char* e = std::getenv("DPX_LABEL_TRANSPORT"))
+      ex->label_transport = std::strcmp(e, "u16") == 0 ? DPX_LABELS_U16 : std::strcmp(e, "i32") == 0 ? DPX_LABELS_I32 : DPX_LABELS_AUTO;
     ex->plan = region_grow_plan(g, th);
     Tables probe{};
     ex->scratch_bytes = carve_tables(g, max_batch, ex->plan.bins_smem != 0, nullptr, &probe);
@@ -370,10 +451,13 @@ void dpx_destroy(dpx_extractor* ex) {
   if (!ex) return;
   DeviceGuard guard(ex->device);
   cudaDeviceSynchronize();
-  for (int i = 0; i < 2; ++i) {
+  ex->pool.reset();
+  for (int i = 0; i < kHostSlots; ++i) {
     if (ex->d_xyz[i]) cudaFree(ex->d_xyz[i]);
     if (ex->d_lab[i]) cudaFree(ex->d_lab[i]);
     if (ex->d_depth[i]) cudaFree(ex->d_depth[i]);
+    if (ex->d_nar[i]) cudaFree(ex->d_nar[i]);
+    if (ex->h_nar[i]) cudaFreeHost(ex->h_nar[i]);
     if (ex->e_h2d[i]) cudaEventDestroy(ex->e_h2d[i]);
     if (ex->e_run[i]) cudaEventDestroy(ex->e_run[i]);
     if (ex->e_d2h[i]) cudaEventDestroy(ex->e_d2h[i]);
@@ -420,7 +504,9 @@ dpx_status dpx_process_batch_device(dpx_extractor* ex, const float* d_xyz, int32
 }
 
 namespace {
-// Host pointers: chunks of host_chunk frames, H2D / kernels / D2H on three streams, double-buffered.
+// Host pointers: tapered chunks, H2D / kernels / D2H on three streams, kHostSlots chunks in flight.  With the narrow
+// label transport the labels come back as uint16 into pinned staging and are widened into `labels` by the host pool
+// while the following chunks are in flight.
 dpx_status process_host_impl(dpx_extractor* ex, const void* src, size_t bytes_per_frame, int32_t n_frames, int layout,
                              const dpx_intrinsics* pin, int32_t* labels) {
   DeviceGuard guard(ex->device);
@@ -429,44 +515,85 @@ dpx_status process_host_impl(dpx_extractor* ex, const void* src, size_t bytes_pe
   if (st != DPX_OK) return st;
   const bool is_depth = layout == kLayoutDepth16;
   const size_t np = static_cast<size_t>(ex->geom.n_points);
-  const int chunk = ex->host_chunk;
+  const int chunk = is_depth ? ex->host_chunk_depth : ex->host_chunk_xyz;
+  int transport = ex->label_transport;
+  if (transport == DPX_LABELS_AUTO) transport = (is_depth && n_frames > 1) ? DPX_LABELS_U16 : DPX_LABELS_I32;
+  const bool narrow = transport == DPX_LABELS_U16 && n_frames > 1;
+  st = ensure_label_staging(ex, chunk, narrow);
+  if (st != DPX_OK) return st;
   if (is_depth && !ex->d_depth[0])
-    for (int i = 0; i < 2; ++i) DPX_CUDA(ex, cudaMalloc(&ex->d_depth[i], std::max<size_t>(16, np * sizeof(uint16_t) * chunk)));
+    for (int i = 0; i < kHostSlots; ++i) DPX_CUDA(ex, cudaMalloc(&ex->d_depth[i], std::max<size_t>(16, np * sizeof(uint16_t) * chunk)));
   if (!is_depth && !ex->d_xyz[0])
-    for (int i = 0; i < 2; ++i) DPX_CUDA(ex, cudaMalloc(&ex->d_xyz[i], std::max<size_t>(16, np * 3 * sizeof(float) * chunk)));
-  if (n_frames <= chunk) {
+    for (int i = 0; i < kHostSlots; ++i) DPX_CUDA(ex, cudaMalloc(&ex->d_xyz[i], std::max<size_t>(16, np * 3 * sizeof(float) * chunk)));
+  auto launch = [&](int slot, int nf) {
+    return is_depth ? run_stages(ex, nullptr, nf, layout, ex->d_lab[slot], ex->s_run, ex->d_depth[slot], pin)
+                    : run_stages(ex, ex->d_xyz[slot], nf, layout, ex->d_lab[slot], ex->s_run);
+  };
+  if (n_frames == 1) {
     // latency path (a single process() call): everything on one stream, no cross-stream hand-offs
     void* d_in = is_depth ? static_cast<void*>(ex->d_depth[0]) : static_cast<void*>(ex->d_xyz[0]);
-    DPX_CUDA(ex, cudaMemcpyAsync(d_in, src, bytes_per_frame * n_frames, cudaMemcpyHostToDevice, ex->s_run));
-    st = is_depth ? run_stages(ex, nullptr, n_frames, layout, ex->d_lab[0], ex->s_run, ex->d_depth[0], pin)
-                  : run_stages(ex, ex->d_xyz[0], n_frames, layout, ex->d_lab[0], ex->s_run);
+    DPX_CUDA(ex, cudaMemcpyAsync(d_in, src, bytes_per_frame, cudaMemcpyHostToDevice, ex->s_run));
+    st = launch(0, 1);
     if (st != DPX_OK) return st;
-    DPX_CUDA(ex, cudaMemcpyAsync(labels, ex->d_lab[0], np * sizeof(int32_t) * n_frames, cudaMemcpyDeviceToHost, ex->s_run));
+    DPX_CUDA(ex, cudaMemcpyAsync(labels, ex->d_lab[0], np * sizeof(int32_t), cudaMemcpyDeviceToHost, ex->s_run));
     DPX_CUDA(ex, cudaStreamSynchronize(ex->s_run));
     return DPX_OK;
   }
-  int n_chunks = 0;
-  for (int f0 = 0; f0 < n_frames; f0 += chunk, ++n_chunks) {
-    const int slot = n_chunks & 1;
-    const int nf = std::min(chunk, n_frames - f0);
+  const std::vector<int> sizes = chunk_schedule(n_frames, chunk);
+  const int n_chunks = static_cast<int>(sizes.size());
+  std::vector<int> first(n_chunks);
+  for (int i = 0, f = 0; i < n_chunks; f += sizes[i], ++i) first[i] = f;
+  // host side of a finished chunk (narrow transport only): wait for its D2H, hand the widening to the pool
+  auto retire = [&](int i) -> dpx_status {
+    const int slot = i % kHostSlots;
+    DPX_CUDA(ex, cudaEventSynchronize(ex->e_d2h[slot]));
+    ex->widen_ticket[slot] = ex->pool->widen(ex->h_nar[slot], labels + static_cast<size_t>(first[i]) * np, np * sizes[i]);
+    return DPX_OK;
+  };
+  for (int i = 0; i < n_chunks; ++i) {
+    const int slot = i % kHostSlots;
+    const int nf = sizes[i], f0 = first[i];
     void* d_in = is_depth ? static_cast<void*>(ex->d_depth[slot]) : static_cast<void*>(ex->d_xyz[slot]);
-    // H2D into slot: the kernels of the chunk that used this slot two rounds ago must be done reading it
-    if (n_chunks >= 2) DPX_CUDA(ex, cudaStreamWaitEvent(ex->s_h2d, ex->e_run[slot], 0));
+    // H2D into slot: the kernels of the chunk that used this slot kHostSlots rounds ago must be done reading it
+    if (i >= kHostSlots) DPX_CUDA(ex, cudaStreamWaitEvent(ex->s_h2d, ex->e_run[slot], 0));
     DPX_CUDA(ex, cudaMemcpyAsync(d_in, static_cast<const char*>(src) + static_cast<size_t>(f0) * bytes_per_frame,
                                  bytes_per_frame * nf, cudaMemcpyHostToDevice, ex->s_h2d));
     DPX_CUDA(ex, cudaEventRecord(ex->e_h2d[slot], ex->s_h2d));
     // kernels: need the input, and the label slot must have been drained
     DPX_CUDA(ex, cudaStreamWaitEvent(ex->s_run, ex->e_h2d[slot], 0));
-    if (n_chunks >= 2) DPX_CUDA(ex, cudaStreamWaitEvent(ex->s_run, ex->e_d2h[slot], 0));
-    st = is_depth ? run_stages(ex, nullptr, nf, layout, ex->d_lab[slot], ex->s_run, ex->d_depth[slot], pin)
-                  : run_stages(ex, ex->d_xyz[slot], nf, layout, ex->d_lab[slot], ex->s_run);
+    if (i >= kHostSlots) DPX_CUDA(ex, cudaStreamWaitEvent(ex->s_run, ex->e_d2h[slot], 0));
+    st = launch(slot, nf);
     if (st != DPX_OK) return st;
+    if (narrow) {
+      DPX_CUDA(ex, launch_narrow_labels(ex->d_lab[slot], ex->d_nar[slot], static_cast<long long>(np) * nf, ex->s_run));
+      ++ex->launches;
+    }
     DPX_CUDA(ex, cudaEventRecord(ex->e_run[slot], ex->s_run));
     // D2H
     DPX_CUDA(ex, cudaStreamWaitEvent(ex->s_d2h, ex->e_run[slot], 0));
-    DPX_CUDA(ex, cudaMemcpyAsync(labels + static_cast<size_t>(f0) * np, ex->d_lab[slot], np * sizeof(int32_t) * nf,
-                                 cudaMemcpyDeviceToHost, ex->s_d2h));
+    if (narrow) {
+      ex->pool->wait(ex->widen_ticket[slot]);  // the staging buffer's previous contents have been widened
+      ex->widen_ticket[slot] = 0;
+      DPX_CUDA(ex, cudaMemcpyAsync(ex->h_nar[slot], ex->d_nar[slot], np * sizeof(uint16_t) * nf, cudaMemcpyDeviceToHost, ex->s_d2h));
+    } else {
+      DPX_CUDA(ex, cudaMemcpyAsync(labels + static_cast<size_t>(f0) * np, ex->d_lab[slot], np * sizeof(int32_t) * nf,
+                                   cudaMemcpyDeviceToHost, ex->s_d2h));
+    }
     DPX_CUDA(ex, cudaEventRecord(ex->e_d2h[slot], ex->s_d2h));
+    if (narrow && i >= kHostLookahead) {
+      st = retire(i - kHostLookahead);
+      if (st != DPX_OK) return st;
+    }
+  }
+  if (narrow) {
+    for (int i = std::max(0, n_chunks - kHostLookahead); i < n_chunks; ++i) {
+      st = retire(i);
+      if (st != DPX_OK) return st;
+    }
+    for (int slot = 0; slot < kHostSlots; ++slot) {
+      ex->pool->wait(ex->widen_ticket[slot]);
+      ex->widen_ticket[slot] = 0;
+    }
   }
   DPX_CUDA(ex, cudaStreamSynchronize(ex->s_d2h));
   DPX_CUDA(ex, cudaStreamSynchronize(ex->s_run));
@@ -613,6 +740,13 @@ dpx_status dpx_get_region_profile(dpx_extractor* ex, int32_t frame, int64_t out[
 }
 
 int64_t dpx_kernel_launches(const dpx_extractor* ex) { return ex ? ex->launches : 0; }
+
+dpx_status dpx_set_label_transport(dpx_extractor* ex, int32_t mode) {
+  if (!ex) return DPX_ERR_ARGUMENT;
+  if (mode != DPX_LABELS_AUTO && mode != DPX_LABELS_I32 && mode != DPX_LABELS_U16) return fail(ex, DPX_ERR_ARGUMENT, "unknown label transport");
+  ex->label_transport = mode;
+  return DPX_OK;
+}
 
 dpx_status dpx_host_alloc(void** ptr, size_t bytes) {
   if (!ptr) return DPX_ERR_ARGUMENT;

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(kLabelThreads) labeling_kernel(const LabelArgs
     lab[i] = (col + i < g.width) ? __ldg(cl + cq) : 0;
     if (++rem == p) { rem = 0; ++cq; }
   }
-  if ((g.width & 3) == 0) {
+  if (args.vec_ok) {
     const int4 v = make_int4(lab[0], lab[1], lab[2], lab[3]);
     for (int r = 0; r < p; ++r) st_stream_i4(reinterpret_cast<int4*>(out + static_cast<long long>(r) * g.width), v);
   } else {
@@ -52,7 +52,39 @@ __global__ void __launch_bounds__(kLabelThreads) labeling_kernel(const LabelArgs
   }
 }
 
+// 8 labels per thread: two 16-byte loads, one 16-byte store
+__global__ void __launch_bounds__(256) narrow_labels_kernel(const int32_t* __restrict__ in, uint16_t* __restrict__ out, long long n8,
+                                                            long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (i < n8) {
+    const int4 a = __ldcs(reinterpret_cast<const int4*>(in) + 2 * i), b = __ldcs(reinterpret_cast<const int4*>(in) + 2 * i + 1);
+    uint4 o;
+    o.x = (static_cast<unsigned>(a.x) & 0xffffu) | (static_cast<unsigned>(a.y) << 16);
+    o.y = (static_cast<unsigned>(a.z) & 0xffffu) | (static_cast<unsigned>(a.w) << 16);
+    o.z = (static_cast<unsigned>(b.x) & 0xffffu) | (static_cast<unsigned>(b.y) << 16);
+    o.w = (static_cast<unsigned>(b.z) & 0xffffu) | (static_cast<unsigned>(b.w) << 16);
+    __stcs(reinterpret_cast<uint4*>(out) + i, o);
+  }
+  // scalar tail (n not a multiple of 8): the last block's first threads
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x < n - 8 * n8) {
+    const long long j = 8 * n8 + threadIdx.x;
+    out[j] = static_cast<uint16_t>(in[j]);
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_narrow_labels(const int32_t* labels, uint16_t* out, long long n, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  const bool vec = (reinterpret_cast<uintptr_t>(labels) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+  const long long n8 = vec ? n / 8 : 0;
+  if (n - 8 * n8 > 256) {  // unaligned buffers: plain element-wise copy through the tail path is not enough
+    return cudaErrorInvalidValue;
+  }
+  const long long blocks = (n8 + 255) / 256 > 0 ? (n8 + 255) / 256 : 1;
+  narrow_labels_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(labels, out, n8, n);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_labeling(const LabelArgs& args, cudaStream_t stream) {
   const Geometry& g = args.geom;

@@ -17,6 +17,7 @@ struct RegionArgs {
   int n_frames;
   long long* prof;  // optional [F][kRegionProfSlots] per-phase cycle counters, or nullptr
   int32_t* labels;  // optional [F][H*W]: when set and the CTA kernel runs, it also paints the per-pixel labels (stage 3 fused)
+  int labels_vec_ok;  // 16-byte stores into `labels` allowed (labeling.cuh: labels_vec_ok)
   RegionPlan plan;
   Geometry geom;
   Thresholds thr;

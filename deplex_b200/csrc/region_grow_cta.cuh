@@ -724,7 +724,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
     const int p = g.patch, width = g.width;
     int32_t* out = args.labels + static_cast<long long>(frame) * g.n_points;
     const int groups = (width + 3) / 4;  // groups of 4 consecutive pixels of one image row
-    const bool vec = (width & 3) == 0;
+    const bool vec = args.labels_vec_ok != 0;
     for (int item = tid; item < nv * groups; item += kCtaThreads) {
       const int cr = item / groups, gi = item - cr * groups;
       const int col = gi * 4;

@@ -127,11 +127,13 @@ class PlaneExtractor:
         """One organized cloud, any numeric (N,3) array (converted to float32 like the pybind Eigen caster).
         Returns int32 labels of shape (N,): 0 = non-planar, k > 0 = plane id (not compacted)."""
         a = np.asarray(pcd_array)
+        # pybind11's Eigen::MatrixX3f caster (cpp/pybind/plane_extraction/plane_extraction.cpp:36) takes an (N, 3)
+        # array and nothing else: a (3, N), flat or (H, W, 3) array is a TypeError there, not a silent reshape
+        if a.ndim != 2 or a.shape[1] != 3:
+            raise TypeError(f"process(): pcd_array must have shape (N, 3), got {a.shape}")
         if a.dtype != np.float32:
             a = a.astype(np.float32)
-        if a.ndim != 2 or (a.size and a.shape[1] != 3):
-            a = a.reshape(-1, 3) if a.size % 3 == 0 else a
-        n = a.shape[0] if a.ndim == 2 else -1
+        n = a.shape[0]
         layout = _host_layout(a) if a.size else LAYOUT_ROWMAJOR
         if layout is None:
             a = np.ascontiguousarray(a)
@@ -252,74 +254,180 @@ class PlaneExtractor:
     def kernel_launches(self):
         return int(self._lib.dpx_kernel_launches(self._h))
 
+    def set_label_transport(self, mode):
+        """'auto' | 'i32' | 'u16': how the batched host entry points bring the labels back over PCIe (the result in
+        the caller's buffer is int32 either way; dpx_set_label_transport)."""
+        m = {"auto": _capi.LABELS_AUTO, "i32": _capi.LABELS_I32, "u16": _capi.LABELS_U16}[mode]
+        self._check(self._lib.dpx_set_label_transport(self._h, m))
+
+    @classmethod
+    def _borrow(cls, handle, height, width):
+        """A view of an extractor owned by someone else (a pipeline lane): never destroyed from here."""
+        self = cls.__new__(cls)
+        self._lib = _capi.load()
+        self._h = C.c_void_p()  # close() / __del__ must not destroy the borrowed handle
+        self._borrowed = C.c_void_p(handle)
+        info = _capi.dpx_info()
+        self._lib.dpx_get_info(self._borrowed, C.byref(info))
+        self.info = info
+        self.height, self.width = int(height), int(width)
+        self.n_points = self.height * self.width
+        self._h = self._borrowed
+        self.close = lambda: None
+        return self
+
 
 class PipelinedExtractor:
-    """`lanes` PlaneExtractor handles, each on its own CUDA stream, fed round-robin (an addition; the reference has no
-    batch API).  Within one batch the HBM-bound cell-stats kernel and the latency-bound region growing run back to
-    back, and the region-growing kernel's tail -- a few long frames on a few SMs -- leaves most of the GPU idle.  With
-    several batches in flight the block scheduler starts the next batch's cell-stats CTAs on every SM that region growing
-    has already left, so the tail is filled (measured on the 256-frame VGA batch: 0.366 ms per batch with one lane,
-    0.277 with two, 0.259 with three).
+    """Several batches in flight on one GPU: a thin owner of a C-ABI `dpx_pipeline` (include/deplex_b200.h), which
+    holds `lanes` extractors, each with its own device tables and CUDA stream, and deals the submitted batches to them
+    round-robin (an addition; the reference's caller loops over process(), examples/process_sequence.cpp:30-43).
+    Within one batch the HBM-bound cell-stats kernel and the latency-bound region growing run back to back, and the
+    region-growing kernel's tail -- a few long frames on a few SMs -- leaves most of the GPU idle; with several
+    batches in flight the next batch's cell-stats CTAs start on every SM region growing has already left.
 
     submit*() is asynchronous: the lane's stream first waits for the work already queued on torch's current stream (the
     producer of the input), and nothing after the call on the current stream is ordered behind the batch until join().
-    Each lane owns its device tables, so results are independent of the lane count; C callers get the same effect with
-    several dpx_extractor handles and streams."""
+    Results do not depend on the lane count."""
 
     def __init__(self, image_height, image_width, config=None, *, max_batch=1, device=-1, lanes=3):
-        import torch
-        assert lanes >= 1
-        self.lanes = [PlaneExtractor(image_height, image_width, config, max_batch=max_batch, device=device)
-                      for _ in range(lanes)]
+        lib = _capi.load()
+        self._lib = lib
+        self._p = C.c_void_p()
+        cfg = config if config is not None else Config()
+        st = lib.dpx_pipeline_create(int(image_height), int(image_width), C.byref(cfg._c), int(device), int(max_batch),
+                                     int(lanes), C.byref(self._p))
+        if st != _capi.DPX_OK:
+            self._p = C.c_void_p()
+            _raise(st, lib.dpx_pipeline_last_error(None))
+        self.lanes = [PlaneExtractor._borrow(lib.dpx_pipeline_lane(self._p, i), image_height, image_width)
+                      for i in range(lib.dpx_pipeline_lanes(self._p))]
         self.info = self.lanes[0].info
         self.n_points = self.lanes[0].n_points
-        self._device = torch.device("cuda", self.info.device)
-        self.streams = [torch.cuda.Stream(self._device) for _ in range(lanes)]
-        self._next = 0
-        self._dirty = [False] * lanes
 
-    def _take_lane(self):
+    def _check(self, st):
+        if st != _capi.DPX_OK:
+            _raise(st, self._lib.dpx_pipeline_last_error(self._p))
+
+    def _current_stream(self, tensor):
         import torch
-        lane = self._next
-        self._next = (lane + 1) % len(self.lanes)
-        self.streams[lane].wait_stream(torch.cuda.current_stream(self._device))
-        self._dirty[lane] = True
-        return lane
+        return torch.cuda.current_stream(tensor.device).cuda_stream
 
     def submit(self, xyz, layout, labels=None):
         """Queue one batch of F <= max_batch device-resident frames; returns the (F,N) int32 CUDA tensor the labels
-        will be in after join() (or after the lane's stream reaches that point)."""
-        lane = self._take_lane()
-        out = self.lanes[lane].process_batch_device(xyz, layout, labels, self.streams[lane])
-        xyz.record_stream(self.streams[lane])
-        out.record_stream(self.streams[lane])
-        return out
+        will be in after join().  Keep `xyz` and the result alive until then."""
+        import torch
+        assert xyz.is_cuda and xyz.dtype == torch.float32 and xyz.is_contiguous()
+        f = xyz.numel() // (3 * self.n_points)
+        assert xyz.numel() == f * 3 * self.n_points
+        if labels is None:
+            labels = torch.empty((f, self.n_points), dtype=torch.int32, device=xyz.device)
+        self._check(self._lib.dpx_pipeline_submit_device(self._p, xyz.data_ptr(), f, layout, labels.data_ptr(),
+                                                         self._current_stream(xyz)))
+        return labels
+
+    def submit_ptr(self, xyz_ptr, n_frames, layout, labels_ptr, stream_ptr):
+        """Raw device pointers (a slice of a larger resident buffer) and a raw cudaStream_t."""
+        self._check(self._lib.dpx_pipeline_submit_device(self._p, xyz_ptr, n_frames, layout, labels_ptr, stream_ptr))
 
     def submit_depth(self, depth, intrinsics, labels=None):
-        """As submit(), for raw uint16 depth frames (dpx_process_depth_batch_device)."""
-        lane = self._take_lane()
-        out = self.lanes[lane].process_depth_batch_device(depth, intrinsics, labels, self.streams[lane])
-        depth.record_stream(self.streams[lane])
-        out.record_stream(self.streams[lane])
-        return out
-
-    def join(self):
-        """Order torch's current stream behind every batch submitted so far (device-side wait, no host sync)."""
+        """As submit(), for raw uint16 depth frames (dpx_pipeline_submit_depth_device)."""
         import torch
-        cur = torch.cuda.current_stream(self._device)
-        for lane, stream in enumerate(self.streams):
-            if self._dirty[lane]:
-                cur.wait_stream(stream)
-                self._dirty[lane] = False
+        assert depth.is_cuda and depth.element_size() == 2 and depth.is_contiguous()
+        f = depth.numel() // self.n_points
+        if labels is None:
+            labels = torch.empty((f, self.n_points), dtype=torch.int32, device=depth.device)
+        k = PlaneExtractor._intrinsics(intrinsics)
+        self._check(self._lib.dpx_pipeline_submit_depth_device(self._p, depth.data_ptr(), f, C.byref(k), labels.data_ptr(),
+                                                               self._current_stream(depth)))
+        return labels
+
+    def join(self, stream=None):
+        """Order `stream` (default: torch's current stream) behind every batch submitted so far (device-side wait)."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(torch.device("cuda", self.info.device))
+        self._check(self._lib.dpx_pipeline_join(self._p, stream.cuda_stream))
 
     def synchronize(self):
-        self.join()
-        for stream in self.streams:
-            stream.synchronize()
+        self._check(self._lib.dpx_pipeline_synchronize(self._p))
 
     def kernel_launches(self):
-        return sum(ex.kernel_launches() for ex in self.lanes)
+        return int(self._lib.dpx_pipeline_kernel_launches(self._p))
 
     def close(self):
-        for ex in self.lanes:
-            ex.close()
+        if getattr(self, "_p", None) and self._p.value:
+            self._lib.dpx_pipeline_destroy(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SequenceExtractor:
+    """A frame sequence sharded over the GPUs of one box from ONE process: a thin owner of a C-ABI `dpx_sequence`
+    (contiguous frame ranges, one worker thread per device, no inter-GPU traffic).  Replaces the loop of
+    examples/process_sequence.cpp:30-43; labels are identical to process() on every frame in order."""
+
+    def __init__(self, image_height, image_width, config=None, *, devices=None, max_batch=64):
+        lib = _capi.load()
+        self._lib = lib
+        self._s = C.c_void_p()
+        cfg = config if config is not None else Config()
+        n = len(devices) if devices else 0
+        arr = (C.c_int32 * max(n, 1))(*(devices or [0]))
+        st = lib.dpx_sequence_create(int(image_height), int(image_width), C.byref(cfg._c), arr if n else None, n,
+                                     int(max_batch), C.byref(self._s))
+        if st != _capi.DPX_OK:
+            self._s = C.c_void_p()
+            _raise(st, lib.dpx_sequence_last_error(None))
+        self.n_devices = int(lib.dpx_sequence_devices(self._s))
+        self.n_points = int(image_height) * int(image_width)
+
+    def _check(self, st):
+        if st != _capi.DPX_OK:
+            _raise(st, self._lib.dpx_sequence_last_error(self._s))
+
+    def frame_range(self, n_frames, slot):
+        b, e = C.c_int64(0), C.c_int64(0)
+        self._lib.dpx_sequence_range(self._s, int(n_frames), int(slot), C.byref(b), C.byref(e))
+        return b.value, e.value
+
+    def process_host(self, xyz, layout, labels=None):
+        a = np.ascontiguousarray(xyz, dtype=np.float32)
+        f = a.size // (3 * self.n_points) if self.n_points else 0
+        assert a.size == f * 3 * self.n_points, "sequence does not hold a whole number of frames"
+        if labels is None:
+            labels = np.empty((f, self.n_points), dtype=np.int32)
+        self._check(self._lib.dpx_sequence_process_host(self._s, a.ctypes.data, f, layout, labels.ctypes.data))
+        return labels
+
+    def process_depth_host(self, depth, intrinsics, labels=None):
+        d = np.ascontiguousarray(depth, dtype=np.uint16)
+        f = d.size // self.n_points if self.n_points else 0
+        assert d.size == f * self.n_points, "sequence does not hold a whole number of frames"
+        if labels is None:
+            labels = np.empty((f, self.n_points), dtype=np.int32)
+        k = PlaneExtractor._intrinsics(intrinsics)
+        self._check(self._lib.dpx_sequence_process_depth_host(self._s, d.ctypes.data, f, C.byref(k), labels.ctypes.data))
+        return labels
+
+    def process_host_ptr(self, xyz_ptr, n_frames, layout, labels_ptr):
+        self._check(self._lib.dpx_sequence_process_host(self._s, xyz_ptr, int(n_frames), layout, labels_ptr))
+
+    def process_depth_host_ptr(self, depth_ptr, n_frames, intrinsics, labels_ptr):
+        k = PlaneExtractor._intrinsics(intrinsics)
+        self._check(self._lib.dpx_sequence_process_depth_host(self._s, depth_ptr, int(n_frames), C.byref(k), labels_ptr))
+
+    def close(self):
+        if getattr(self, "_s", None) and self._s.value:
+            self._lib.dpx_sequence_destroy(self._s)
+            self._s = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -121,8 +121,19 @@ py::array_t<float> transform_to_pcd(const DepthImage& self, py::array_t<float, p
   for (int i = 0; i < 9; ++i) k[i] = intrinsics.data()[i];
   std::vector<float> pts = self.toPointCloudRowMajor(k);
   const py::ssize_t n = static_cast<py::ssize_t>(self.getWidth()) * self.getHeight();
-  py::array_t<float> out = pinned_array<float>({n, static_cast<py::ssize_t>(3)});
-  std::copy(pts.begin(), pts.end(), out.mutable_data());
+  // The reference returns an Eigen::MatrixX3f (cpp/pybind/utils/utils.cpp:34), which pybind11 hands to numpy as a
+  // Fortran-ordered (N, 3) array: X[N] Y[N] Z[N] in memory.  Same here, so that arr.flags, ravel(order="K") and
+  // the column-major path of process() behave as with the reference.
+  py::array_t<float> flat = pinned_array<float>({static_cast<py::ssize_t>(3) * n});
+  float* dst = flat.mutable_data();
+  for (py::ssize_t i = 0; i < n; ++i) {
+    dst[i] = pts[3 * i];
+    dst[n + i] = pts[3 * i + 1];
+    dst[2 * n + i] = pts[3 * i + 2];
+  }
+  py::array_t<float> out(std::vector<py::ssize_t>{n, 3},
+                         std::vector<py::ssize_t>{static_cast<py::ssize_t>(sizeof(float)), static_cast<py::ssize_t>(sizeof(float)) * n},
+                         dst, flat);
   return out;
 }
 

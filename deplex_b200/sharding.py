@@ -39,34 +39,55 @@ def process_range(extractor, load_frames, begin, end, layout, max_batch):
     return out
 
 
-def gather_labels(local_labels, n_frames, dst=0, group=None):
-    """Gather every rank's (frames_of_rank, n_points) int32 label block to rank `dst`, in frame order.
-    Works on CPU tensors (gloo) and CUDA tensors (NCCL).  Returns the full (n_frames, n_points) tensor on `dst`,
-    None elsewhere.  This is the 'final gather' of the north star: 1.2 MB per VGA frame, off the hot path."""
+def process_range_device(pipeline, pool, pool_frames, begin, end, layout, max_batch, labels_out, stream):
+    """Device-resident counterpart of process_range for synthetic sequences: frame i of the sequence is frame
+    i % pool_frames of `pool`, a CUDA tensor holding the unique frames tiled to at least max_batch + pool_frames frames,
+    so that any batch of consecutive sequence frames is one contiguous slice of it.  Batches go through `pipeline`
+    (deplex_b200.PipelinedExtractor, i.e. the C-ABI dpx_pipeline) on `stream`; labels land in labels_out[i - begin].
+    Asynchronous: the caller joins the pipeline."""
+    n = pipeline.n_points
+    frame_bytes_in, frame_bytes_out = n * 3 * 4, n * 4
+    assert pool.shape[0] >= max_batch + pool_frames and labels_out.shape[0] >= end - begin
+    for b, e in batches(begin, end, max_batch):
+        pipeline.submit_ptr(pool.data_ptr() + (b % pool_frames) * frame_bytes_in, e - b, layout,
+                            labels_out.data_ptr() + (b - begin) * frame_bytes_out, stream.cuda_stream)
+
+
+def gather_labels(local_labels, n_frames, dst=0, group=None, out=None):
+    """Gather every rank's (frames_of_rank, n_points) label block to rank `dst`, in frame order: the 'final gather' of
+    the north star (1.2 MB per VGA frame, off the hot path).  Point-to-point, straight into the destination's slices --
+    no padding and no staging copy, so a 100 000-frame sequence needs only the result itself on `dst`.  Works on CPU
+    tensors (gloo) and CUDA tensors (NCCL over NVLink).  `out` (on dst): a preallocated (n_frames, n_points) tensor;
+    when dst's own block is already a view of its slice, nothing is copied for it.  Returns the full tensor on `dst`,
+    None elsewhere."""
     import torch
     import torch.distributed as dist
     t = local_labels if isinstance(local_labels, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(local_labels))
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        if out is not None and out.data_ptr() != t.data_ptr():
+            out[: t.shape[0]].copy_(t)
+            return out
         return t
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    n_points = t.shape[1]
     sizes = [frame_range(n_frames, r, world) for r in range(world)]
     assert t.shape[0] == sizes[rank][1] - sizes[rank][0], "local block does not match this rank's frame range"
-    # gather needs equal shapes: pad every block to the largest range
-    longest = max(e - b for b, e in sizes)
-    padded = torch.zeros((longest, n_points), dtype=t.dtype, device=t.device)
-    padded[: t.shape[0]] = t
-    if t.is_cuda:
-        # NCCL: all_gather into one buffer (gather is not universally supported), rank dst keeps the result
-        buf = torch.empty((world, longest, n_points), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(buf, padded, group=group)
-        blocks = list(buf) if rank == dst else None
-    else:
-        blocks = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
-        dist.gather(padded, blocks, dst=dst, group=group)
+    t = t.contiguous()
     if rank != dst:
+        if t.shape[0] > 0:
+            dist.send(t, dst=dst, group=group)
         return None
-    return torch.cat([blocks[r][: sizes[r][1] - sizes[r][0]] for r in range(world)], dim=0)
+    if out is None:
+        out = torch.empty((n_frames, t.shape[1]), dtype=t.dtype, device=t.device)
+    mine = out[sizes[rank][0]:sizes[rank][1]]
+    if mine.data_ptr() != t.data_ptr():
+        mine.copy_(t)
+    # frame-major rows: every rank's block is one contiguous slice of `out`, so it is received in place
+    ops = [dist.P2POp(dist.irecv, out[sizes[r][0]:sizes[r][1]], r, group=group)
+           for r in range(world) if r != dst and sizes[r][1] > sizes[r][0]]
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return out
 
 
 def bind_to_gpu_numa_node(device_index):

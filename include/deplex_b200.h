@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DPX_VERSION 100
+#define DPX_VERSION 200
 
 #if defined(__GNUC__)
 #define DPX_API __attribute__((visibility("default")))
@@ -167,6 +167,74 @@ DPX_API dpx_status dpx_get_stage_ms(dpx_extractor* ex, float ms[DPX_N_STAGES]);
 DPX_API dpx_status dpx_get_region_profile(dpx_extractor* ex, int32_t frame, int64_t out[DPX_REGION_PROFILE_SLOTS]);
 /* Number of kernels launched by this handle since creation. */
 DPX_API int64_t dpx_kernel_launches(const dpx_extractor* ex);
+
+/* ---- label transport of the host-pointer entry points ----
+ * The result is always int32 in the caller's buffer (Eigen::VectorXi, plane_extractor.h:48).  Labels never exceed
+ * plane_capacity <= 65535, so the batched host calls may bring them back over PCIe as uint16 (2 B/pixel instead of 4) and
+ * widen them into the caller's buffer with a few host threads while the next chunks are in flight.
+ * DPX_LABELS_AUTO (default): uint16 for multi-frame raw-depth batches, where the labels are most of the PCIe bytes;
+ * int32 otherwise.  Environment DPX_LABEL_TRANSPORT=i32|u16 sets the default of new handles. */
+enum { DPX_LABELS_AUTO = 0, DPX_LABELS_I32 = 1, DPX_LABELS_U16 = 2 };
+DPX_API dpx_status dpx_set_label_transport(dpx_extractor* ex, int32_t mode);
+
+/* ---- batches in flight on one GPU: replaces the caller's loop over process() ----
+ * (examples/process_sequence.cpp:30-43 calls process() frame after frame; here the unit is a device-resident batch.)
+ * A pipeline owns `lanes` extractors, each with its own device tables and CUDA stream, and deals the submitted batches
+ * to them round-robin: within one batch the HBM-bound cell-statistics kernel and the latency-bound region growing run
+ * back to back, and with several batches in flight the next batch's first kernel fills the SMs the previous batch's
+ * region growing has already left.  Results do not depend on `lanes`.
+ * submit: asynchronous; the lane first waits (on the device) for the work queued so far on `producer_stream`
+ *   (a cudaStream_t, NULL = legacy default stream), i.e. for whatever produced d_xyz.  n_frames <= max_batch.
+ * join: orders `consumer_stream` behind every batch submitted so far (device-side wait, no host synchronisation).
+ * synchronize: join + host wait. */
+typedef struct dpx_pipeline dpx_pipeline;
+DPX_API dpx_status dpx_pipeline_create(int32_t height, int32_t width, const dpx_config* cfg, int32_t device, int32_t max_batch,
+                                       int32_t lanes, dpx_pipeline** out);
+DPX_API void dpx_pipeline_destroy(dpx_pipeline* p);
+DPX_API const char* dpx_pipeline_last_error(const dpx_pipeline* p);
+DPX_API int32_t dpx_pipeline_lanes(const dpx_pipeline* p);
+/* lane's extractor, for dpx_get_info / dpx_get_planes / profiling; owned by the pipeline */
+DPX_API dpx_extractor* dpx_pipeline_lane(dpx_pipeline* p, int32_t lane);
+DPX_API dpx_status dpx_pipeline_submit_device(dpx_pipeline* p, const float* d_xyz, int32_t n_frames, dpx_layout layout,
+                                              int32_t* d_labels, void* producer_stream);
+DPX_API dpx_status dpx_pipeline_submit_depth_device(dpx_pipeline* p, const uint16_t* d_depth, int32_t n_frames,
+                                                    const dpx_intrinsics* k, int32_t* d_labels, void* producer_stream);
+DPX_API dpx_status dpx_pipeline_join(dpx_pipeline* p, void* consumer_stream);
+DPX_API dpx_status dpx_pipeline_synchronize(dpx_pipeline* p);
+DPX_API int64_t dpx_pipeline_kernel_launches(const dpx_pipeline* p);
+
+/* ---- a frame sequence sharded over the GPUs of one box: replaces the loop of examples/process_sequence.cpp:30-43 ----
+ * Frames are independent (process() keeps no state across calls, plane_extractor.cpp:281,428), so a sequence of
+ * n_frames host frames is split into contiguous ranges, one per device (device g of G gets frames
+ * [g*n/G, (g+1)*n/G), remainder to the first devices), and one worker thread per device runs the batched host entry
+ * point on its range.  No inter-GPU traffic at all: every device copies its labels into its slice of the caller's
+ * buffer.  n_devices <= 0 or devices == NULL: all visible devices.  Labels are identical to calling process() on
+ * every frame in order. */
+typedef struct dpx_sequence dpx_sequence;
+DPX_API dpx_status dpx_sequence_create(int32_t height, int32_t width, const dpx_config* cfg, const int32_t* devices,
+                                       int32_t n_devices, int32_t max_batch, dpx_sequence** out);
+DPX_API void dpx_sequence_destroy(dpx_sequence* s);
+DPX_API const char* dpx_sequence_last_error(const dpx_sequence* s);
+DPX_API int32_t dpx_sequence_devices(const dpx_sequence* s);
+/* [begin, end) of device slot `slot` for a sequence of n_frames */
+DPX_API void dpx_sequence_range(const dpx_sequence* s, int64_t n_frames, int32_t slot, int64_t* begin, int64_t* end);
+DPX_API dpx_status dpx_sequence_process_host(dpx_sequence* s, const float* xyz, int64_t n_frames, dpx_layout layout,
+                                             int32_t* labels);
+DPX_API dpx_status dpx_sequence_process_depth_host(dpx_sequence* s, const uint16_t* depth, int64_t n_frames,
+                                                   const dpx_intrinsics* k, int32_t* labels);
+/* Device-resident form, for measurements and for callers whose frames are produced on the GPUs: every device processes
+ * `n_frames_per_device` frames that are already in ITS memory (d_xyz[slot], d_labels[slot]: arrays of n_devices device
+ * pointers), max_batch frames per submit through a `lanes`-lane pipeline; returns when all devices are done.
+ * ms_per_device (optional, n_devices floats): CUDA-event time of each device's range. */
+DPX_API dpx_status dpx_sequence_process_device(dpx_sequence* s, const float* const* d_xyz, int64_t n_frames_per_device,
+                                               dpx_layout layout, int32_t* const* d_labels, int32_t lanes, float* ms_per_device);
+
+/* ---- device memory helpers for callers without the CUDA headers (cudaMalloc / cudaFree / cudaMemcpy) ---- */
+DPX_API int32_t dpx_device_count(void);
+DPX_API dpx_status dpx_device_alloc(int32_t device, void** ptr, size_t bytes);
+DPX_API void dpx_device_free(int32_t device, void* ptr);
+DPX_API dpx_status dpx_memcpy_to_device(int32_t device, void* dst, const void* src, size_t bytes);
+DPX_API dpx_status dpx_memcpy_to_host(int32_t device, void* dst, const void* src, size_t bytes);
 
 /* ---- pinned host memory helpers (cudaHostAlloc / cudaFreeHost) ---- */
 DPX_API dpx_status dpx_host_alloc(void** ptr, size_t bytes);

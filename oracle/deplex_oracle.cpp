@@ -253,6 +253,33 @@ bool eig3_hybrid(const Sym3& A, double Q[9], double w[3]) {
 // It answers one question: would the labels change if Eigen's real orders differed from the restatement?
 static int g_sum_variant = 0;
 
+// std::uniform_int_distribution<int>(0, n - 1)(gen) over std::mt19937 (RANSAC.hpp:107-111 draws its samples with it).
+// The C++ standard leaves the mapping to the implementation, and libstdc++ changed it:
+//   variant 0  libstdc++ >= 11 (bits/uniform_int_dist.h, _S_nd): Lemire's multiply-shift -- product = u * n (64 bit),
+//              low 32 bits below (2^32 - n) % n are rejected, result = product >> 32;
+//   variant 1  libstdc++ <= 10: scaling = (2^32 - 1) / n, draws >= n * scaling are rejected, result = u / scaling.
+// (The reference's own wheels are built in manylinux2014 images, .github/workflows/wheels.yml:10; which of the two those
+// binaries carry depends on that image's GCC.)  Refinement parity is defined against variant 0 unless switched.
+static int g_uniform_variant = 0;
+static int uniform_below(std::mt19937& gen, uint32_t n) {
+  if (g_uniform_variant == 1) {
+    const uint64_t scaling = 0xffffffffull / n, past = n * scaling;
+    uint64_t r;
+    do r = gen(); while (r >= past);
+    return static_cast<int>(r / scaling);
+  }
+  uint64_t product = static_cast<uint64_t>(static_cast<uint32_t>(gen())) * n;
+  uint32_t low = static_cast<uint32_t>(product);
+  if (low < n) {
+    const uint32_t threshold = (0u - n) % n;
+    while (low < threshold) {
+      product = static_cast<uint64_t>(static_cast<uint32_t>(gen())) * n;
+      low = static_cast<uint32_t>(product);
+    }
+  }
+  return static_cast<int>(product >> 32);
+}
+
 float eigen_sum_f32(const float* p, long n, long s) {
   if (g_sum_variant == 1) {
     float r = p[0];
@@ -738,7 +765,9 @@ void Extractor::process(const float* xyz, int64_t n_points, int layout, int32_t*
     }
 
   // refineLabels (plane_extractor.cpp:472-509) + RTL::PlaneRANSAC (libs/rtl/include/rtl/RANSAC.hpp:25-111)
-  // + PlaneEstimator (Plane.hpp:13-49).  Uses this host's libstdc++ <random>, as the reference does.
+  // + PlaneEstimator (Plane.hpp:13-49).  std::mt19937 is fully specified by the standard; the mapping of its outputs
+  // to [0, n) by std::uniform_int_distribution<int> is NOT -- it is restated explicitly in uniform_below() for both
+  // libstdc++ generations instead of inheriting whatever this build host ships.
   if (cfg.ransac_refinement) {
     auto px = [&](long i, int a) -> float {
       return layout == DPXO_LAYOUT_COLMAJOR ? xyz[a * NP + i] : xyz[3 * i + a];
@@ -757,7 +786,6 @@ void Extractor::process(const float* xyz, int64_t n_points, int layout, int32_t*
       if (pts.empty()) continue;
       const int n = static_cast<int>(pts.size());
       float best[4] = {0, 0, 0, 0};
-      std::uniform_int_distribution<int> uni(0, n - 1);
       double bestloss = HUGE_VAL;
       int iteration = 0;
       for (;;) {
@@ -766,7 +794,7 @@ void Extractor::process(const float* xyz, int64_t n_points, int layout, int32_t*
         if (!(iteration < max_iter && inl < ratio * n)) break;
         ++iteration;
         std::set<int> smp;
-        while (static_cast<int>(smp.size()) < 3) smp.insert(uni(gen));
+        while (static_cast<int>(smp.size()) < 3) smp.insert(uniform_below(gen, static_cast<uint32_t>(n)));
         auto it = smp.begin();
         const long i0 = pts[*it++], i1 = pts[*it++], i2 = pts[*it++];
         const float x0 = px(i0, 0), x1 = px(i1, 0), x2 = px(i2, 0);
@@ -925,6 +953,19 @@ int dpxo_process_batch(int32_t h, int32_t w, const dpxo_config* cfg, const float
   return 0;
 }
 
+int dpxo_uniform_selftest(uint32_t n, int draws) {
+  // variant 0 against this build host's own std::uniform_int_distribution<int> (libstdc++ >= 11 here)
+  std::mt19937 a, b;
+  std::uniform_int_distribution<int> uni(0, static_cast<int>(n) - 1);
+  const int keep = g_uniform_variant;
+  g_uniform_variant = 0;
+  int bad = 0;
+  for (int i = 0; i < draws; ++i) bad += uni(a) != uniform_below(b, n);
+  g_uniform_variant = keep;
+  return bad + (a() != b());  // and both generators consumed the same number of outputs
+}
+void dpxo_set_uniform_int_variant(int v) { g_uniform_variant = v == 1 ? 1 : 0; }
+int dpxo_uniform_below(void* mt19937, uint32_t n) { return uniform_below(*static_cast<std::mt19937*>(mt19937), n); }
 void dpxo_set_sum_variant(int v) { g_sum_variant = (v == 1 || v == 2) ? v : 0; }
 
 int dpxo_eig3(const double* A, double* Q, double* w) {

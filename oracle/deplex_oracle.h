@@ -90,6 +90,14 @@ int dpxo_process_batch(int32_t h, int32_t w, const dpxo_config* cfg, const float
  * left-to-right fp32, 2 = fp64 accumulation rounded once.  Process-global; parity is always judged against 0. */
 void dpxo_set_sum_variant(int variant);
 
+/* Which libstdc++ generation's std::uniform_int_distribution<int> the RANSAC refinement draws with: 0 = GCC >= 11
+ * (Lemire multiply-shift, default), 1 = GCC <= 10 (scaling + rejection).  Process-global.
+ * dpxo_uniform_below draws one value in [0, n) from a caller-owned std::mt19937 (tests pin it to <random>). */
+void dpxo_set_uniform_int_variant(int variant);
+int dpxo_uniform_below(void* mt19937, uint32_t n);
+/* mismatches between variant 0 and this build host's std::uniform_int_distribution<int>(0, n-1) over `draws` draws */
+int dpxo_uniform_selftest(uint32_t n, int draws);
+
 /* The oracle's own restatement of Kopp's hybrid 3x3 symmetric eigensolver (row-major 3x3 in/out).
  * Returns 1 if the QL branch was taken, else 0. */
 int dpxo_eig3(const double* A, double* Q, double* w);

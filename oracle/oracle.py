@@ -70,6 +70,72 @@ def ref_dsyev_path():
     return os.path.join(_HERE, "_ref", "libdsyev_ref.so")
 
 
+def ref_full_path():
+    """oracle/_ref/libdeplex_ref.so: the UNMODIFIED reference hot path behind oracle/ref_full_shim.cpp.  Exists only
+    after `make -C oracle ref_full EIGEN3_INCLUDE_DIR=...` found an Eigen >= 3.4 tree (absent from this image)."""
+    return os.path.join(_HERE, "_ref", "libdeplex_ref.so")
+
+
+_ref_full = None
+
+
+def _load_ref_full():
+    global _ref_full
+    if _ref_full is None:
+        lib = C.CDLL(ref_full_path())
+        lib.ref_process.argtypes = [C.c_int32, C.c_int32, C.POINTER(OracleConfig), C.c_void_p, C.c_int64, C.c_void_p,
+                                    C.c_char_p, C.c_int]
+        lib.ref_cell_stats.argtypes = [C.c_int32, C.c_int32, C.POINTER(OracleConfig)] + [C.c_void_p] * 8 + [C.c_char_p, C.c_int]
+        lib.ref_eigen_version.restype = C.c_char_p
+        _ref_full = lib
+    return _ref_full
+
+
+def ref_available():
+    return os.path.exists(ref_full_path())
+
+
+def ref_process(height, width, cfg, xyz):
+    """deplex::PlaneExtractor(height, width, cfg).process(xyz) on the reference's own build.  xyz: (N,3) float32 in
+    either order (converted to Eigen's column-major)."""
+    lib = _load_ref_full()
+    a = np.asfortranarray(np.asarray(xyz, dtype=np.float32))
+    labels = np.empty(max(a.shape[0], 1), dtype=np.int32)
+    err = C.create_string_buffer(512)
+    rc = lib.ref_process(height, width, C.byref(cfg), a.ctypes.data if a.size else None, a.shape[0], labels.ctypes.data, err, 512)
+    if rc:
+        raise OracleError(rc, err.value.decode())
+    return labels[: a.shape[0]]
+
+
+def ref_cell_stats(height, width, cfg, xyz):
+    """Per-cell coord_sum_, variance_, normal, mse, score, d, planar of the reference's own CellGrid for one frame."""
+    lib = _load_ref_full()
+    a = np.asfortranarray(np.asarray(xyz, dtype=np.float32))
+    p = max(cfg.patch_size, 1)
+    nc = max((width // p) * (height // p), 1)
+    out = {"cell_sum": np.zeros((nc, 3), np.float32), "cell_var": np.zeros((nc, 9), np.float32),
+           "cell_normal": np.zeros((nc, 3), np.float32), "cell_mse": np.zeros(nc, np.float32),
+           "cell_score": np.zeros(nc, np.float32), "cell_d": np.zeros(nc, np.float32), "cell_planar": np.zeros(nc, np.uint8)}
+    err = C.create_string_buffer(512)
+    rc = lib.ref_cell_stats(height, width, C.byref(cfg), a.ctypes.data, *[out[k].ctypes.data for k in
+                            ("cell_sum", "cell_var", "cell_normal", "cell_mse", "cell_score", "cell_d", "cell_planar")], err, 512)
+    if rc:
+        raise OracleError(rc, err.value.decode())
+    return out
+
+
+def ref_process_batch(height, width, cfg, xyz_batch, layout, n_threads=1):
+    """Frame-parallel run of the reference build (one PlaneExtractor per call; ctypes drops the GIL): the CPU baseline
+    of bench.py when oracle/_ref/libdeplex_ref.so exists (cpu_baseline.kind = "reference")."""
+    from concurrent.futures import ThreadPoolExecutor
+    f = xyz_batch.shape[0]
+    n = height * width
+    frames = [xyz_batch[i].reshape(n, 3) if layout == LAYOUT_ROWMAJOR else xyz_batch[i].reshape(3, n).T for i in range(f)]
+    with ThreadPoolExecutor(max(1, n_threads)) as pool:
+        return np.stack(list(pool.map(lambda x: ref_process(height, width, cfg, x), frames)))
+
+
 def _load():
     global _lib
     if _lib is None:
@@ -85,6 +151,9 @@ def _load():
         lib.dpxo_eig3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.dpxo_set_sum_variant.argtypes = [C.c_int]
         lib.dpxo_set_sum_variant.restype = None
+        lib.dpxo_set_uniform_int_variant.argtypes = [C.c_int]
+        lib.dpxo_set_uniform_int_variant.restype = None
+        lib.dpxo_uniform_selftest.argtypes = [C.c_uint32, C.c_int]
         lib.dpxo_depth_to_cloud.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float,
                                             C.c_float, C.c_void_p]
         _lib = lib
@@ -95,6 +164,17 @@ def set_sum_variant(variant):
     """0 = the restated Eigen 3.4 reduction orders (default, what parity is judged against); 1 = plain left-to-right
     fp32; 2 = fp64 accumulation rounded once.  Process-global; only tools/order_sensitivity.py changes it."""
     _load().dpxo_set_sum_variant(int(variant))
+
+
+def set_uniform_int_variant(variant):
+    """Which libstdc++ generation's std::uniform_int_distribution<int> the RANSAC refinement draws with: 0 = GCC >= 11
+    (Lemire multiply-shift, default), 1 = GCC <= 10 (scaling + rejection).  Process-global."""
+    _load().dpxo_set_uniform_int_variant(int(variant))
+
+
+def uniform_selftest(n, draws):
+    """Mismatches between the explicit variant-0 mapping and this host's std::uniform_int_distribution<int>(0, n-1)."""
+    return int(_load().dpxo_uniform_selftest(int(n), int(draws)))
 
 
 def load_ini(path):
@@ -183,9 +263,26 @@ def process(height, width, cfg, xyz, debug=False):
     return labels
 
 
-def process_batch(height, width, cfg, xyz_batch, layout, n_threads=1):
-    """Frame-parallel CPU baseline: xyz_batch is (F, N, 3) row-major or (F, 3, N) column-major float32."""
-    lib = _load()
+_lib_o3 = None
+
+
+def _load_o3():
+    """The -O3 -DNDEBUG build of the same source (CMake Release flags): what bench.py times."""
+    global _lib_o3
+    if _lib_o3 is None:
+        path = os.path.join(_HERE, "libdeplex_oracle_o3.so")
+        if not os.path.exists(path):
+            build(force=True)
+        lib = C.CDLL(path)
+        lib.dpxo_process_batch.argtypes = _load().dpxo_process_batch.argtypes
+        _lib_o3 = lib
+    return _lib_o3
+
+
+def process_batch(height, width, cfg, xyz_batch, layout, n_threads=1, timed_build=False):
+    """Frame-parallel CPU baseline: xyz_batch is (F, N, 3) row-major or (F, 3, N) column-major float32.
+    timed_build=True runs the -O3 -DNDEBUG build (identical labels, tests/test_oracle_cpu.py)."""
+    lib = _load_o3() if timed_build else _load()
     xyz_batch = np.ascontiguousarray(xyz_batch, dtype=np.float32)
     f = xyz_batch.shape[0]
     n = height * width

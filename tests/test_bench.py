@@ -33,7 +33,7 @@ import pytest  # noqa: E402
 @pytest.mark.gpu
 def test_gpu_arm_prints_the_contract_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "5", "--warmup", "3", "--frames", "16",
-                        "--unique", "4", "--cpu-sample-frames", "4"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+                        "--unique", "4", "--cpu-sample-frames", "4", "--seq-frames", "1000", "--latency-calls", "40"], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -47,5 +47,23 @@ def test_gpu_arm_prints_the_contract_line():
     e2e = line["e2e"]
     assert e2e["h2d_bytes_per_step"] == 16 * 480 * 640 * 12 and e2e["d2h_bytes_per_step"] == 16 * 480 * 640 * 4
     assert e2e["matches_device_path"] is True and line["e2e_depth16"]["matches_point_path"] is True
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1
-    assert line["latency"]["tum"]["planes"] == 34
+    assert 0 < e2e["frac_of_pcie_ceiling"] < 1.5 and e2e["pcie_ceiling"]["h2d_gbs"] > 1
+    assert line["e2e_depth16"]["d2h_bytes_per_step"] == 16 * 480 * 640 * 2  # labels cross PCIe as uint16
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] == 1
+    # configs[0] / configs[1]: latency with the CPU path and a roofline beside it
+    for name, planes in (("tum", 34), ("icl", None)):
+        lat = line["latency"][name]
+        assert lat["cpu_baseline"]["cores"] == 1 and lat["cpu_baseline"]["value"] > 0
+        assert set(lat["roofline"]["stages"]) == {"cell_stats", "region_grow", "labeling"}
+        assert lat["host_ptr_us"]["min"] <= lat["host_ptr_us"]["mean"] <= lat["host_ptr_us"]["max"]
+        if planes:
+            assert lat["planes"] == planes
+    # configs[3]: 1920x1080 at patch 10, 8 and 5 (82 944 cells)
+    fhd = line["fhd_stress"]
+    assert fhd["patch5"]["cells"] == 82944 and fhd["patch10"]["cells"] == 20736
+    for rec in fhd.values():
+        assert rec["e2e"]["matches_device_path"] is True and rec["cpu_baseline"]["value"] > 0
+        assert rec["roofline"]["stages"]["cell_stats"]["frac"] > 0
+    # configs[4]: the sharded sequence (shortened here), verified frame by frame inside the bench
+    seq = line["sharded_sequence"]
+    assert seq["frames"] == 1000 and seq["frames_with_wrong_labels"] == 0 and seq["checksum"] > 0

@@ -61,6 +61,8 @@ def test_depth_image_png16_and_backprojection(deplex_mod, tmp_path):
         K = np.array([[k["fx"], 0, k["cx"]], [0, k["fy"], k["cy"]], [0, 0, 1]])
         pts = img.transform_to_pcd(K)
         assert pts.shape == (480 * 640, 3) and pts.dtype == np.float32
+        # Eigen::MatrixX3f comes back Fortran-ordered from the reference's module (cpp/pybind/utils/utils.cpp:34)
+        assert pts.flags.f_contiguous and not pts.flags.c_contiguous
         assert np.array_equal(pts[:, 2], depth.reshape(-1).astype(np.float32))
         want = synth.depth_to_cloud(depth, k, "rowmajor")
         assert np.array_equal(pts.view(np.uint32), want.view(np.uint32))
@@ -83,11 +85,69 @@ def test_depth_image_other_png_flavours(deplex_mod, tmp_path):
     z = img.transform_to_pcd(np.eye(3))[:, 2].reshape(21, 34)
     r, g, b = (rgb16[:, :, i].astype(np.uint32) for i in range(3))
     assert np.array_equal(z, ((r * 77 + g * 150 + b * 29) >> 8).astype(np.float32))
+    # 8-bit colour: stb reduces to luma on the 8-bit samples first, then widens by 257 (r=1,g=0,b=0 -> 0, not 77)
+    rgb8 = rng.integers(0, 256, (19, 31, 3), dtype=np.uint8)
+    rgb8[0, 0] = (1, 0, 0)
+    cv2.imwrite(str(tmp_path / "rgb8.png"), rgb8[:, :, ::-1])
+    img.reset(str(tmp_path / "rgb8.png"))
+    z = img.transform_to_pcd(np.eye(3))[:, 2].reshape(19, 31)
+    r, g, b = (rgb8[:, :, i].astype(np.uint32) for i in range(3))
+    assert np.array_equal(z, (((r * 77 + g * 150 + b * 29) >> 8) * 257).astype(np.float32)) and z[0, 0] == 0
     # invalid / empty files throw (cpp/tests/test_depth_image.cpp:30-40)
     (tmp_path / "empty.png").write_bytes(b"")
     for bad in ("empty.png", "missing.png"):
         with pytest.raises(RuntimeError, match="Error: Couldn't read image"):
             deplex_mod.utils.DepthImage(str(tmp_path / bad))
+
+
+def test_png_reader_matches_reference_stb_image(deplex_mod, tmp_path):
+    """Differential test against the reference's own decoder: oracle/_ref/libstb_ref.so is the vendored stb_image.h
+    compiled where it lies (oracle/Makefile), called exactly like depth_image.cpp:32 (stbi_load_16, STBI_grey)."""
+    import ctypes as C
+    Image = pytest.importorskip("PIL.Image")
+    so = os.path.join(ROOT, "oracle", "_ref", "libstb_ref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libstb_ref.so not built (reference tree not mounted)")
+    stb = C.CDLL(so)
+    stb.stb_ref_load16_grey.argtypes = [C.c_char_p, C.c_void_p, C.c_long, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    rng = np.random.default_rng(11)
+    h, w = 23, 37
+    files = {}
+    files["grey8"] = Image.fromarray(rng.integers(0, 256, (h, w), dtype=np.uint8), "L")
+    files["grey16"] = Image.fromarray(rng.integers(0, 65536, (h, w), dtype=np.uint16))
+    files["rgb8"] = Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8), "RGB")
+    files["rgba8"] = Image.fromarray(rng.integers(0, 256, (h, w, 4), dtype=np.uint8), "RGBA")
+    files["la8"] = Image.fromarray(rng.integers(0, 256, (h, w, 2), dtype=np.uint8), "LA")
+    files["bilevel"] = Image.fromarray(rng.integers(0, 2, (h, w), dtype=np.uint8) * 255, "L").convert("1")
+    pal = Image.fromarray(rng.integers(0, 256, (h, w), dtype=np.uint8), "P")
+    pal.putpalette([int(v) for v in rng.integers(0, 256, 768)])
+    files["palette8"] = pal
+    pal4 = Image.fromarray(rng.integers(0, 16, (h, w), dtype=np.uint8), "P")
+    pal4.putpalette([int(v) for v in rng.integers(0, 256, 48)])
+    files["palette4"] = pal4
+    checked = 0
+    for name, im in files.items():
+        path = str(tmp_path / f"{name}.png")
+        im.save(path, bits=4) if name == "palette4" else im.save(path)
+        ref = np.zeros(h * w, dtype=np.uint16)
+        rw, rh = C.c_int(0), C.c_int(0)
+        assert stb.stb_ref_load16_grey(path.encode(), ref.ctypes.data, ref.size, C.byref(rw), C.byref(rh)) == 1, name
+        img = deplex_mod.utils.DepthImage(path)
+        assert (img.height, img.width) == (rh.value, rw.value) == (h, w), name
+        z = np.asarray(img.transform_to_pcd(np.eye(3)))[:, 2]
+        assert np.array_equal(z, ref.astype(np.float32)), name
+        checked += 1
+    # the shipped frames as 16-bit grey: the format deplex is actually used with
+    cv2 = pytest.importorskip("cv2")
+    for name in ("tum", "icl"):
+        depth, _, _ = load_frame(name)
+        path = str(tmp_path / f"{name}.png")
+        cv2.imwrite(path, depth)
+        ref = np.zeros(depth.size, dtype=np.uint16)
+        rw, rh = C.c_int(0), C.c_int(0)
+        assert stb.stb_ref_load16_grey(path.encode(), ref.ctypes.data, ref.size, C.byref(rw), C.byref(rh)) == 1
+        assert np.array_equal(ref.reshape(depth.shape), depth)
+    assert checked == len(files)
 
 
 def test_no_cpu_fallback_through_the_bindings(deplex_mod):

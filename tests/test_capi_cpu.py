@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol(lib_built):
     lib = C.CDLL(lib_built)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _capi.load().dpx_version() == 100
+    assert _capi.load().dpx_version() == 200
 
 
 def test_struct_layouts_match_header(lib_built):

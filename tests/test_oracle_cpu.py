@@ -213,3 +213,67 @@ def test_synthetic_determinism():
     cm = synth.make_cloud(120, 160, 1, "colmajor")
     rm = synth.make_cloud(120, 160, 1, "rowmajor")
     assert cm.shape == (3, 120 * 160) and np.array_equal(cm.T, rm)
+
+
+def test_oracle_matches_reference_build(oracle_mod):
+    """The pin VERDICT r01 asked for: when oracle/_ref/libdeplex_ref.so exists (the UNMODIFIED reference sources built by
+    `make -C oracle ref_full EIGEN3_INCLUDE_DIR=...`, oracle/ref_full_shim.cpp), the oracle must reproduce its labels and
+    the raw coord_sum_ / variance_ bits of every cell -- the three Eigen reductions (cell_segment_stat.cpp:29-35,56,74)
+    that could only be restated, never run, in an image without Eigen.  Skipped, not passed, until such a build exists."""
+    if not oracle_mod.ref_available():
+        pytest.skip("oracle/_ref/libdeplex_ref.so not built: no Eigen >= 3.4 tree in this image "
+                    "(external/eigen3/CMakeLists.txt:1-16 fetches it from the network)")
+    from deplex_b200 import synth
+    cases = []
+    for name in ("tum", "icl"):
+        xyz, ini = frame_cloud(name)
+        cases.append((name, 480, 640, oracle_mod.load_ini(ini), xyz))
+    for i in range(32):
+        h, w, patch = [(480, 640, 10), (480, 640, 4), (720, 1280, 8), (480, 640, 6)][i % 4]
+        cases.append((f"synth{i}", h, w, oracle_mod.OracleConfig(patch_size=patch), synth.make_cloud(h, w, 7000 + i)))
+    for name, h, w, cfg, xyz in cases:
+        labels, dbg = oracle_mod.process(h, w, cfg, xyz, debug=True)
+        ref = oracle_mod.ref_process(h, w, cfg, xyz)
+        assert np.array_equal(labels, ref), f"{name}: {(labels != ref).sum()} labels differ from the reference build"
+        st = oracle_mod.ref_cell_stats(h, w, cfg, xyz)
+        valid = dbg["cell_valid"].astype(bool)
+        assert np.array_equal(st["cell_planar"].astype(bool), dbg["cell_planar"].astype(bool)), name
+        for key in ("cell_sum", "cell_var", "cell_mse", "cell_score", "cell_d", "cell_normal"):
+            a = np.ascontiguousarray(st[key][valid]).view(np.uint32)
+            b = np.ascontiguousarray(dbg[key][valid]).view(np.uint32)
+            assert np.array_equal(a, b), f"{name}: {key} differs in {(a != b).any(axis=-1).sum() if a.ndim > 1 else (a != b).sum()} cells"
+
+
+def test_release_build_of_the_oracle_gives_identical_labels(oracle_mod):
+    """bench.py times the -O3 -DNDEBUG build (CMake Release); parity is judged on the -O2 one.
+    Both keep contraction off and use no -march, so they must agree bit for bit."""
+    from deplex_b200 import synth
+    cfg = oracle_mod.OracleConfig()
+    batch = synth.make_batch(480, 640, 31000, 4, "rowmajor")
+    a = oracle_mod.process_batch(480, 640, cfg, batch, 1, 2)
+    b = oracle_mod.process_batch(480, 640, cfg, batch, 1, 2, timed_build=True)
+    assert np.array_equal(a, b)
+    xyz, ini = frame_cloud("icl")
+    cfg = oracle_mod.load_ini(ini)
+    a = oracle_mod.process_batch(480, 640, cfg, xyz[None], 1, 1)
+    b = oracle_mod.process_batch(480, 640, cfg, xyz[None], 1, 1, timed_build=True)
+    assert np.array_equal(a, b)
+
+
+def test_uniform_int_mapping_is_explicit_and_pinned(oracle_mod):
+    """std::uniform_int_distribution is implementation-defined; the oracle restates both libstdc++ generations
+    explicitly.  Variant 0 (GCC >= 11) is pinned against this host's <random>; variant 1 (GCC <= 10)
+    is a different stream, and refinement labels depend on the choice."""
+    for n in (3, 7, 100, 4097, 307200, (1 << 31) - 1):
+        assert oracle_mod.uniform_selftest(n, 20000) == 0, n
+    xyz, ini = frame_cloud("tum")
+    cfg = oracle_mod.load_ini(ini)
+    cfg.ransac_refinement = 1
+    try:
+        a = oracle_mod.process(480, 640, cfg, xyz)
+        oracle_mod.set_uniform_int_variant(1)
+        b = oracle_mod.process(480, 640, cfg, xyz)
+    finally:
+        oracle_mod.set_uniform_int_variant(0)
+    assert np.array_equal(a, oracle_mod.process(480, 640, cfg, xyz))
+    assert a.max() == b.max() and (a != b).any()  # same planes, different sampled triples
