@@ -627,8 +627,7 @@ def run_ours(a):
         ceil = pcie_ceiling(dev, a.frames, n_px * 12, n_px * 4, 16, k_e2e, barrier, all_reduce_max, world)
         e2e["pcie_ceiling"] = ceil
         e2e["frac_of_pcie_ceiling"] = e2e["value"] / ceil["frames_per_s"]
-        # the same workload entering as raw uint16 depth (toPointCloud fused on the device); labels
-        # return as uint16 over PCIe and are widened into the int32 result by host threads (dpx_set_label_transport)
+        # the same workload entering as raw uint16 depth (toPointCloud fused on the device)
         pin_depth = torch.from_numpy(depth_np.view(np.int16)).pin_memory()
         pin_out2 = torch.empty_like(pin_out).pin_memory()
         for _ in range(2):
@@ -642,13 +641,30 @@ def run_ours(a):
         if not torch.equal(pin_out2, pin_out):
             raise RuntimeError("e2e_depth16: the raw-depth path and the point path disagree")
         e2e_depth = {"value": world * k_e2e * a.frames / dt, "unit": UNIT,
-                     "h2d_bytes_per_step": int(a.frames * n_px * 2), "d2h_bytes_per_step": int(a.frames * n_px * 2),
-                     "api": "dpx_process_depth_batch_host (uint16 depth + intrinsics in; labels cross PCIe as uint16 and are "
-                            "widened into the caller's int32 buffer by host threads)",
+                     "h2d_bytes_per_step": int(a.frames * n_px * 2), "d2h_bytes_per_step": int(a.frames * n_px * 4),
+                     "api": "dpx_process_depth_batch_host (uint16 depth + intrinsics in, int32 labels out)",
                      "matches_point_path": True}
-        ceil = pcie_ceiling(dev, a.frames, n_px * 2, n_px * 2, 64, k_e2e, barrier, all_reduce_max, world)
+        ceil = pcie_ceiling(dev, a.frames, n_px * 2, n_px * 4, 34, k_e2e, barrier, all_reduce_max, world)
         e2e_depth["pcie_ceiling"] = ceil
         e2e_depth["frac_of_pcie_ceiling"] = e2e_depth["value"] / ceil["frames_per_s"]
+        # ... and with the labels taken as uint16 (dpx_process_depth_batch_host_u16): 2 + 2 B/pixel over PCIe
+        pin_out16 = torch.empty((a.frames, n_px), dtype=torch.int16).pin_memory()
+        for _ in range(2):
+            ex.process_depth_batch_host_ptr(pin_depth.data_ptr(), a.frames, intr, pin_out16.data_ptr(), labels_u16=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            ex.process_depth_batch_host_ptr(pin_depth.data_ptr(), a.frames, intr, pin_out16.data_ptr(), labels_u16=True)
+        torch.cuda.synchronize()
+        dt = all_reduce_max(time.perf_counter() - t0)
+        if not torch.equal(pin_out16.to(torch.int32), pin_out):  # labels < 32768 here, so the int16 view is the value
+            raise RuntimeError("e2e_depth16 (uint16 labels): differs from the int32 path")
+        ceil16 = pcie_ceiling(dev, a.frames, n_px * 2, n_px * 2, 34, k_e2e, barrier, all_reduce_max, world)
+        e2e_depth["labels_u16"] = {"value": world * k_e2e * a.frames / dt, "unit": UNIT,
+                                   "h2d_bytes_per_step": int(a.frames * n_px * 2), "d2h_bytes_per_step": int(a.frames * n_px * 2),
+                                   "api": "dpx_process_depth_batch_host_u16 (the caller takes uint16 labels: same values)",
+                                   "matches_int32_path": True, "pcie_ceiling": ceil16,
+                                   "frac_of_pcie_ceiling": world * k_e2e * a.frames / dt / ceil16["frames_per_s"]}
 
     # ---- configs[4]: the sharded 100k-frame sequence + final gather (all ranks) ------------------------------
     pipe.close()

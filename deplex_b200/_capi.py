@@ -16,7 +16,7 @@ EXPORTS = (
     "dpx_process_host", "dpx_process_batch_host", "dpx_process_batch_device", "dpx_process_depth_batch_host",
     "dpx_process_depth_batch_device", "dpx_get_cells", "dpx_get_planes",
     "dpx_set_profiling", "dpx_get_stage_ms", "dpx_get_region_profile", "dpx_kernel_launches", "dpx_host_alloc", "dpx_host_free", "dpx_version",
-    "dpx_set_label_transport",
+    "dpx_set_label_transport", "dpx_process_batch_host_u16", "dpx_process_depth_batch_host_u16",
     "dpx_pipeline_create", "dpx_pipeline_destroy", "dpx_pipeline_last_error", "dpx_pipeline_lanes", "dpx_pipeline_lane",
     "dpx_pipeline_submit_device", "dpx_pipeline_submit_depth_device", "dpx_pipeline_join", "dpx_pipeline_synchronize",
     "dpx_pipeline_kernel_launches",
@@ -101,6 +101,8 @@ def load():
         "dpx_host_free": (None, [vp]),
         "dpx_version": (i32, []),
         "dpx_set_label_transport": (C.c_int, [vp, i32]),
+        "dpx_process_batch_host_u16": (C.c_int, [vp, vp, i32, C.c_int, vp]),
+        "dpx_process_depth_batch_host_u16": (C.c_int, [vp, vp, i32, C.POINTER(dpx_intrinsics), vp]),
         "dpx_pipeline_create": (C.c_int, [i32, i32, C.POINTER(dpx_config), i32, i32, i32, C.POINTER(vp)]),
         "dpx_pipeline_destroy": (None, [vp]),
         "dpx_pipeline_last_error": (C.c_char_p, [vp]),

@@ -74,6 +74,7 @@ struct dpx_extractor {
   bool stage_valid = false;
   int64_t launches = 0;
   int last_frames = 0;
+  int last_first = 0;  // index, within the last call, of the first frame whose tables are still resident (host path: last chunk)
   std::string err;
 };
 
@@ -233,6 +234,7 @@ dpx_status run_stages(dpx_extractor* ex, const float* d_xyz, int n_frames, int l
     ex->stage_valid = true;
   }
   ex->last_frames = n_frames;
+  ex->last_first = 0;
   return DPX_OK;
 }
 
@@ -244,8 +246,8 @@ int env_int(const char* name, int fallback) {
 // Streams, events and chunk sizes of the host-pointer path (first host call only).
 dpx_status ensure_host_path(dpx_extractor* ex) {
   if (ex->s_run) return DPX_OK;
-  // A chunk is what one H2D copy moves: about 64 MB, so that the copy engine works in long transfers while the kernels of
-  // the previous chunk run (640x480: 16 frames of points, 64 frames of raw depth).  DPX_HOST_CHUNK overrides (A/B).
+  // A chunk is what one copy moves: about 64 MB, so that the copy engines work in long transfers while the kernels of
+  // the previous chunk run (640x480: 16 frames of points, 34 frames of raw depth).  DPX_HOST_CHUNK overrides (A/B).
   const size_t np = std::max<size_t>(1, static_cast<size_t>(ex->geom.n_points));
   const size_t target = 64u << 20;
   const int forced = env_int("DPX_HOST_CHUNK", 0);
@@ -254,7 +256,7 @@ dpx_status ensure_host_path(dpx_extractor* ex) {
     return std::max(1, std::min(ex->max_batch, c));
   };
   ex->host_chunk_xyz = sized(np * 3 * sizeof(float));
-  ex->host_chunk_depth = sized(np * sizeof(uint16_t));
+  ex->host_chunk_depth = sized(np * (sizeof(uint16_t) + sizeof(int32_t)));  // here the labels going back are the larger copy
   for (int i = 0; i < kHostSlots; ++i) {
     DPX_CUDA(ex, cudaEventCreateWithFlags(&ex->e_h2d[i], cudaEventDisableTiming));
     DPX_CUDA(ex, cudaEventCreateWithFlags(&ex->e_run[i], cudaEventDisableTiming));
@@ -267,7 +269,7 @@ dpx_status ensure_host_path(dpx_extractor* ex) {
 }
 
 // Device label staging for chunks of up to `chunk` frames (grown on demand: the depth path uses larger chunks).
-dpx_status ensure_label_staging(dpx_extractor* ex, int chunk, bool narrow) {
+dpx_status ensure_label_staging(dpx_extractor* ex, int chunk, bool narrow, bool widen) {
   const size_t np = static_cast<size_t>(ex->geom.n_points);
   if (chunk > ex->lab_chunk) {
     DPX_CUDA(ex, cudaDeviceSynchronize());
@@ -280,14 +282,14 @@ dpx_status ensure_label_staging(dpx_extractor* ex, int chunk, bool narrow) {
     }
     ex->lab_chunk = chunk;
   }
-  if (narrow && !ex->d_nar[0]) {
-    for (int i = 0; i < kHostSlots; ++i) {
+  if (narrow && !ex->d_nar[0])
+    for (int i = 0; i < kHostSlots; ++i)
       DPX_CUDA(ex, cudaMalloc(&ex->d_nar[i], std::max<size_t>(16, np * sizeof(uint16_t) * ex->lab_chunk)));
+  if (widen && !ex->h_nar[0])
+    for (int i = 0; i < kHostSlots; ++i)
       DPX_CUDA(ex, cudaHostAlloc(reinterpret_cast<void**>(&ex->h_nar[i]), std::max<size_t>(16, np * sizeof(uint16_t) * ex->lab_chunk),
                                  cudaHostAllocDefault));
-    }
-  }
-  if (narrow && !ex->pool) {
+  if (widen && !ex->pool) {
     // widening threads: DPX_HOST_THREADS, else the host's hardware threads shared among the visible GPUs, at most 8
     int n_dev = 1;
     cudaGetDeviceCount(&n_dev);
@@ -508,7 +510,7 @@ namespace {
 // label transport the labels come back as uint16 into pinned staging and are widened into `labels` by the host pool
 // while the following chunks are in flight.
 dpx_status process_host_impl(dpx_extractor* ex, const void* src, size_t bytes_per_frame, int32_t n_frames, int layout,
-                             const dpx_intrinsics* pin, int32_t* labels) {
+                             const dpx_intrinsics* pin, int32_t* labels, uint16_t* labels16 = nullptr) {
   DeviceGuard guard(ex->device);
   if (!guard.ok) return fail(ex, DPX_ERR_CUDA, "cudaSetDevice failed");
   dpx_status st = ensure_host_path(ex);
@@ -516,10 +518,10 @@ dpx_status process_host_impl(dpx_extractor* ex, const void* src, size_t bytes_pe
   const bool is_depth = layout == kLayoutDepth16;
   const size_t np = static_cast<size_t>(ex->geom.n_points);
   const int chunk = is_depth ? ex->host_chunk_depth : ex->host_chunk_xyz;
-  int transport = ex->label_transport;
-  if (transport == DPX_LABELS_AUTO) transport = (is_depth && n_frames > 1) ? DPX_LABELS_U16 : DPX_LABELS_I32;
-  const bool narrow = transport == DPX_LABELS_U16 && n_frames > 1;
-  st = ensure_label_staging(ex, chunk, narrow);
+  // labels16: the caller takes uint16 labels as they are (no widening, 2 B/pixel over PCIe and in host memory)
+  const bool out16 = labels16 != nullptr;
+  const bool narrow = !out16 && ex->label_transport == DPX_LABELS_U16 && n_frames > 1;
+  st = ensure_label_staging(ex, chunk, narrow || out16, narrow);
   if (st != DPX_OK) return st;
   if (is_depth && !ex->d_depth[0])
     for (int i = 0; i < kHostSlots; ++i) DPX_CUDA(ex, cudaMalloc(&ex->d_depth[i], std::max<size_t>(16, np * sizeof(uint16_t) * chunk)));
@@ -535,7 +537,13 @@ dpx_status process_host_impl(dpx_extractor* ex, const void* src, size_t bytes_pe
     DPX_CUDA(ex, cudaMemcpyAsync(d_in, src, bytes_per_frame, cudaMemcpyHostToDevice, ex->s_run));
     st = launch(0, 1);
     if (st != DPX_OK) return st;
-    DPX_CUDA(ex, cudaMemcpyAsync(labels, ex->d_lab[0], np * sizeof(int32_t), cudaMemcpyDeviceToHost, ex->s_run));
+    if (out16) {
+      DPX_CUDA(ex, launch_narrow_labels(ex->d_lab[0], ex->d_nar[0], static_cast<long long>(np), ex->s_run));
+      ++ex->launches;
+      DPX_CUDA(ex, cudaMemcpyAsync(labels16, ex->d_nar[0], np * sizeof(uint16_t), cudaMemcpyDeviceToHost, ex->s_run));
+    } else {
+      DPX_CUDA(ex, cudaMemcpyAsync(labels, ex->d_lab[0], np * sizeof(int32_t), cudaMemcpyDeviceToHost, ex->s_run));
+    }
     DPX_CUDA(ex, cudaStreamSynchronize(ex->s_run));
     return DPX_OK;
   }
@@ -564,7 +572,8 @@ dpx_status process_host_impl(dpx_extractor* ex, const void* src, size_t bytes_pe
     if (i >= kHostSlots) DPX_CUDA(ex, cudaStreamWaitEvent(ex->s_run, ex->e_d2h[slot], 0));
     st = launch(slot, nf);
     if (st != DPX_OK) return st;
-    if (narrow) {
+    ex->last_first = f0;
+    if (narrow || out16) {
       DPX_CUDA(ex, launch_narrow_labels(ex->d_lab[slot], ex->d_nar[slot], static_cast<long long>(np) * nf, ex->s_run));
       ++ex->launches;
     }
@@ -575,6 +584,9 @@ dpx_status process_host_impl(dpx_extractor* ex, const void* src, size_t bytes_pe
       ex->pool->wait(ex->widen_ticket[slot]);  // the staging buffer's previous contents have been widened
       ex->widen_ticket[slot] = 0;
       DPX_CUDA(ex, cudaMemcpyAsync(ex->h_nar[slot], ex->d_nar[slot], np * sizeof(uint16_t) * nf, cudaMemcpyDeviceToHost, ex->s_d2h));
+    } else if (out16) {
+      DPX_CUDA(ex, cudaMemcpyAsync(labels16 + static_cast<size_t>(f0) * np, ex->d_nar[slot], np * sizeof(uint16_t) * nf,
+                                   cudaMemcpyDeviceToHost, ex->s_d2h));
     } else {
       DPX_CUDA(ex, cudaMemcpyAsync(labels + static_cast<size_t>(f0) * np, ex->d_lab[slot], np * sizeof(int32_t) * nf,
                                    cudaMemcpyDeviceToHost, ex->s_d2h));
@@ -620,6 +632,24 @@ dpx_status dpx_process_depth_batch_host(dpx_extractor* ex, const uint16_t* depth
   return process_host_impl(ex, depth, static_cast<size_t>(ex->geom.n_points) * sizeof(uint16_t), n_frames, kLayoutDepth16, k, labels);
 }
 
+dpx_status dpx_process_batch_host_u16(dpx_extractor* ex, const float* xyz, int32_t n_frames, dpx_layout layout, uint16_t* labels) {
+  if (!ex) return DPX_ERR_ARGUMENT;
+  if (n_frames < 0) return fail(ex, DPX_ERR_ARGUMENT, "negative n_frames");
+  if (layout != DPX_LAYOUT_COLMAJOR && layout != DPX_LAYOUT_ROWMAJOR) return fail(ex, DPX_ERR_ARGUMENT, "unknown layout");
+  if (n_frames == 0 || ex->geom.n_points == 0) return DPX_OK;
+  if (!xyz || !labels) return fail(ex, DPX_ERR_ARGUMENT, "null host pointer");
+  return process_host_impl(ex, xyz, static_cast<size_t>(ex->geom.n_points) * 3 * sizeof(float), n_frames, layout, nullptr, nullptr, labels);
+}
+
+dpx_status dpx_process_depth_batch_host_u16(dpx_extractor* ex, const uint16_t* depth, int32_t n_frames, const dpx_intrinsics* k,
+                                            uint16_t* labels) {
+  if (!ex) return DPX_ERR_ARGUMENT;
+  if (n_frames < 0) return fail(ex, DPX_ERR_ARGUMENT, "negative n_frames");
+  if (n_frames == 0 || ex->geom.n_points == 0) return DPX_OK;
+  if (!depth || !labels || !k) return fail(ex, DPX_ERR_ARGUMENT, "null pointer");
+  return process_host_impl(ex, depth, static_cast<size_t>(ex->geom.n_points) * sizeof(uint16_t), n_frames, kLayoutDepth16, k, nullptr, labels);
+}
+
 dpx_status dpx_process_depth_batch_device(dpx_extractor* ex, const uint16_t* d_depth, int32_t n_frames, const dpx_intrinsics* k,
                                           int32_t* d_labels, void* cuda_stream) {
   if (!ex) return DPX_ERR_ARGUMENT;
@@ -642,10 +672,25 @@ dpx_status dpx_process_host(dpx_extractor* ex, const float* xyz, int64_t n_point
   return dpx_process_batch_host(ex, xyz, 1, layout, labels);
 }
 
+namespace {
+// Frame index within the last call -> index into the device tables.  The batched host entry points work through a call
+// in chunks, so only the frames of its last chunk are still resident afterwards.
+dpx_status resident_frame(dpx_extractor* ex, int32_t frame, int* table_index) {
+  const int rel = frame - ex->last_first;
+  if (frame < 0 || rel >= ex->last_frames) return fail(ex, DPX_ERR_ARGUMENT, "frame index outside the last batch");
+  if (rel < 0)
+    return fail(ex, DPX_ERR_ARGUMENT, "frame " + std::to_string(frame) + " of the last host call was processed in an earlier chunk: only frames [" +
+                                          std::to_string(ex->last_first) + ", " + std::to_string(ex->last_first + ex->last_frames) +
+                                          ") are still resident (use a device-resident call to inspect a whole batch)");
+  *table_index = rel;
+  return DPX_OK;
+}
+}  // namespace
+
 dpx_status dpx_get_cells(dpx_extractor* ex, int32_t frame, dpx_cell* out, int32_t capacity) {
   if (!ex || !out) return DPX_ERR_ARGUMENT;
   const int C = ex->geom.n_cells;
-  if (frame < 0 || frame >= ex->last_frames) return fail(ex, DPX_ERR_ARGUMENT, "frame index outside the last batch");
+  if (dpx_status rs = resident_frame(ex, frame, &frame); rs != DPX_OK) return rs;
   if (capacity < C) return fail(ex, DPX_ERR_ARGUMENT, "dpx_get_cells: capacity < n_cells");
   if (C == 0) return DPX_OK;
   DeviceGuard guard(ex->device);
@@ -683,7 +728,7 @@ dpx_status dpx_get_cells(dpx_extractor* ex, int32_t frame, dpx_cell* out, int32_
 dpx_status dpx_get_planes(dpx_extractor* ex, int32_t frame, dpx_plane* out, int32_t capacity, int32_t* n_planes) {
   if (!ex || !n_planes) return DPX_ERR_ARGUMENT;
   *n_planes = 0;
-  if (frame < 0 || frame >= ex->last_frames) return fail(ex, DPX_ERR_ARGUMENT, "frame index outside the last batch");
+  if (dpx_status rs = resident_frame(ex, frame, &frame); rs != DPX_OK) return rs;
   if (ex->geom.n_cells == 0) return DPX_OK;
   DeviceGuard guard(ex->device);
   DPX_CUDA(ex, cudaDeviceSynchronize());
@@ -731,7 +776,7 @@ dpx_status dpx_get_region_profile(dpx_extractor* ex, int32_t frame, int64_t out[
   if (!ex || !out) return DPX_ERR_ARGUMENT;
   static_assert(DPX_REGION_PROFILE_SLOTS == kRegionProfSlots, "header and kernel disagree");
   if (!ex->stage_valid) return fail(ex, DPX_ERR_ARGUMENT, "no profiled batch: call dpx_set_profiling(ex, 1) first");
-  if (frame < 0 || frame >= ex->last_frames) return fail(ex, DPX_ERR_ARGUMENT, "frame index outside the last batch");
+  if (dpx_status rs = resident_frame(ex, frame, &frame); rs != DPX_OK) return rs;
   DeviceGuard guard(ex->device);
   DPX_CUDA(ex, cudaDeviceSynchronize());
   DPX_CUDA(ex, cudaMemcpy(out, ex->region_prof + static_cast<size_t>(frame) * kRegionProfSlots,

@@ -4,7 +4,7 @@
 // into the caller's int32 buffer here, overlapped with the copies of the following chunks.  Pure host plumbing: no
 // arithmetic on labels other than the zero extension.
 #pragma once
-#include <emmintrin.h>
+#include <immintrin.h>
 
 #include <condition_variable>
 #include <cstdint>
@@ -15,10 +15,30 @@
 
 namespace dpx {
 
+// uint16 -> int32 with 256-bit loads / streaming stores (chosen at run time when the CPU has AVX2)
+__attribute__((target("avx2"))) inline size_t widen_u16_to_i32_avx2(const uint16_t* src, int32_t* dst, size_t n) {
+  size_t i = 0;
+  for (; i + 32 <= n; i += 32) {
+    const __m256i a = _mm256_cvtepu16_epi32(_mm_load_si128(reinterpret_cast<const __m128i*>(src + i)));
+    const __m256i b = _mm256_cvtepu16_epi32(_mm_load_si128(reinterpret_cast<const __m128i*>(src + i + 8)));
+    const __m256i c = _mm256_cvtepu16_epi32(_mm_load_si128(reinterpret_cast<const __m128i*>(src + i + 16)));
+    const __m256i d = _mm256_cvtepu16_epi32(_mm_load_si128(reinterpret_cast<const __m128i*>(src + i + 24)));
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), a);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 8), b);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 16), c);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 24), d);
+  }
+  _mm_sfence();
+  return i;
+}
+
 // uint16 -> int32, streaming stores when the destination allows (the widened labels are not read again here)
 inline void widen_u16_to_i32(const uint16_t* src, int32_t* dst, size_t n) {
   size_t i = 0;
-  if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+  static const bool has_avx2 = __builtin_cpu_supports("avx2");
+  if (has_avx2 && (reinterpret_cast<uintptr_t>(dst) & 31u) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0)
+    i = widen_u16_to_i32_avx2(src, dst, n);
+  if ((reinterpret_cast<uintptr_t>(dst + i) & 15u) == 0 && (reinterpret_cast<uintptr_t>(src + i) & 15u) == 0) {
     const __m128i zero = _mm_setzero_si128();
     for (; i + 8 <= n; i += 8) {
       const __m128i v = _mm_load_si128(reinterpret_cast<const __m128i*>(src + i));

@@ -195,9 +195,29 @@ class PlaneExtractor:
         self._check(self._lib.dpx_process_depth_batch_host(self._h, d.ctypes.data, f, C.byref(k), labels.ctypes.data))
         return labels
 
-    def process_depth_batch_host_ptr(self, depth_ptr, n_frames, intrinsics, labels_ptr):
+    def process_depth_batch_host_ptr(self, depth_ptr, n_frames, intrinsics, labels_ptr, labels_u16=False):
+        """Raw host pointers; labels_u16=True: labels_ptr receives uint16 labels (dpx_process_depth_batch_host_u16)."""
         k = self._intrinsics(intrinsics)
-        self._check(self._lib.dpx_process_depth_batch_host(self._h, depth_ptr, n_frames, C.byref(k), labels_ptr))
+        fn = self._lib.dpx_process_depth_batch_host_u16 if labels_u16 else self._lib.dpx_process_depth_batch_host
+        self._check(fn(self._h, depth_ptr, n_frames, C.byref(k), labels_ptr))
+
+    def process_batch_host_u16(self, xyz, layout):
+        """As process_batch_host, returning uint16 labels (same values; 2 B/pixel over PCIe and in host memory)."""
+        a = np.ascontiguousarray(xyz, dtype=np.float32)
+        f = a.size // (3 * self.n_points) if self.n_points else 0
+        assert a.size == f * 3 * self.n_points, "batch does not hold a whole number of frames"
+        labels = np.empty((f, self.n_points), dtype=np.uint16)
+        self._check(self._lib.dpx_process_batch_host_u16(self._h, a.ctypes.data, f, layout, labels.ctypes.data))
+        return labels
+
+    def process_depth_batch_host_u16(self, depth, intrinsics):
+        d = np.ascontiguousarray(depth, dtype=np.uint16)
+        f = d.size // self.n_points if self.n_points else 0
+        assert d.size == f * self.n_points, "batch does not hold a whole number of frames"
+        labels = np.empty((f, self.n_points), dtype=np.uint16)
+        k = self._intrinsics(intrinsics)
+        self._check(self._lib.dpx_process_depth_batch_host_u16(self._h, d.ctypes.data, f, C.byref(k), labels.ctypes.data))
+        return labels
 
     def process_depth_batch_device(self, depth, intrinsics, labels=None, stream=None):
         """depth: CUDA int16/uint16 tensor of F frames; asynchronous on `stream`."""

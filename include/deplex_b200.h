@@ -152,7 +152,10 @@ DPX_API dpx_status dpx_process_depth_batch_host(dpx_extractor* ex, const uint16_
 DPX_API dpx_status dpx_process_depth_batch_device(dpx_extractor* ex, const uint16_t* d_depth, int32_t n_frames,
                                           const dpx_intrinsics* k, int32_t* d_labels, void* cuda_stream);
 
-/* ---- introspection of the last batch (the reference computes these and discards them) ---- */
+/* ---- introspection of the last batch (the reference computes these and discards them) ----
+ * `frame` counts within the last process call.  The batched HOST entry points work through a call in chunks, so after
+ * them only the frames of the last chunk are still resident (others: DPX_ERR_ARGUMENT naming the resident range);
+ * a device-resident call keeps all of its frames. */
 DPX_API dpx_status dpx_get_cells(dpx_extractor* ex, int32_t frame, dpx_cell* out, int32_t capacity);
 DPX_API dpx_status dpx_get_planes(dpx_extractor* ex, int32_t frame, dpx_plane* out, int32_t capacity, int32_t* n_planes);
 
@@ -168,14 +171,24 @@ DPX_API dpx_status dpx_get_region_profile(dpx_extractor* ex, int32_t frame, int6
 /* Number of kernels launched by this handle since creation. */
 DPX_API int64_t dpx_kernel_launches(const dpx_extractor* ex);
 
-/* ---- label transport of the host-pointer entry points ----
- * The result is always int32 in the caller's buffer (Eigen::VectorXi, plane_extractor.h:48).  Labels never exceed
- * plane_capacity <= 65535, so the batched host calls may bring them back over PCIe as uint16 (2 B/pixel instead of 4) and
- * widen them into the caller's buffer with a few host threads while the next chunks are in flight.
- * DPX_LABELS_AUTO (default): uint16 for multi-frame raw-depth batches, where the labels are most of the PCIe bytes;
- * int32 otherwise.  Environment DPX_LABEL_TRANSPORT=i32|u16 sets the default of new handles. */
+/* ---- narrow labels on the host-pointer path ----
+ * The reference returns int32 labels (Eigen::VectorXi, plane_extractor.h:48) and so do the entry points above.  Labels
+ * never exceed plane_capacity <= 65535, and on the raw-depth path the int32 labels are two thirds of all PCIe bytes
+ * (4 of 6 B/pixel), so two narrower forms exist:
+ *  - dpx_process_*_host_u16: the caller takes the labels as uint16 (same values).  2 B/pixel over PCIe AND in host
+ *    memory: this is the form that lifts the ceiling (640x480 raw depth: ~76 k frames/s copy-bound instead of ~45 k).
+ *  - dpx_set_label_transport(ex, DPX_LABELS_U16): the int32 entry points bring the labels over PCIe as uint16 and widen
+ *    them into the caller's int32 buffer with a few host threads while the next chunks are in flight.  This halves the
+ *    D2H bytes but adds 6 B/pixel of host memory traffic, so it pays only where the PCIe link, not host memory bandwidth,
+ *    is the limit (measured on the B200 box: no gain, profiles/r02_e2e_probe.txt); off by default (DPX_LABELS_AUTO ==
+ *    DPX_LABELS_I32).  Environment DPX_LABEL_TRANSPORT=i32|u16 sets the default of new handles, DPX_HOST_THREADS the
+ *    number of widening threads. */
 enum { DPX_LABELS_AUTO = 0, DPX_LABELS_I32 = 1, DPX_LABELS_U16 = 2 };
 DPX_API dpx_status dpx_set_label_transport(dpx_extractor* ex, int32_t mode);
+DPX_API dpx_status dpx_process_batch_host_u16(dpx_extractor* ex, const float* xyz, int32_t n_frames, dpx_layout layout,
+                                              uint16_t* labels);
+DPX_API dpx_status dpx_process_depth_batch_host_u16(dpx_extractor* ex, const uint16_t* depth, int32_t n_frames,
+                                                    const dpx_intrinsics* k, uint16_t* labels);
 
 /* ---- batches in flight on one GPU: replaces the caller's loop over process() ----
  * (examples/process_sequence.cpp:30-43 calls process() frame after frame; here the unit is a device-resident batch.)

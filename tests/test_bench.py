@@ -48,7 +48,8 @@ def test_gpu_arm_prints_the_contract_line():
     assert e2e["h2d_bytes_per_step"] == 16 * 480 * 640 * 12 and e2e["d2h_bytes_per_step"] == 16 * 480 * 640 * 4
     assert e2e["matches_device_path"] is True and line["e2e_depth16"]["matches_point_path"] is True
     assert 0 < e2e["frac_of_pcie_ceiling"] < 1.5 and e2e["pcie_ceiling"]["h2d_gbs"] > 1
-    assert line["e2e_depth16"]["d2h_bytes_per_step"] == 16 * 480 * 640 * 2  # labels cross PCIe as uint16
+    assert line["e2e_depth16"]["d2h_bytes_per_step"] == 16 * 480 * 640 * 4
+    assert line["e2e_depth16"]["labels_u16"]["d2h_bytes_per_step"] == 16 * 480 * 640 * 2 and line["e2e_depth16"]["labels_u16"]["matches_int32_path"]
     assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] == 1
     # configs[0] / configs[1]: latency with the CPU path and a roofline beside it
     for name, planes in (("tum", 34), ("icl", None)):

@@ -141,6 +141,11 @@ def test_synthetic_scenes_match_oracle(oracle_mod, hw, patch, layout):
     ex = PlaneExtractor(h, w, cfg, max_batch=n_frames)
     lay = LAYOUT_ROWMAJOR if layout == "rowmajor" else LAYOUT_COLMAJOR
     labels = ex.process_batch_host(batch, lay)
+    # the host path works through the batch in chunks; the per-cell tables of all frames at once come from one
+    # device-resident call over the same frames (which must also give the same labels)
+    import torch
+    dev_labels = ex.process_batch_device(torch.from_numpy(np.ascontiguousarray(batch)).cuda(), lay).cpu().numpy()
+    assert np.array_equal(dev_labels, labels)
     total = mismatched = 0
     for f in range(n_frames):
         host = batch[f] if layout == "rowmajor" else np.asfortranarray(batch[f].T)
@@ -239,8 +244,10 @@ def test_depth_input_equals_point_input(oracle_mod, hw, patch):
     want = ex.process_batch_host(clouds, LAYOUT_ROWMAJOR)
     got = ex.process_depth_batch_host(depth, k)
     assert np.array_equal(got, want)
+    # per-cell tables through the device-resident calls (the host path works in chunks and keeps only its last one)
+    assert np.array_equal(ex.process_depth_batch_device(torch.from_numpy(depth.view(np.int16)).cuda(), k).cpu().numpy(), want)
     cells_depth = ex.cells(1)
-    ex.process_batch_host(clouds, LAYOUT_ROWMAJOR)
+    assert np.array_equal(ex.process_batch_device(torch.from_numpy(clouds).cuda(), LAYOUT_ROWMAJOR).cpu().numpy(), want)
     cells_pts = ex.cells(1)
     for name in ("sum", "var", "mean", "normal", "d", "mse", "bin"):
         assert np.array_equal(cells_depth[name], cells_pts[name], equal_nan=True), name

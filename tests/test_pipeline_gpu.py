@@ -43,6 +43,11 @@ def test_host_path_label_transport_matches_oracle(oracle_mod, transport, n_frame
     assert np.array_equal(got_depth, ref)
     # a second call reuses the staging buffers and the widening threads
     assert np.array_equal(ex.process_depth_batch_host(depth, k), ref)
+    # the uint16-output entry points: the same values, narrow
+    l16 = ex.process_depth_batch_host_u16(depth, k)
+    assert l16.dtype == np.uint16 and np.array_equal(l16, ref)
+    assert np.array_equal(ex.process_batch_host_u16(clouds, LAYOUT_ROWMAJOR), ref)
+    assert np.array_equal(ex.process_depth_batch_host_u16(depth[:1], k), ref[:1])
 
 
 def test_env_chunk_override_and_small_max_batch(oracle_mod, monkeypatch):
