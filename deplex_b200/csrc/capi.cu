@@ -62,6 +62,7 @@ struct dpx_extractor {
   int lab_chunk = 0;                   // frames d_lab[] / d_nar[] / h_nar[] are sized for
   // narrow label transport: labels cross PCIe as uint16 and are widened into the caller's int32 buffer by host threads
   int label_transport = DPX_LABELS_AUTO;
+  int uniform_variant = 0;    // std::uniform_int_distribution mapping of the refinement stage (dpx_set_rng_compat)
   uint16_t* d_nar[kHostSlots] = {};
   uint16_t* h_nar[kHostSlots] = {};    // pinned
   uint64_t widen_ticket[kHostSlots] = {};
@@ -130,6 +131,7 @@ size_t carve_tables(const Geometry& g, int max_batch, bool bins_in_smem, char* b
   tb->cell_label = reinterpret_cast<int32_t*>(take(F * C * sizeof(int32_t)));
   tb->queue = reinterpret_cast<int32_t*>(take(F * C * sizeof(int32_t)));
   tb->pairs = reinterpret_cast<uint32_t*>(take(F * C * 2 * sizeof(uint32_t)));
+  tb->skeys = reinterpret_cast<unsigned long long*>(take(F * C * sizeof(unsigned long long)));
   tb->bin_work = reinterpret_cast<int16_t*>(take(bins_in_smem ? 0 : F * C * sizeof(int16_t)));
   tb->cell_words = reinterpret_cast<uint32_t*>(take(F * C * sizeof(uint32_t)));
   tb->paint_state = reinterpret_cast<int32_t*>(take((F + 2) * sizeof(int32_t)));
@@ -198,7 +200,7 @@ dpx_status run_stages(dpx_extractor* ex, const float* d_xyz, int n_frames, int l
     ra.labels = ex->fuse_labeling ? d_labels : nullptr;
     ra.labels_vec_ok = labels_vec_ok(ex->geom, d_labels) ? 1 : 0;
     DPX_CUDA(ex, launch_region_grow(ra, st, &labels_painted));
-    ex->launches += 2;  // edge masks + region growing
+    ex->launches += region_grow_mode(ex->geom, ex->thr) >= 1 ? 3 : 2;  // edge masks (+ seed sort) + region growing
   }
   if (prof) DPX_CUDA(ex, cudaEventRecord(ex->e_stage[2], st));
   {
@@ -223,6 +225,7 @@ dpx_status run_stages(dpx_extractor* ex, const float* d_xyz, int n_frames, int l
     fa.threshold = ex->cfg.ransac_threshold;
     fa.inliers_ratio = ex->cfg.ransac_inliers_ratio;
     fa.mt_init = ex->mt_init;
+    fa.uniform_variant = ex->uniform_variant;
     fa.geom = ex->geom;
     fa.tables = ex->tb;
     fa.labels = d_labels;
@@ -421,6 +424,7 @@ dpx_status dpx_create(int32_t height, int32_t width, const dpx_config* cfg_in, i
     if (const char* e = std::getenv("DPX_STREAM_WARPS")) { const int w = std::atoi(e); ex->stream_warps = (w == 8 || w == 12) ? w : 16; }
     if (const char* e = std::getenv("DPX_CELL_KERNEL")) ex->force_tile_kernel = std::strcmp(e, "tile") == 0;
     if (const char* e = std::getenv("DPX_FUSE_LABELING")) ex->fuse_labeling = std::atoi(e) != 0;
+    if (const char* e = std::getenv("DPX_RNG_COMPAT")) ex->uniform_variant = std::strcmp(e, "libstdc++10") == 0 ? 1 : 0;
     if (const char* e = std::getenv("DPX_LABEL_TRANSPORT"))
       ex->label_transport = std::strcmp(e, "u16") == 0 ? DPX_LABELS_U16 : std::strcmp(e, "i32") == 0 ? DPX_LABELS_I32 : DPX_LABELS_AUTO;
     ex->plan = region_grow_plan(g, th);
@@ -756,6 +760,20 @@ dpx_status dpx_get_planes(dpx_extractor* ex, int32_t frame, dpx_plane* out, int3
   return DPX_OK;
 }
 
+dpx_status dpx_get_seed_order(dpx_extractor* ex, int32_t frame, uint64_t* out, int32_t capacity) {
+  if (!ex || !out) return DPX_ERR_ARGUMENT;
+  const int C = ex->geom.n_cells;
+  if (dpx_status rs = resident_frame(ex, frame, &frame); rs != DPX_OK) return rs;
+  if (capacity < C) return fail(ex, DPX_ERR_ARGUMENT, "dpx_get_seed_order: capacity < n_cells");
+  if (C == 0) return DPX_OK;
+  if (region_grow_mode(ex->geom, ex->thr) < 1)
+    return fail(ex, DPX_ERR_UNSUPPORTED, "frames this small (or histograms this large) are grown without a sorted seed order");
+  DeviceGuard guard(ex->device);
+  DPX_CUDA(ex, cudaDeviceSynchronize());
+  DPX_CUDA(ex, cudaMemcpy(out, ex->tb.skeys + static_cast<size_t>(frame) * C, static_cast<size_t>(C) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return DPX_OK;
+}
+
 dpx_status dpx_set_profiling(dpx_extractor* ex, int32_t enabled) {
   if (!ex) return DPX_ERR_ARGUMENT;
   ex->profiling = enabled != 0;
@@ -785,6 +803,13 @@ dpx_status dpx_get_region_profile(dpx_extractor* ex, int32_t frame, int64_t out[
 }
 
 int64_t dpx_kernel_launches(const dpx_extractor* ex) { return ex ? ex->launches : 0; }
+
+dpx_status dpx_set_rng_compat(dpx_extractor* ex, int32_t mode) {
+  if (!ex) return DPX_ERR_ARGUMENT;
+  if (mode != DPX_RNG_LIBSTDCXX11 && mode != DPX_RNG_LIBSTDCXX10) return fail(ex, DPX_ERR_ARGUMENT, "unknown rng compatibility mode");
+  ex->uniform_variant = mode;
+  return DPX_OK;
+}
 
 dpx_status dpx_set_label_transport(dpx_extractor* ex, int32_t mode) {
   if (!ex) return DPX_ERR_ARGUMENT;

@@ -63,7 +63,8 @@ struct Tables {
   int32_t* seg_label;
   int32_t* cell_label;
   int32_t* queue;
-  uint32_t* pairs;     // [F][2C] packed (min<<16 | max) adjacent plane pairs
+  uint32_t* pairs;     // [F][2C] packed (min<<16 | max) adjacent plane pairs; scratch of the seed sort and of region growing
+  unsigned long long* skeys;  // [F][C] cells sorted by (histogram bin, MSE, cell id): seed_sort.cuh
   int16_t* bin_work;   // used by region growing when the bins do not fit in shared memory
   uint32_t* cell_words; // [F][C] region-growing cell words when a frame is too large for shared memory
   int32_t* paint_state; // [2 + F] finished-frame counter, number of frames left to stage 3, then the list of those frames

@@ -110,21 +110,41 @@ __device__ __forceinline__ uint32_t mt_next_warp(RefShared& s, int lane, int& id
   return mt_temper(s.mt[idx++]);
 }
 
-// std::uniform_int_distribution<int>(0, n - 1)(gen) for a 32-bit generator, libstdc++ >= 11 (bits/uniform_int_dist.h,
-// _S_nd): Lemire's nearly divisionless method.  `draws` counts generator calls.
-__device__ __forceinline__ int uniform_below_warp(RefShared& s, int lane, int& idx, uint32_t n, int& draws) {
-  unsigned long long product = static_cast<unsigned long long>(mt_next_warp(s, lane, idx)) * n;
-  ++draws;
-  uint32_t low = static_cast<uint32_t>(product);
-  if (low < n) {
-    const uint32_t threshold = (0u - n) % n;
-    while (low < threshold) {
-      product = static_cast<unsigned long long>(mt_next_warp(s, lane, idx)) * n;
-      ++draws;
-      low = static_cast<uint32_t>(product);
-    }
+// std::uniform_int_distribution<int>(0, n - 1)(gen) over std::mt19937.  The mapping is implementation-defined and
+// libstdc++ changed it (bits/uniform_int_dist.h), so both generations are here, selected by RefineArgs::uniform_variant:
+//   0  libstdc++ >= 11 (_S_nd): Lemire's nearly divisionless method -- product = u * n, the low 32 bits below
+//      (2^32 - n) % n are rejected, result = product >> 32;
+//   1  libstdc++ <= 10: scaling = (2^32 - 1) / n, draws >= n * scaling are rejected, result = u / scaling.
+// One generator output either yields a value or is rejected; `accept_draw` is that step for both variants.
+struct UniformMap {
+  uint32_t n, threshold, scaling, past_lo;  // past = n * scaling fits 32 bits (<= 2^32 - 1)
+  int variant;
+};
+__device__ __forceinline__ UniformMap make_uniform_map(uint32_t n, int variant) {
+  UniformMap m;
+  m.n = n;
+  m.variant = variant;
+  m.threshold = (0u - n) % n;
+  m.scaling = 0xffffffffu / n;
+  m.past_lo = n * m.scaling;
+  return m;
+}
+__device__ __forceinline__ bool accept_draw(const UniformMap& m, uint32_t u, int& value) {
+  if (m.variant == 1) {
+    value = static_cast<int>(u / m.scaling);
+    return u < m.past_lo;
   }
-  return static_cast<int>(product >> 32);
+  const unsigned long long product = static_cast<unsigned long long>(u) * m.n;
+  value = static_cast<int>(product >> 32);
+  return static_cast<uint32_t>(product) >= m.threshold;  // (low < n && low < threshold) rejects; threshold < n always
+}
+// `draws` counts generator calls.
+__device__ __forceinline__ int uniform_below_warp(RefShared& s, int lane, int& idx, const UniformMap& m, int& draws) {
+  int value;
+  do {
+    ++draws;
+  } while (!accept_draw(m, mt_next_warp(s, lane, idx), value));
+  return value;
 }
 
 struct LabelCells {
@@ -317,8 +337,7 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
             }
             __syncwarp();
           }
-          const uint32_t un = static_cast<uint32_t>(n);
-          const uint32_t threshold = (0u - un) % un;
+          const UniformMap umap = make_uniform_map(static_cast<uint32_t>(n), args.uniform_variant);
           // Lane h consumes tape entries from 3h + (extra draws of the hypotheses before it) until it holds three distinct
           // accepted values.  The extra draws (a rejection in the distribution, a repeated sample: probability ~3/n per
           // hypothesis) shift everything behind them, so the offsets are iterated to a fixed point: a prefix sum of the
@@ -329,10 +348,8 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
             int pos = 3 * lane + off, cnt = 0;
             a = b = c = -1;
             while (cnt < 3 && pos < kTape) {
-              const unsigned long long product = static_cast<unsigned long long>(s.tape[pos++]) * un;
-              const uint32_t low = static_cast<uint32_t>(product);
-              if (low < un && low < threshold) continue;  // the distribution draws again
-              const int vv = static_cast<int>(product >> 32);
+              int vv;
+              if (!accept_draw(umap, s.tape[pos++], vv)) continue;  // the distribution draws again
               if (vv == a || vv == b || vv == c) continue;  // std::set already holds it
               if (cnt == 0) a = vv;
               else if (cnt == 1) { if (vv < a) { b = a; a = vv; } else b = vv; }
@@ -379,7 +396,7 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
             for (int h = 0; h < kHyp; ++h) {
               int a = -1, b = -1, c = -1, cnt = 0;  // the std::set<int>, kept sorted
               while (cnt < 3) {
-                const int vv = uniform_below_warp(s, lane, mt_idx, un, draws);
+                const int vv = uniform_below_warp(s, lane, mt_idx, umap, draws);
                 if (vv == a || vv == b || vv == c) continue;
                 if (cnt == 0) a = vv;
                 else if (cnt == 1) { if (vv < a) { b = a; a = vv; } else b = vv; }

@@ -11,6 +11,7 @@ struct RefineArgs {
   int max_iterations;  // ransacMaxIterations
   float threshold;     // ransacThreshold
   float inliers_ratio; // ransacInliersRatio
+  int uniform_variant; // std::uniform_int_distribution<int> mapping: 0 = libstdc++ >= 11, 1 = libstdc++ <= 10 (refine.cu)
   const uint32_t* mt_init;  // [624] std::mt19937 default-seeded state (before the first twist)
   Geometry geom;
   Tables tables;       // reads cell_label / n_planes; uses queue and pairs as scratch

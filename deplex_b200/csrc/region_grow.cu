@@ -30,6 +30,7 @@
 #include <cstring>
 
 #include "plane_fit.cuh"
+#include "seed_sort.cuh"
 
 namespace dpx {
 namespace {
@@ -616,10 +617,10 @@ bool force_warp_kernel_env() {
 }  // namespace
 
 namespace {
-// 0 / 1 / 2 = storage mode of region_grow_cta_kernel, -1 = the generic single-warp kernels
+// 0 .. 3 = storage mode of region_grow_cta_kernel, -1 = the generic single-warp kernels
 int cta_mode(const Geometry& g, const Thresholds& th, CtaPlan* plan) {
   if (g.n_cells == 0 || force_warp_kernel_env()) return -1;
-  for (int mode = 0; mode <= 2; ++mode) {
+  for (int mode = 0; mode <= 3; ++mode) {
     const CtaPlan p = region_grow_cta_plan(g, th, mode);
     if (p.bytes > 0) {
       if (plan) *plan = p;
@@ -637,6 +638,7 @@ cudaError_t launch_cta(const RegionArgs& args, const CtaPlan& plan, cudaStream_t
 }  // namespace
 
 bool region_grow_uses_cta(const Geometry& g, const Thresholds& th) { return cta_mode(g, th, nullptr) >= 0; }
+int region_grow_mode(const Geometry& g, const Thresholds& th) { return cta_mode(g, th, nullptr); }
 
 cudaError_t launch_region_grow(const RegionArgs& args, cudaStream_t stream, bool* painted) {
   if (painted) *painted = false;
@@ -649,7 +651,14 @@ cudaError_t launch_region_grow(const RegionArgs& args, cudaStream_t stream, bool
   const int mode = cta_mode(args.geom, args.thr, &cta);
   if (mode >= 0) {
     if (painted) *painted = args.labels != nullptr;
-    return mode == 0 ? launch_cta<0>(args, cta, stream) : mode == 1 ? launch_cta<1>(args, cta, stream) : launch_cta<2>(args, cta, stream);
+    // frames beyond mode 0: the seed order, cells sorted by (bin, MSE, cell id); `pairs` is its scratch
+    if (mode >= 1) e = launch_seed_sort(args.tables.bin, args.tables.mse, args.tables.skeys, reinterpret_cast<unsigned long long*>(args.tables.pairs),
+                         args.n_frames, args.geom.n_cells, stream);
+    if (e != cudaSuccess) return e;
+    return mode == 0   ? launch_cta<0>(args, cta, stream)
+           : mode == 1 ? launch_cta<1>(args, cta, stream)
+           : mode == 2 ? launch_cta<2>(args, cta, stream)
+                       : launch_cta<3>(args, cta, stream);
   }
   const bool all_smem = args.plan.bins_smem && args.plan.list_smem && args.plan.members_smem && args.plan.merge_smem;
   if (all_smem) {
@@ -663,3 +672,16 @@ cudaError_t launch_region_grow(const RegionArgs& args, cudaStream_t stream, bool
 }
 
 }  // namespace dpx
+
+#ifdef DPX_BFS_PROBE
+// probe builds only (make NVFLAGS+=-DDPX_BFS_PROBE): cycles of lane 0 in the phases of bfs_wide_step
+extern "C" __attribute__((visibility("default"))) int dpx_debug_wide_probe(long long* out, int reset) {
+  cudaDeviceSynchronize();
+  if (out) cudaMemcpyFromSymbol(out, dpx::g_wide_probe, sizeof(long long) * 8);
+  if (reset) {
+    long long zero[8] = {};
+    cudaMemcpyToSymbol(dpx::g_wide_probe, zero, sizeof(zero));
+  }
+  return 0;
+}
+#endif

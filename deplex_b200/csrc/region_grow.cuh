@@ -27,6 +27,8 @@ struct RegionArgs {
 RegionPlan region_grow_plan(const Geometry& g, const Thresholds& th);
 // whether launch_region_grow takes the CTA kernel (which can paint the pixel labels itself) for this geometry
 bool region_grow_uses_cta(const Geometry& g, const Thresholds& th);
+// storage mode of the CTA kernel for this geometry (0: all shared memory, no seed sort; 1 .. 3: sorted seeds), -1 = generic kernel
+int region_grow_mode(const Geometry& g, const Thresholds& th);
 // *painted (optional) tells the caller whether the per-pixel labels were written, i.e. whether stage 3 is still needed
 cudaError_t launch_region_grow(const RegionArgs& args, cudaStream_t stream, bool* painted = nullptr);
 

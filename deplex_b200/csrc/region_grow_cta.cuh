@@ -22,8 +22,11 @@
 //               bit matrix (:430-453), final per-cell labels (:464-465).  findMergedLabels (:402-423) is a
 //               short sequential loop run by warp 0 on shared-memory plane records.
 //
-// Storage modes (template parameter, chosen by the frame size): see region_grow_cta_kernel.  Frames above ~6 000 cells
-// take bfs_wide_step (one lane per queue entry, 32 entries per step) when the frontier is wide.
+// Seeds: for frames beyond mode 0 the cells arrive sorted by (histogram bin, MSE, cell id) from seed_sort_kernel
+// (seed_sort.cuh), so "first strict-minimum MSE among the bin's unassigned cells" (plane_extractor.cpp:309-316) is the
+// first entry of the bin's run that is still alive, found by a per-bin cursor that only moves forward.
+//
+// Storage modes (template parameter, chosen by the frame size): see region_grow_cta_kernel.
 #pragma once
 #include "labeling.cuh"
 
@@ -41,29 +44,72 @@ constexpr unsigned kAlive = 1u << 20;
 constexpr unsigned kClaimIdle = 0x7ffu << 21;
 constexpr int kRecFloats = kSegFloats;  // region / plane records use the segs layout
 
+constexpr int kWin = 8;        // modes 1/2: sorted-key entries cached per bin in shared memory
+constexpr int kRing = 1024;    // modes 1/2: most recent queue entries mirrored in shared memory (power of two)
+
 struct CtaPlan {
-  int off_stage, off_hkey, off_binslot, off_binoff, off_runend, off_cw, off_list, off_members, off_msem, off_recs, off_merge,
-      off_misc;
+  int off_stage, off_hkey, off_binslot, off_cursor, off_binend, off_cw, off_list, off_keys, off_ring, off_win, off_wpos, off_wend,
+      off_recs, off_merge, off_misc;
   int rec_cap;       // region / plane records held in shared memory (the rest spill to the global segs table)
-  int adj_bytes;     // bytes available to the adjacency bit matrix (the member runs' storage)
-  int cache_cap;     // modes 1/2: member-run entries of small bins kept in shared memory (positions below it)
-  int off_cmem, off_cmse;
+  int adj_bytes;     // bytes available to the adjacency bit matrix
+  int merge_smem;    // merge labels in shared memory (else in the global merge table)
   size_t bytes;
 };
 
 __device__ __noinline__ void fit_plane_call(const Moments& m, PlaneFit& f) { fit_plane(m, f); }
 
-// Wide BFS step: one lane per queue entry (up to 32), each lane probes its four neighbours.  FIFO order is
-// (entry, slot) lexicographic; a cell reached more than once goes to the smallest entry * 4 + slot, posted into the
-// cell word's claim field with a shared-memory atomicMin.  Kept out of line so that the narrow step's register
-// allocation is not disturbed.  Returns {cells appended, appended cells that belong to the seed's bin}.
+// Cell words.  32-bit form (modes 0 and 1): bits 0-15 slot of the cell's initial bin in the compacted histogram, 16-19
+// edge mask, 20 alive (planar and unassigned), 21-31 claim field (all ones while idle; see the BFS step).
+// 16-bit form (mode 2, frames too large for 4 bytes per cell of shared memory): bits 0-9 slot, 10-13 edge mask, 14
+// alive; no claim field -- clashes between queue entries are settled with shuffles instead.
+template <bool CW16>
+struct CellWordT {
+  using type = unsigned;
+  static constexpr unsigned slot_mask = 0xffffu, alive = kAlive;
+  static constexpr int edge_shift = 16;
+};
+template <>
+struct CellWordT<true> {
+  using type = uint16_t;
+  static constexpr unsigned slot_mask = 0x3ffu, alive = 1u << 14;
+  static constexpr int edge_shift = 10;
+};
+
+// Queue storage of the BFS: the cell list of a frame.  Mode 0 keeps it in shared memory; the larger modes keep it in the
+// global `queue` table (its reads and writes are sequential) and mirror the most recent kRing entries in shared memory,
+// which is where the BFS reads them back from unless the frontier is longer than the ring.
+template <bool RING>
+struct QueueT {
+  int32_t* list;     // mode 0: shared memory; else global, frame base
+  unsigned* ring;    // [kRing] or nullptr
+  __device__ __forceinline__ unsigned read(int abs_pos, bool in_ring) const {
+    if (RING) return in_ring ? ring[abs_pos & (kRing - 1)] : static_cast<unsigned>(__ldcg(list + abs_pos));
+    return static_cast<unsigned>(list[abs_pos]);
+  }
+};
+
+// Wide BFS step (32-bit cell words only): one lane per queue entry (up to 32), each lane probes its four neighbours.
+// FIFO order is (entry, slot) lexicographic; a cell reached more than once goes to the smallest entry * 4 + slot, posted
+// into the cell word's claim field with a shared-memory atomicMin.  Kept out of line so that the narrow step's register
+// allocation is not disturbed.  `base` = absolute list position of the region's first entry.  Returns {cells appended,
+// appended cells that belong to the seed's bin}.
 constexpr int kWideThreshold = 12;
-template <bool BIG_GLOBAL>
-__device__ __noinline__ int2 bfs_wide_step(int32_t* q, unsigned* cw, unsigned* hkey, int32_t* sink, int head, int tail, int lane,
-                                           int nh, int bslot) {
+#ifdef DPX_BFS_PROBE
+__device__ long long g_wide_probe[8];
+#define WIDE_PROBE(slot) do { if (lane == 0) { const long long t__ = clock64(); g_wide_probe[slot] += t__ - wp_t; wp_t = t__; } } while (0)
+#else
+#define WIDE_PROBE(slot) do { } while (0)
+#endif
+template <bool RING>
+__device__ __noinline__ int2 bfs_wide_step(const QueueT<RING> qs, int base, unsigned* cw, unsigned* hkey, int32_t* sink, int head,
+                                           int tail, int lane, int nh, int bslot) {
+#ifdef DPX_BFS_PROBE
+  long long wp_t = clock64();
+#endif
   const int nbw = min(32, tail - head);
+  const bool in_ring = tail - head <= kRing - 128;
   unsigned pk = 0;
-  if (lane < nbw) pk = static_cast<unsigned>(q[head + lane]);
+  if (lane < nbw) pk = qs.read(base + head + lane, in_ring);
   const int u = static_cast<int>(pk & 0xffffffu);
   int vv[4];
   unsigned ww[4];
@@ -76,6 +122,7 @@ __device__ __noinline__ int2 bfs_wide_step(int32_t* q, unsigned* cw, unsigned* h
     if (ww[sl4] & kAlive) passm |= 1u << sl4;
   }
   const unsigned anyp = __ballot_sync(kFull, passm != 0);
+  WIDE_PROBE(0);
   unsigned winm = passm;
   if (anyp & (anyp - 1u)) {  // at least two entries have candidates: they may clash
 #pragma unroll
@@ -85,9 +132,9 @@ __device__ __noinline__ int2 bfs_wide_step(int32_t* q, unsigned* cw, unsigned* h
     __syncwarp();
 #pragma unroll
     for (int sl4 = 0; sl4 < 4; ++sl4)
-      if ((passm & (1u << sl4)) && ((BIG_GLOBAL ? __ldcg(cw + vv[sl4]) : cw[vv[sl4]]) >> 21) != static_cast<unsigned>(lane * 4 + sl4))
-        winm &= ~(1u << sl4);
+      if ((passm & (1u << sl4)) && (cw[vv[sl4]] >> 21) != static_cast<unsigned>(lane * 4 + sl4)) winm &= ~(1u << sl4);
   }
+  WIDE_PROBE(1);
   // append position of (lane, slot) = winners of lower lanes + own lower slots.  A lane has 0..4 winners: the prefix
   // over the lanes comes from three ballots on the bits of that count instead of a five-round shuffle scan.
   const unsigned nwin = __popc(winm);
@@ -95,6 +142,7 @@ __device__ __noinline__ int2 bfs_wide_step(int32_t* q, unsigned* cw, unsigned* h
   const unsigned b0 = __ballot_sync(kFull, nwin & 1u), b1 = __ballot_sync(kFull, nwin & 2u), b2 = __ballot_sync(kFull, nwin & 4u);
   int pos = tail + __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
   const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+  WIDE_PROBE(2);
   int same = 0;
   // branch-free: slots that did not win write to a private sink (see the narrow step)
 #pragma unroll
@@ -102,28 +150,45 @@ __device__ __noinline__ int2 bfs_wide_step(int32_t* q, unsigned* cw, unsigned* h
     const bool won = (winm >> sl4) & 1u;
     const unsigned slt = ww[sl4] & 0xffffu;
     const bool other_bin = won && slt != static_cast<unsigned>(bslot);
-    int32_t* qdst = won ? q + pos : sink + lane;
+    const int entry = vv[sl4] | static_cast<int>(((ww[sl4] >> 16) & 0xfu) << 24);
     unsigned* cdst = won ? cw + vv[sl4] : reinterpret_cast<unsigned*>(sink) + lane;
-    *qdst = vv[sl4] | static_cast<int>(((ww[sl4] >> 16) & 0xfu) << 24);
+    if (RING) {
+      // large frames: the step writes the shared-memory ring only; the caller copies the ring to the global list in bulk
+      unsigned* rdst = won ? qs.ring + ((base + pos) & (kRing - 1)) : reinterpret_cast<unsigned*>(sink) + lane;
+      *rdst = static_cast<unsigned>(entry);
+    } else {
+      int32_t* qdst = won ? qs.list + base + pos : sink + lane;
+      *qdst = entry;
+    }
     *cdst = ww[sl4] & ~kAlive;
     pos += won ? 1 : 0;
     same += (won && !other_bin) ? 1 : 0;
     atomicSub(other_bin ? hkey + slt : reinterpret_cast<unsigned*>(sink) + lane, 1u << 15);
+    WIDE_PROBE(3 + 0 * sl4);
   }
   __syncwarp();
+  WIDE_PROBE(4);
   return make_int2(total, same);
 }
 
 
-// MODE 0: everything in shared memory (frames of up to ~6 000 cells, several CTAs per SM).
-// MODE 1: member runs (and later the adjacency bit matrix) in the global scratch table `pairs` (8 bytes per cell,
-// L2-resident), so that frames of up to ~27 000 cells keep the BFS state -- cell words and queue -- in shared memory.
-// MODE 2 (frames above ~27 000 cells): cell words and queue in global memory as well (L2-resident, ~10x the latency
-// of shared memory per probe, but the same algorithmic structure instead of the single-warp fallback).
+// MODE 0: everything in shared memory -- cell words, cell list, member runs grouped by bin (frames of up to ~5 000
+//         cells, several CTAs per SM).  No sort: at this size the minimum scan over a bin's run is cheaper than sorting.
+// MODE 1: sorted seeds (keys in global memory / L2 with a small window per bin in shared memory); 32-bit cell words and the
+//         cell list in shared memory (up to ~21 000 cells: 640x480 at patch 4, 1920x1080 at patch 10).
+// MODE 2: as mode 1 with the cell list in the global `queue` table and a shared-memory ring of its most recent entries
+//         (up to ~42 000 cells); merge labels in global memory when they do not fit.
+// MODE 3: as mode 2 with 16-bit cell words (up to ~85 000 cells: 1920x1080 at patch 5, 1280x720 at patch 4); queue
+//         clashes are settled with shuffles and only the narrow BFS step is used.
 template <int MODE>
 __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const RegionArgs args, const CtaPlan plan) {
-  constexpr bool MEMBERS_SMEM = MODE == 0;
-  constexpr bool BIG_GLOBAL = MODE == 2;
+  constexpr bool ALL_SMEM = MODE == 0;   // no sort: member runs in shared memory, minimum scan per seed
+  constexpr bool RING = MODE >= 2;       // cell list in global memory + shared-memory ring (else the list is in shared memory)
+  constexpr bool CW16 = MODE == 3;
+  using CW = CellWordT<CW16>;
+  using word_t = typename CW::type;
+  constexpr unsigned kAliveW = CW::alive, kSlotMask = CW::slot_mask;
+  constexpr int kEdgeShift = CW::edge_shift;
   extern __shared__ float4 smem_f4[];
   const Geometry& g = args.geom;
   const Thresholds& th = args.thr;
@@ -137,38 +202,42 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
   float* stage_all = reinterpret_cast<float*>(smem + plan.off_stage);        // [kCtaWarps - 1][32][12]
   unsigned* hkey = reinterpret_cast<unsigned*>(smem + plan.off_hkey);        // [K] count << 15 | (0x7fff - slot), non-empty bins
   int16_t* binslot = reinterpret_cast<int16_t*>(smem + plan.off_binslot);    // [B2] bin -> slot in hkey (or -1)
-  int* bin_off = reinterpret_cast<int*>(smem + plan.off_binoff);             // [K] start of the bin's member run
-  int* run_end = reinterpret_cast<int*>(smem + plan.off_runend);             // [K] end of its still-unassigned members
-  // [C] cell words (later the segment labels) and [C] BFS queues = region cell lists
-  unsigned* cw = BIG_GLOBAL ? args.tables.cell_words + fc : reinterpret_cast<unsigned*>(smem + plan.off_cw);
-  int32_t* list = BIG_GLOBAL ? args.tables.queue + fc : reinterpret_cast<int32_t*>(smem + plan.off_list);
-  // [C] cell ids grouped by initial bin, and [C] their MSE in the same order.  Run positions below `cap` index the
-  // shared-memory arrays, the others the global ones (modes 1/2: only the small bins' runs fit in shared memory).
-  int32_t* members = MEMBERS_SMEM ? reinterpret_cast<int32_t*>(smem + plan.off_members)
-                                  : reinterpret_cast<int32_t*>(args.tables.pairs + 2 * fc);
-  float* msem = MEMBERS_SMEM ? reinterpret_cast<float*>(smem + plan.off_msem)
-                             : reinterpret_cast<float*>(args.tables.pairs + 2 * fc + C);
-  const int cap = MEMBERS_SMEM ? 0x7fffffff : plan.cache_cap;
-  int32_t* cmem = MEMBERS_SMEM ? members : reinterpret_cast<int32_t*>(smem + plan.off_cmem);
-  float* cmse = MEMBERS_SMEM ? msem : reinterpret_cast<float*>(smem + plan.off_cmse);
-  int32_t* gmem = MEMBERS_SMEM ? members : members - cap;  // indexed with positions >= cap
-  float* gmse = MEMBERS_SMEM ? msem : msem - cap;
+  int* cursor = reinterpret_cast<int*>(smem + plan.off_cursor);              // [K] first entry of the bin's run that may be alive
+  int* bin_end = reinterpret_cast<int*>(smem + plan.off_binend);             // [K] end of the bin's run in the sorted keys
+  word_t* cw = reinterpret_cast<word_t*>(smem + plan.off_cw);                // [C] cell words (later the segment labels)
+  // [C] BFS queues = region cell lists
+  QueueT<RING> qs;
+  qs.list = RING ? args.tables.queue + fc : reinterpret_cast<int32_t*>(smem + plan.off_list);
+  qs.ring = RING ? reinterpret_cast<unsigned*>(smem + plan.off_ring) : nullptr;
+  int32_t* list = qs.list;
+  // the frame's cells sorted by (bin, MSE, cell id): seed_sort_kernel's output
+  const unsigned long long* skeys_g = args.tables.skeys + fc;
+  // mode 0 (small frames, where a sort would cost more than it saves): [C] cell ids grouped by initial bin and [C] their
+  // MSE in the same order; the seed search is a minimum scan over the bin's run that compacts the run as it goes
+  int32_t* members = reinterpret_cast<int32_t*>(smem + plan.off_keys);
+  float* msem = reinterpret_cast<float*>(smem + plan.off_keys) + C;
+  int* bin_off = bin_end;  // mode 0: start of the bin's member run
+  int* run_end = cursor;   // mode 0: end of its still-unassigned members
+  const float* mse_g = args.tables.mse + fc;
+  unsigned long long* win = reinterpret_cast<unsigned long long*>(smem + plan.off_win);       // modes 1/2: [K][kWin]
+  int* wpos = reinterpret_cast<int*>(smem + plan.off_wpos);                  // modes 1/2: [K] sorted position of win[slot][0]
+  int* wend = reinterpret_cast<int*>(smem + plan.off_wend);                  // modes 1/2: [K] end of the window's valid entries
   float* recs = reinterpret_cast<float*>(smem + plan.off_recs);              // [rec_cap][24]
-  int32_t* merge = reinterpret_cast<int32_t*>(smem + plan.off_merge);        // [plane_cap]
+  int32_t* merge_out = args.tables.merge + static_cast<long long>(frame) * g.plane_cap;
+  int32_t* merge = plan.merge_smem ? reinterpret_cast<int32_t*>(smem + plan.off_merge) : merge_out;  // [plane_cap]
   volatile int* misc = reinterpret_cast<volatile int*>(smem + plan.off_misc);
   // misc: [0] regions published, [1] growing finished, [2] scratch counter, [3] remaining planar cells, [4] K,
   //       [8..8+kCtaWarps) per-warp counts for the ordered compaction
-  int* hist_tmp = reinterpret_cast<int*>(list);  // [B2] raw histogram during setup (the list is still unused)
+  // [B2] raw histogram during setup, in storage that is not in use yet (the list / the key windows)
+  int* hist_tmp = ALL_SMEM ? reinterpret_cast<int*>(list) : reinterpret_cast<int*>(win);
   int32_t* dummy = reinterpret_cast<int32_t*>(smem + plan.off_misc) + 32;  // [32] per-lane sink of the branch-free BFS tail
 
   const float4* rec_b4 = args.tables.rec_b + 3 * fc;
   const int16_t* bin_in = args.tables.bin + fc;
   const uint8_t* edge_in = args.tables.edge + fc;
-  const float* mse_g = args.tables.mse + fc;
   int32_t* seg_label = args.tables.seg_label + fc;
   int32_t* cell_label = args.tables.cell_label + fc;
   float* segs_g = args.tables.segs + static_cast<long long>(frame) * g.plane_cap * kSegFloats;
-  int32_t* merge_out = args.tables.merge + static_cast<long long>(frame) * g.plane_cap;
   auto rec_ptr = [&](int r) -> float* {
     return r < plan.rec_cap ? recs + r * kRecFloats : segs_g + static_cast<long long>(r) * kSegFloats;
   };
@@ -188,71 +257,64 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
   for (int c = tid; c < C; c += kCtaThreads) {
     const int b = static_cast<int>(__ldg(bin_in + c));
     const unsigned e = static_cast<unsigned>(__ldg(edge_in + c));
-    cw[c] = b >= 0 ? (static_cast<unsigned>(b) | (e << 16) | kAlive | kClaimIdle) : 0u;
+    const unsigned w0 = b >= 0 ? (static_cast<unsigned>(b) | (e << kEdgeShift) | kAliveW | (CW16 ? 0u : kClaimIdle)) : 0u;
+    cw[c] = static_cast<word_t>(w0);
     seg_label[c] = 0;
     if (b >= 0) atomicAdd(&hist_tmp[b], 1);
   }
   __syncthreads();
-  // compact the non-empty bins and lay out their member runs (warp 0; ascending bin order)
+  // compact the non-empty bins; their runs in the sorted keys follow each other in bin order (warp 0)
   if (warp == 0) {
-    int K = 0, run = 0, crun = 0, total = 0;
-    auto scan = [&](int v) {
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(kFull, v, o);
-        if (lane >= o) v += t;
-      }
-      return v;
-    };
+    int K = 0, run = 0;
     for (int b0 = 0; b0 < B2; b0 += 32) {
       const int b = b0 + lane;
       const int cnt = b < B2 ? hist_tmp[b] : 0;
       const unsigned nz = __ballot_sync(kFull, cnt > 0);
-      // small bins go to the shared-memory position space while it has room (always, in mode 0), the rest behind it
-      const bool small = MEMBERS_SMEM || (cnt > 0 && cnt <= 32);
-      const int incl_s = scan(small ? cnt : 0);
-      const bool cached = MEMBERS_SMEM || (small && crun + incl_s <= cap);
-      const int incl_c = MEMBERS_SMEM ? incl_s : scan(cached ? cnt : 0);
-      const int incl_g = MEMBERS_SMEM ? 0 : scan(cached ? 0 : cnt);
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += t;
+      }
+      __syncwarp();  // (hist_tmp aliases the key windows: all lanes have read their counts before wpos / wend are written)
       if (cnt > 0) {
         const int slot = K + __popc(nz & ((1u << lane) - 1u));
         binslot[b] = static_cast<int16_t>(slot);
         hkey[slot] = (static_cast<unsigned>(cnt) << 15) | (0x7fffu - static_cast<unsigned>(slot));
-        const int pos = cached ? crun + incl_c - cnt : cap + run + incl_g - cnt;
-        bin_off[slot] = pos;
-        run_end[slot] = pos;
+        const int pos = run + incl - cnt;
+        cursor[slot] = pos;                           // mode 0: end of the run's live members, filled by the scatter below
+        bin_end[slot] = ALL_SMEM ? pos : pos + cnt;   // mode 0: start of the bin's member run
+        if (!ALL_SMEM) {
+          wpos[slot] = pos;
+          wend[slot] = pos;  // empty window
+        }
       }
       K += __popc(nz);
-      crun += __shfl_sync(kFull, incl_c, 31);
-      run += __shfl_sync(kFull, incl_g, 31);
-      total += __shfl_sync(kFull, MEMBERS_SMEM ? incl_s : scan(cnt), 31);
+      run += __shfl_sync(kFull, incl, 31);
     }
     if (lane == 0) {
-      misc[3] = total;
+      misc[3] = run;
       misc[4] = K;
     }
   }
   __syncthreads();
   for (int c = tid; c < C; c += kCtaThreads) {
     const unsigned w = cw[c];
-    if (w & kAlive) {
-      const unsigned slot = static_cast<unsigned>(binslot[w & 0xffffu]);
-      cw[c] = (w & 0xffff0000u) | slot;  // from here on the word carries the histogram slot instead of the bin id
-      const int pos = atomicAdd(&run_end[slot], 1);
-      const float mse = __ldg(mse_g + c);
-      if (pos < cap) {
-        cmem[pos] = c;
-        cmse[pos] = mse;
-      } else {
-        gmem[pos] = c;
-        gmse[pos] = mse;
+    if (w & kAliveW) {
+      const unsigned slot = static_cast<unsigned>(binslot[w & kSlotMask]);
+      cw[c] = static_cast<word_t>((w & ~kSlotMask) | slot);  // from here on the word carries the histogram slot, not the bin id
+      if (ALL_SMEM) {
+        // small frames: the bin's members in arrival order; the seed search scans (and compacts) the run
+        const int pos = atomicAdd(&cursor[slot], 1);
+        members[pos] = c;
+        msem[pos] = __ldg(mse_g + c);
       }
     }
   }
-  __syncthreads();  // (hist_tmp aliases the list: nobody touches the list before this barrier)
+  __syncthreads();  // (hist_tmp aliases the list / the windows: nobody touches those before this barrier)
 
   const int cell_pts = g.patch * g.patch;
-  long long t_seed = 0, t_bfs = 0, t_mark = 0;
+  long long t_seed = 0, t_bfs = 0, t_mark = 0, t_wide = 0;
   int n_seeds = 0, n_steps = 0;
   const long long t_init = prof ? clock64() - t_kernel0 : 0;
 
@@ -285,87 +347,162 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
       const unsigned long long n_cand = bc > 0 ? static_cast<unsigned long long>(bc) : 0ull;
       if (n_cand < th.min_candidate_size) break;  // plane_extractor.cpp:305-307
 
-      // seed = first strict minimum of the MSE among the bin's unassigned cells (plane_extractor.cpp:309-316);
-      // the scan also compacts the bin's member run down to the cells that are still unassigned
+      // seed = first strict minimum of the MSE among the bin's unassigned cells (plane_extractor.cpp:309-316)
       float lm = __int_as_float(0x7f800000);
       int seed = kNoSeed;
-      {
-        const int start = bin_off[bslot], end = run_end[bslot];
-        int w = start;
-        int32_t* mp = start < cap ? cmem : gmem;  // a run lies entirely in one of the two position spaces
-        float* sp = start < cap ? cmse : gmse;
-        // four 32-member chunks per round: their loads are independent, so a round costs one memory round trip
-        if (end - start <= 32) {
-          // short run (the usual case for the left-over bins that produce one-cell regions): one chunk, straight-line
-          const int i = start + lane;
-          const bool in = i < end;
-          const int c = in ? mp[i] : 0;
-          const float m = in ? sp[i] : 0.f;
-          const unsigned wv = in ? cw[c] : 0u;
-          const bool alive = (wv & kAlive) != 0;
-          const unsigned am = __ballot_sync(kFull, alive);
-          // stable compaction; lanes without a live member write to their private sink
-          const int pos = start + __popc(am & ((1u << lane) - 1u));
-          int32_t* mdst = alive ? mp + pos : dummy + lane;
-          float* sdst = alive ? sp + pos : reinterpret_cast<float*>(dummy) + lane;
-          *mdst = c;
-          *sdst = m;
-          if (alive) { lm = m; seed = c; }
-          w = start + __popc(am);
-          __syncwarp();
-        } else {
-          // long run: four 32-member chunks per round; the loads of the next round are issued before this round is
-          // processed, so that a round costs its processing and not a memory round trip (member runs of large
-          // frames live in global memory)
-          int cn[4];
-          float mn[4];
-          auto fetch = [&](int i0) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int i = i0 + 32 * u + lane;
-              const bool in = i < end;
-              cn[u] = in ? mp[i] : -1;
-              mn[u] = in ? sp[i] : 0.f;
-            }
-          };
-          fetch(start);
-          for (int i0 = start; i0 < end; i0 += 128) {
-            int c[4];
-            float m[4];
-            bool alive[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              c[u] = cn[u];
-              m[u] = mn[u];
-            }
-            if (i0 + 128 < end) fetch(i0 + 128);  // reads entries the compaction below cannot reach
-#pragma unroll
-            for (int u = 0; u < 4; ++u) alive[u] = c[u] >= 0 && (cw[c[u]] & kAlive);
-            __syncwarp();  // all reads of this round precede its (possibly overlapping) compaction writes
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (alive[u] && (m[u] < lm || (m[u] == lm && c[u] < seed))) { lm = m[u]; seed = c[u]; }
-              const unsigned am = __ballot_sync(kFull, alive[u]);
-              if (alive[u] && (am != kFull || w != i0 + 32 * u)) {
-                const int pos = w + __popc(am & ((1u << lane) - 1u));
-                mp[pos] = c[u];
-                sp[pos] = m[u];
-              }
-              w += __popc(am);
-            }
+      if (ALL_SMEM) {
+        // small frames: first strict minimum of the MSE among the bin's unassigned cells (plane_extractor.cpp:309-316) by a
+        // scan over the bin's member run that also compacts the run down to the cells that are still unassigned
+        {
+          const int start = bin_off[bslot], end = run_end[bslot];
+          int w = start;
+          int32_t* mp = members;
+          float* sp = msem;
+          // four 32-member chunks per round: their loads are independent, so a round costs one memory round trip
+          if (end - start <= 32) {
+            // short run (the usual case for the left-over bins that produce one-cell regions): one chunk, straight-line
+            const int i = start + lane;
+            const bool in = i < end;
+            const int c = in ? mp[i] : 0;
+            const float m = in ? sp[i] : 0.f;
+            const unsigned wv = in ? cw[c] : 0u;
+            const bool alive = (wv & kAliveW) != 0;
+            const unsigned am = __ballot_sync(kFull, alive);
+            // stable compaction; lanes without a live member write to their private sink
+            const int pos = start + __popc(am & ((1u << lane) - 1u));
+            int32_t* mdst = alive ? mp + pos : dummy + lane;
+            float* sdst = alive ? sp + pos : reinterpret_cast<float*>(dummy) + lane;
+            *mdst = c;
+            *sdst = m;
+            if (alive) { lm = m; seed = c; }
+            w = start + __popc(am);
             __syncwarp();
+          } else {
+            // long run: four 32-member chunks per round; the loads of the next round are issued before this round is
+            // processed, so that a round costs its processing and not a memory round trip (member runs of large
+            // frames live in global memory)
+            int cn[4];
+            float mn[4];
+            auto fetch = [&](int i0) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int i = i0 + 32 * u + lane;
+                const bool in = i < end;
+                cn[u] = in ? mp[i] : -1;
+                mn[u] = in ? sp[i] : 0.f;
+              }
+            };
+            fetch(start);
+            for (int i0 = start; i0 < end; i0 += 128) {
+              int c[4];
+              float m[4];
+              bool alive[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                c[u] = cn[u];
+                m[u] = mn[u];
+              }
+              if (i0 + 128 < end) fetch(i0 + 128);  // reads entries the compaction below cannot reach
+#pragma unroll
+              for (int u = 0; u < 4; ++u) alive[u] = c[u] >= 0 && (cw[c[u]] & kAliveW);
+              __syncwarp();  // all reads of this round precede its (possibly overlapping) compaction writes
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                if (alive[u] && (m[u] < lm || (m[u] == lm && c[u] < seed))) { lm = m[u]; seed = c[u]; }
+                const unsigned am = __ballot_sync(kFull, alive[u]);
+                if (alive[u] && (am != kFull || w != i0 + 32 * u)) {
+                  const int pos = w + __popc(am & ((1u << lane) - 1u));
+                  mp[pos] = c[u];
+                  sp[pos] = m[u];
+                }
+                w += __popc(am);
+              }
+              __syncwarp();
+            }
           }
+          if (lane == 0) run_end[bslot] = w;
         }
-        if (lane == 0) run_end[bslot] = w;
-      }
-      {
-        const unsigned fb = __float_as_uint(lm);
-        const unsigned ord = fb ^ ((fb >> 31) ? 0xffffffffu : 0x80000000u);
-        const unsigned best = __reduce_min_sync(kFull, seed == kNoSeed ? 0xffffffffu : ord);
-        const unsigned cand = (seed != kNoSeed && ord == best) ? static_cast<unsigned>(seed) : static_cast<unsigned>(kNoSeed);
-        seed = static_cast<int>(__reduce_min_sync(kFull, cand));
-        const unsigned bb = best ^ ((best >> 31) ? 0x80000000u : 0xffffffffu);
-        lm = __uint_as_float(bb);
+        {
+          const unsigned fb = __float_as_uint(lm);
+          const unsigned ord = fb ^ ((fb >> 31) ? 0xffffffffu : 0x80000000u);
+          const unsigned best = __reduce_min_sync(kFull, seed == kNoSeed ? 0xffffffffu : ord);
+          const unsigned cand = (seed != kNoSeed && ord == best) ? static_cast<unsigned>(seed) : static_cast<unsigned>(kNoSeed);
+          seed = static_cast<int>(__reduce_min_sync(kFull, cand));
+          const unsigned bb = best ^ ((best >> 31) ? 0x80000000u : 0xffffffffu);
+          lm = __uint_as_float(bb);
+        }
+      } else {
+        // larger frames: the first entry of the bin's (MSE, cell id)-sorted run that is still alive (seed_sort.cuh);
+        // everything before the cursor is dead for good
+        unsigned seed_ord = 0xffffffffu;
+        {
+          int pos = cursor[bslot];
+          const int end = bin_end[bslot];
+          {
+            int wb = wpos[bslot], we = wend[bslot];
+            while (pos < end) {
+              if (pos >= wb && pos < we) {
+                // the bin's window in shared memory holds sorted entries [wb, we)
+                const int i = pos + lane;
+                const bool in = i < we;
+                const unsigned long long k = in ? win[bslot * kWin + (i - wb)] : 0ull;
+                const int c = static_cast<int>(k & kSeedCellMask);
+                const bool alive = in && (cw[c] & kAliveW) != 0;
+                const unsigned am = __ballot_sync(kFull, alive);
+                if (am) {
+                  const int f = __ffs(am) - 1;
+                  seed = __shfl_sync(kFull, c, f);
+                  seed_ord = __shfl_sync(kFull, static_cast<unsigned>(k >> kSeedCellBits), f);
+                  pos += f + 1;
+                  break;
+                }
+                pos = we;
+                continue;
+              }
+              // 128 entries from the L2-resident sorted keys; the entries behind the seed refill the window
+              unsigned long long k[4];
+              unsigned am[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int i = pos + 32 * u + lane;
+                k[u] = i < end ? __ldg(skeys_g + i) : 0ull;
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int i = pos + 32 * u + lane;
+                const bool alive = i < end && (cw[static_cast<int>(k[u] & kSeedCellMask)] & kAliveW) != 0;
+                am[u] = __ballot_sync(kFull, alive);
+              }
+              const int fu = am[0] ? 0 : am[1] ? 1 : am[2] ? 2 : am[3] ? 3 : -1;
+              if (fu < 0) {
+                pos += 128;
+                continue;
+              }
+              const unsigned amf = fu == 0 ? am[0] : fu == 1 ? am[1] : fu == 2 ? am[2] : am[3];
+              const unsigned long long kf = fu == 0 ? k[0] : fu == 1 ? k[1] : fu == 2 ? k[2] : k[3];
+              const int f = __ffs(amf) - 1;
+              seed = __shfl_sync(kFull, static_cast<int>(kf & kSeedCellMask), f);
+              seed_ord = __shfl_sync(kFull, static_cast<unsigned>(kf >> kSeedCellBits), f);
+              const int fpos = pos + 32 * fu + f;
+              const int loaded_end = min(end, pos + 128);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int i = pos + 32 * u + lane;
+                if (i > fpos && i <= fpos + kWin && i < loaded_end) win[bslot * kWin + (i - fpos - 1)] = k[u];
+              }
+              wb = fpos + 1;
+              we = min(fpos + 1 + kWin, loaded_end);
+              if (lane == 0) {
+                wpos[bslot] = wb;
+                wend[bslot] = we;
+              }
+              pos = fpos + 1;
+              break;
+            }
+          }
+          if (lane == 0) cursor[bslot] = pos;
+        }
+        lm = seed_mse_from_order(seed_ord);
       }
       // no candidate with mse < INT_MAX: the reference reads an uninitialised seed id here.  (double)lm < 2147483647.0
       // is lm < 2^31 for a float: the largest float below 2^31 is 2^31 - 128.
@@ -373,68 +510,115 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
       if (prof) { const long long t = clock64(); t_seed += t - t_mark; t_mark = t; ++n_seeds; }
 
       // growSeed (plane_extractor.cpp:349-392): batched FIFO BFS into list[list_off ...)
-      int32_t* q = list + list_off;
       int same = 0;  // cells of the seed's bin activated by this lane (histogram is settled after the BFS)
       const unsigned seed_w = cw[seed];
       __syncwarp();
       {
-        int32_t* qd = lane == 0 ? q : dummy + lane;
-        unsigned* cd = lane == 0 ? cw + seed : reinterpret_cast<unsigned*>(dummy) + lane;
-        *qd = seed | static_cast<int>(((seed_w >> 16) & 0xfu) << 24);
-        *cd = seed_w & ~kAlive;
+        const int entry = seed | static_cast<int>(((seed_w >> kEdgeShift) & 0xfu) << 24);
+        word_t* cd = lane == 0 ? cw + seed : reinterpret_cast<word_t*>(dummy + lane);
+        if (RING) {
+          unsigned* rd = lane == 0 ? qs.ring + (list_off & (kRing - 1)) : reinterpret_cast<unsigned*>(dummy) + lane;
+          *rd = static_cast<unsigned>(entry);
+        } else {
+          int32_t* qd = lane == 0 ? list + list_off : dummy + lane;
+          *qd = entry;
+        }
+        *cd = static_cast<word_t>(seed_w & ~kAliveW);
         same = lane == 0 ? 1 : 0;
       }
       __syncwarp();
+      // Large frames: the steps below append to the shared-memory ring only (a global store inside the step would put its
+      // latency on the chain through the warp barrier that follows it); the ring is copied to the global list in blocks of
+      // kFlush entries while the region grows -- always before the ring wraps over them -- and the rest when the region is
+      // published.  Regions that are discarded never reach global memory at all.
+      constexpr int kFlush = 512;
+      int flush_pos = list_off;  // absolute list position up to which the global list is complete
+      auto flush_to = [&](int upto) {
+        for (int p0 = flush_pos; p0 < upto; p0 += 32) {
+          const int p1 = p0 + lane;
+          if (p1 < upto) list[p1] = static_cast<int32_t>(qs.ring[p1 & (kRing - 1)]);
+        }
+        flush_pos = upto;
+      };
       // a seed without a single passing edge is a region of one cell: no BFS step needed
-      int head = ((seed_w >> 16) & 0xfu) ? 0 : 1, tail = 1;
+      int head = ((seed_w >> kEdgeShift) & 0xfu) ? 0 : 1, tail = 1;
       const int ent = lane >> 2;
       const unsigned lt_mask = (1u << lane) - 1u;
       const unsigned my_claim = static_cast<unsigned>(lane) << 21;
       while (head < tail) {
-        // (large frames only: the instantiation for small frames keeps the narrow step's tighter code)
-        if (!MEMBERS_SMEM && tail - head > kWideThreshold) {
-          const int2 r = bfs_wide_step<BIG_GLOBAL>(q, cw, hkey, dummy, head, tail, lane, nh, bslot);
+        // (32-bit words of large frames only: the instantiation for small frames keeps the narrow step's tighter code)
+        if ((MODE == 1 || MODE == 2) && tail - head > kWideThreshold) {
+          const long long tw0 = prof ? clock64() : 0;
+          const int2 r = bfs_wide_step<RING>(qs, list_off, reinterpret_cast<unsigned*>(cw), hkey, dummy, head, tail, lane, nh, bslot);
           head += min(32, tail - head);
           tail += r.x;
           same += r.y;
           ++n_steps;
+          if (list_off + tail - flush_pos >= kFlush) flush_to(flush_pos + kFlush);
+          if (prof) t_wide += clock64() - tw0;
           continue;
         }
         // straight-line step (a single warp pays every branch and every dependent instruction in full)
         const int nb = min(8, tail - head);
+        const bool in_ring = tail - head <= kRing - 64;  // the step's entries are still mirrored in shared memory
         unsigned pk = 0;
-        if (ent < nb) pk = static_cast<unsigned>(q[head + ent]);
+        if (ent < nb) pk = qs.read(list_off + head + ent, in_ring);
         const bool edge_ok = ((pk >> (24 + slot4)) & 1u) != 0;
         const int v = static_cast<int>(pk & 0xffffffu) + delta;
         unsigned w = 0;
         if (edge_ok) w = cw[v];
-        const bool pass = (w & kAlive) != 0;  // edge test passed, still unassigned, not yet activated
+        const bool pass = (w & kAliveW) != 0;  // edge test passed, still unassigned, not yet activated
         const unsigned pm = __ballot_sync(kFull, pass);
         // lanes of one queue entry have distinct targets: a clash needs passing lanes in two different nibbles.
-        // Then every candidate posts its lane number into the cell word's claim field with a shared-memory
-        // atomicMin (the rest of the word is identical for all of them) and the lowest lane -- the earliest in
-        // FIFO order -- finds itself there.  (match.any would do the same but costs ~250 cycles on this path.)
         const unsigned nib = (pm | (pm >> 1) | (pm >> 2) | (pm >> 3)) & 0x11111111u;
         bool win = pass;
         if (nib & (nib - 1u)) {
-          if (pass) atomicMin(&cw[v], (w & ~kClaimIdle) | my_claim);
-          __syncwarp();
-          if (pass) win = ((BIG_GLOBAL ? __ldcg(cw + v) : cw[v]) >> 21) == static_cast<unsigned>(lane);
+          if (!CW16) {
+            // every candidate posts its lane number into the cell word's claim field with a shared-memory atomicMin (the
+            // rest of the word is identical for all of them) and the lowest lane -- the earliest in FIFO order -- finds
+            // itself there.  (match.any would do the same but costs ~250 cycles on this path.)
+            unsigned* cw32 = reinterpret_cast<unsigned*>(cw);
+            if (pass) atomicMin(&cw32[v], (w & ~kClaimIdle) | my_claim);
+            __syncwarp();
+            if (pass) win = (cw32[v] >> 21) == static_cast<unsigned>(lane);
+          } else {
+            // no room for a claim field in 16-bit words: an earlier entry e2 reaches the same cell v through its slot s2
+            // exactly when its own cell is v's neighbour on the opposite side and that lane passed too
+            const int ucell = static_cast<int>(pk & 0xffffffu);
+            bool lose = false;
+#pragma unroll
+            for (int e2 = 0; e2 < 7; ++e2) {
+              const int u2 = __shfl_sync(kFull, ucell, 4 * e2);
+              const int d = u2 - v;
+              const unsigned p4 = (pm >> (4 * e2)) & 0xfu;
+              const bool hit = (d == nh && (p4 & 1u)) || (d == -nh && (p4 & 2u)) || (d == 1 && (p4 & 4u)) || (d == -1 && (p4 & 8u));
+              lose |= (e2 < ent) && hit;
+            }
+            win = pass && !lose;
+          }
         }
         const unsigned wm = __ballot_sync(kFull, win);
         // branch-free tail: lanes that did not win write to a private dummy word instead of skipping
-        const unsigned sl = w & 0xffffu;
+        const unsigned sl = w & kSlotMask;
         const bool other_bin = win && sl != static_cast<unsigned>(bslot);
-        int32_t* qdst = win ? q + tail + __popc(wm & lt_mask) : dummy + lane;
-        unsigned* cdst = win ? cw + v : reinterpret_cast<unsigned*>(dummy) + lane;
-        *qdst = v | static_cast<int>(((w >> 16) & 0xfu) << 24);
-        *cdst = w & ~kAlive;  // removePoint + unassigned_mask[v] = false (plane_extractor.cpp:324-325); claim idle again
+        const int wpos_q = list_off + tail + __popc(wm & lt_mask);
+        const int entry = v | static_cast<int>(((w >> kEdgeShift) & 0xfu) << 24);
+        word_t* cdst = win ? cw + v : reinterpret_cast<word_t*>(dummy + lane);
+        if (RING) {
+          unsigned* rdst = win ? qs.ring + (wpos_q & (kRing - 1)) : reinterpret_cast<unsigned*>(dummy) + lane;
+          *rdst = static_cast<unsigned>(entry);
+        } else {
+          int32_t* qdst = win ? list + wpos_q : dummy + lane;
+          *qdst = entry;
+        }
+        *cdst = static_cast<word_t>(w & ~kAliveW);  // removePoint + unassigned_mask[v] = false (plane_extractor.cpp:324-325); claim idle again
         same += (win && !other_bin) ? 1 : 0;
         atomicSub(other_bin ? hkey + sl : reinterpret_cast<unsigned*>(dummy) + lane, 1u << 15);
         tail += __popc(wm);
         head += nb;
         ++n_steps;
         __syncwarp();
+        if (RING && list_off + tail - flush_pos >= kFlush) flush_to(flush_pos + kFlush);
       }
       same = __reduce_add_sync(kFull, same);
       if (lane == 0) hkey[bslot] -= static_cast<unsigned>(same) << 15;
@@ -442,6 +626,11 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
       if (prof) { const long long t = clock64(); t_bfs += t - t_mark; t_mark = t; }
       if (static_cast<unsigned long long>(tail) < th.min_cells_activated) { __syncwarp(); continue; }  // :329-331
       if (n_regions < g.plane_cap) {
+        if (RING) {
+          flush_to(list_off + tail);
+          __threadfence_block();
+          __syncwarp();
+        }
         // publish the region to the accumulating warps
         if (lane == 0) {
           float* rec = rec_ptr(n_regions);
@@ -514,7 +703,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
   const long long t_grow_end = prof ? clock64() : 0;
   const int n_regions = misc[0];
 
-  // ---- labels_map_ starts at zero; cw becomes the per-cell segment label ------------------------------
+  // ---- labels_map_ starts at zero; cw becomes the per-cell segment label (<= 65535, fits either word size) ------
   for (int c = tid; c < C; c += kCtaThreads) cw[c] = 0;
 
   // ---- plane fit of every grown region, one thread per region (plane_extractor.cpp:333-343) -----------
@@ -573,10 +762,17 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
   for (int s = warp; s < nseg; s += kCtaWarps) {
     const float* rec = rec_ptr(s);
     const int off = __float_as_int(rec[kSegOff]), cnt = __float_as_int(rec[kSegCnt]);
-    for (int i = lane; i < cnt; i += 32) {
-      const int c = list[off + i] & 0xffffff;
-      cw[c] = static_cast<unsigned>(s + 1);
-      seg_label[c] = s + 1;
+    // (the list of a large frame is in global memory: four independent loads per round)
+    for (int i = lane; i < cnt; i += 128) {
+      int c4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) c4[u] = i + 32 * u < cnt ? (list[off + i + 32 * u] & 0xffffff) : -1;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (c4[u] >= 0) {
+          cw[c4[u]] = static_cast<word_t>(s + 1);
+          seg_label[c4[u]] = s + 1;
+        }
     }
   }
   __syncthreads();
@@ -584,7 +780,8 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
 
   // ---- getConnectedComponents (plane_extractor.cpp:430-453): upper-triangle adjacency bits --------------
   const int words = (nseg + 31) / 32;
-  unsigned* adj = reinterpret_cast<unsigned*>(members);  // [nseg][words], reuses the member runs
+  // [nseg][words]: reuses the member runs (mode 0) or the `pairs` scratch of this frame (the sort is long over)
+  unsigned* adj = ALL_SMEM ? reinterpret_cast<unsigned*>(members) : args.tables.pairs + 2 * fc;
   const bool adj_fits = static_cast<long long>(nseg) * words * 4 <= plan.adj_bytes;
   unsigned* rowbits = adj;  // fallback: one row at a time
   const int limit = (nv - 1) * nh;
@@ -760,7 +957,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
     o[1] = t_init;                     // setup
     o[2] = t_seed;                     // bin argmax + seed search (all seeds)
     o[3] = t_bfs;                      // BFS (all seeds)
-    o[4] = 0;                          // moment accumulation runs concurrently on the other warps
+    o[4] = t_wide;                     // part of [3] spent in wide BFS steps (mode 1)
     o[5] = t_fit_end - t_grow_end;     // plane fits + label painting
     o[6] = t_merge_end - t_fit_end;    // adjacency + merging
     o[7] = t_end - t_merge_end;        // final labels
@@ -771,48 +968,47 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
   }
 }
 
-// Shared-memory layout of the CTA kernel; bytes == 0 means "does not fit, use the generic kernel".
+// Shared-memory layout of the CTA kernel; bytes == 0 means "does not fit, try the next mode / the generic kernel".
 inline CtaPlan region_grow_cta_plan(const Geometry& g, const Thresholds& th, int mode) {
   CtaPlan p{};
   auto align16 = [](size_t v) { return (v + 15) & ~static_cast<size_t>(15); };
   const size_t B2 = static_cast<size_t>(th.histogram_bins_per_coord) * th.histogram_bins_per_coord;
   const size_t C = static_cast<size_t>(g.n_cells);
+  // small frames keep several CTAs per SM; large ones may take (almost) a whole SM's shared memory
+  const size_t limit = (mode == 0 ? 100u : 226u) * 1024;
   size_t off = 0;
   p.off_stage = static_cast<int>(off);   off = align16(off + static_cast<size_t>(kCtaWarps - 1) * 32 * 12 * 4);
   p.off_hkey = static_cast<int>(off);    off = align16(off + (B2 + 4) * 4);
   p.off_binslot = static_cast<int>(off); off = align16(off + B2 * 2);
-  p.off_binoff = static_cast<int>(off);  off = align16(off + B2 * 4);
-  p.off_runend = static_cast<int>(off);  off = align16(off + B2 * 4);
+  p.off_cursor = static_cast<int>(off);  off = align16(off + B2 * 4);
+  p.off_binend = static_cast<int>(off);  off = align16(off + B2 * 4);
+  p.off_cw = static_cast<int>(off);      off = align16(off + C * (mode == 3 ? 2 : 4));
   if (mode <= 1) {
-    p.off_cw = static_cast<int>(off);      off = align16(off + C * 4);
-    p.off_list = static_cast<int>(off);    off = align16(off + (C > B2 ? C : B2) * 4);
+    p.off_list = static_cast<int>(off);  off = align16(off + (C > B2 ? C : B2) * 4);
+  } else {
+    p.off_ring = static_cast<int>(off);  off = align16(off + kRing * 4);
   }
   if (mode == 0) {
-    p.off_members = static_cast<int>(off); off = align16(off + C * 4);
-    p.off_msem = static_cast<int>(off);    off = align16(off + C * 4);
-    p.adj_bytes = static_cast<int>(off - p.off_members);
+    p.off_keys = static_cast<int>(off);  off = align16(off + C * 8);  // member runs: cell ids + their MSE
   } else {
-    p.adj_bytes = static_cast<int>(C * 8);  // the `pairs` scratch of this frame
+    p.off_win = static_cast<int>(off);   off = align16(off + B2 * kWin * 8);
+    p.off_wpos = static_cast<int>(off);  off = align16(off + B2 * 4);
+    p.off_wend = static_cast<int>(off);  off = align16(off + B2 * 4);
   }
-  p.cache_cap = 0;
+  p.adj_bytes = static_cast<int>(C * 8);  // mode 0: the member runs; else the `pairs` scratch of this frame
   p.rec_cap = g.plane_cap < 128 ? g.plane_cap : 128;
   p.off_recs = static_cast<int>(off);    off = align16(off + static_cast<size_t>(p.rec_cap) * kRecFloats * 4);
-  p.off_merge = static_cast<int>(off);   off = align16(off + static_cast<size_t>(g.plane_cap) * 4);
   p.off_misc = static_cast<int>(off);    off = align16(off + (32 + 32) * 4);
-  if (mode != 0) {
-    // whatever shared memory is left (up to 8 bytes per cell) caches the member runs of the small bins: the one-cell
-    // regions that dominate noisy frames are seeded from those, and their searches then stay out of global memory
-    const size_t limit = 220u * 1024;
-    const size_t room = off + 64 < limit ? (limit - off - 64) / 8 : 0;
-    const size_t cap = room < C ? (room / 32) * 32 : C;
-    p.cache_cap = static_cast<int>(cap);
-    p.off_cmem = static_cast<int>(off);  off = align16(off + cap * 4);
-    p.off_cmse = static_cast<int>(off);  off = align16(off + cap * 4);
+  // merge labels last: in shared memory when there is room, else the kernel works on the global merge table
+  const size_t merge_bytes = static_cast<size_t>(g.plane_cap) * 4;
+  if (mode == 0 || off + merge_bytes <= limit) {
+    p.merge_smem = 1;
+    p.off_merge = static_cast<int>(off);
+    off = align16(off + merge_bytes);
   }
-  // small frames keep several CTAs per SM; large ones may take (almost) a whole SM's shared memory
-  p.bytes = off <= (mode == 0 ? 100u : 220u) * 1024 ? off : 0;
-  // mode 2 keeps the queue in global memory, where the raw histogram of the setup needs B2 words (C >= B2 or not)
-  if (mode == 2 && C < B2) p.bytes = 0;
+  p.bytes = off <= limit ? off : 0;
+  // 16-bit cell words hold the bin id / histogram slot in 10 bits
+  if (mode == 3 && B2 > 1024) p.bytes = 0;
   return p;
 }
 

@@ -254,6 +254,13 @@ class PlaneExtractor:
             ("merge_label", "i4")]))[:n.value]
         return rec.copy()
 
+    def seed_order(self, frame=0):
+        """(n_cells,) uint64 keys [bin:15][MSE order:32][cell:17] of the frame's cells in seed order (dpx_get_seed_order)."""
+        n = self.info.n_cells
+        out = np.empty(max(n, 1), dtype=np.uint64)
+        self._check(self._lib.dpx_get_seed_order(self._h, frame, out.ctypes.data, n))
+        return out[:n]
+
     # ---- measurement ----------------------------------------------------------------------------------
     def set_profiling(self, enabled):
         self._check(self._lib.dpx_set_profiling(self._h, 1 if enabled else 0))
@@ -267,7 +274,7 @@ class PlaneExtractor:
         """Cycle counters of the region-growing stage for one frame of the last profiled batch."""
         buf = (C.c_int64 * 12)()
         self._check(self._lib.dpx_get_region_profile(self._h, frame, C.byref(buf)))
-        names = ("total", "init", "seed", "bfs", "accumulate", "fit", "merge", "final", "n_seeds", "n_steps",
+        names = ("total", "init", "seed", "bfs", "wide", "fit", "merge", "final", "n_seeds", "n_steps",
                  "n_regions", "n_segments")
         return dict(zip(names, [int(x) for x in buf]))
 
@@ -279,6 +286,11 @@ class PlaneExtractor:
         the caller's buffer is int32 either way; dpx_set_label_transport)."""
         m = {"auto": _capi.LABELS_AUTO, "i32": _capi.LABELS_I32, "u16": _capi.LABELS_U16}[mode]
         self._check(self._lib.dpx_set_label_transport(self._h, m))
+
+    def set_rng_compat(self, which):
+        """'libstdc++11' (default) | 'libstdc++10': which std::uniform_int_distribution mapping the RANSAC refinement's
+        sampling reproduces (dpx_set_rng_compat)."""
+        self._check(self._lib.dpx_set_rng_compat(self._h, {"libstdc++11": 0, "libstdc++10": 1}[which]))
 
     @classmethod
     def _borrow(cls, handle, height, width):

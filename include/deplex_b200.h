@@ -158,6 +158,10 @@ DPX_API dpx_status dpx_process_depth_batch_device(dpx_extractor* ex, const uint1
  * a device-resident call keeps all of its frames. */
 DPX_API dpx_status dpx_get_cells(dpx_extractor* ex, int32_t frame, dpx_cell* out, int32_t capacity);
 DPX_API dpx_status dpx_get_planes(dpx_extractor* ex, int32_t frame, dpx_plane* out, int32_t capacity, int32_t* n_planes);
+/* The seed order of one frame (n_cells entries): its cells sorted by the key [bin : 15][MSE as order-preserving
+ * uint32 : 32][cell id : 17]; cells that are not planar carry the largest bin and MSE fields and come last.  createPlaneSegments' seed of a
+ * bin (first strict-minimum MSE, plane_extractor.cpp:309-316) is the first entry of the bin's run that is still unassigned. */
+DPX_API dpx_status dpx_get_seed_order(dpx_extractor* ex, int32_t frame, uint64_t* out, int32_t capacity);
 
 /* ---- measurement: CUDA-event time of each stage of the last dpx_process_batch_device call ---- */
 DPX_API dpx_status dpx_set_profiling(dpx_extractor* ex, int32_t enabled);
@@ -170,6 +174,16 @@ DPX_API dpx_status dpx_get_stage_ms(dpx_extractor* ex, float ms[DPX_N_STAGES]);
 DPX_API dpx_status dpx_get_region_profile(dpx_extractor* ex, int32_t frame, int64_t out[DPX_REGION_PROFILE_SLOTS]);
 /* Number of kernels launched by this handle since creation. */
 DPX_API int64_t dpx_kernel_launches(const dpx_extractor* ex);
+
+/* ---- which standard library the RANSAC refinement's sampling reproduces ----
+ * refineLabels draws its 3-point samples with std::uniform_int_distribution<int> over a default-seeded std::mt19937
+ * (libs/rtl/include/rtl/RANSAC.hpp:81-87,107-111).  The generator is fixed by the C++ standard; the distribution's
+ * mapping is not, and libstdc++ changed it in GCC 11 (Lemire multiply-shift; before: scaling + rejection).  The refined
+ * labels depend on it.  Default: DPX_RNG_LIBSTDCXX11, what a reference built with GCC >= 11 produces (and what the oracle
+ * is checked against on this toolchain); DPX_RNG_LIBSTDCXX10 reproduces binaries built with GCC <= 10 (e.g. manylinux2014
+ * wheels, .github/workflows/wheels.yml:10).  Environment DPX_RNG_COMPAT=libstdc++10 sets the default of new handles. */
+enum { DPX_RNG_LIBSTDCXX11 = 0, DPX_RNG_LIBSTDCXX10 = 1 };
+DPX_API dpx_status dpx_set_rng_compat(dpx_extractor* ex, int32_t mode);
 
 /* ---- narrow labels on the host-pointer path ----
  * The reference returns int32 labels (Eigen::VectorXi, plane_extractor.h:48) and so do the entry points above.  Labels

@@ -400,3 +400,35 @@ def test_capi_argument_errors_on_device():
     ms = (C.c_float * _capi.N_STAGES)()
     assert lib.dpx_get_stage_ms(ex._h, C.byref(ms)) == _capi.DPX_ERR_ARGUMENT                 # profiling was never enabled
     assert lib.dpx_process_host(None, None, 0, LAYOUT_ROWMAJOR, None) == _capi.DPX_ERR_ARGUMENT
+
+
+@pytest.mark.parametrize("hw,patch", [((480, 640), 4), ((720, 1280), 10), ((1080, 1920), 8), ((1080, 1920), 5)])
+def test_seed_order_is_the_sorted_cell_list(hw, patch):
+    """seed_sort_kernel: the cells of a frame sorted by (bin, MSE, cell id) -- shared-memory and global-memory variants --
+    against numpy's lexsort over the per-cell table of the same frame."""
+    import torch
+    from deplex_b200 import Config, PlaneExtractor, synth, LAYOUT_ROWMAJOR
+    h, w = hw
+    ex = PlaneExtractor(h, w, Config(patch_size=patch), max_batch=2)
+    batch = synth.make_batch(h, w, 4300, 2, "rowmajor")
+    ex.process_batch_device(torch.from_numpy(batch).cuda(), LAYOUT_ROWMAJOR)
+    for f in range(2):
+        cells = ex.cells(f)
+        keys = ex.seed_order(f)
+        planar = cells["bin"] >= 0
+        n = int(planar.sum())
+        # cells that are not planar: largest bin / MSE fields, in cell order, behind everything
+        rest = np.nonzero(~planar)[0].astype(np.uint64)
+        assert np.array_equal(keys[n:], (np.uint64(0x7fff) << np.uint64(49)) | (np.uint64(0xffffffff) << np.uint64(17)) | rest)
+        mse_bits = cells["mse"].view(np.uint32).astype(np.uint64)
+        assert (cells["mse"][planar] >= 0).all()
+        order_key = mse_bits ^ np.uint64(0x80000000)  # non-negative floats: flip the sign bit
+        full = (cells["bin"].astype(np.int64).astype(np.uint64) << np.uint64(49)) | (order_key << np.uint64(17)) | np.arange(len(cells), dtype=np.uint64)
+        want = np.sort(full[planar])
+        assert np.array_equal(keys[:n], want)
+    # small frames are grown without a sort (a minimum scan over the bin's members is cheaper there)
+    from deplex_b200 import UnsupportedError
+    small = PlaneExtractor(480, 640, Config(), max_batch=1)
+    small.process_batch_device(torch.from_numpy(synth.make_batch(480, 640, 1, 1, "rowmajor")).cuda(), LAYOUT_ROWMAJOR)
+    with pytest.raises(UnsupportedError):
+        small.seed_order(0)

@@ -64,3 +64,28 @@ def test_refinement_fine_grid_and_fhd(oracle_mod):
         labels = PlaneExtractor(h, w, cfg).process(xyz)
         ref = oracle_mod.process(h, w, to_oracle_cfg(oracle_mod, cfg), xyz)
         assert np.array_equal(labels, ref), f"{h}x{w}/p{patch}: {(labels != ref).sum()} pixels differ ({time.time() - t0:.1f}s)"
+
+
+def test_refinement_with_pre_gcc11_uniform_int_mapping(oracle_mod):
+    """ADVICE r01: std::uniform_int_distribution is implementation-defined.  With dpx_set_rng_compat(libstdc++10) the
+    kernel reproduces the oracle's explicit restatement of the GCC <= 10 mapping (scaling + rejection), for the tape fast
+    path and the sequential fallback alike; the default stays the GCC >= 11 mapping."""
+    from deplex_b200 import Config, PlaneExtractor
+    for name in ("tum", "icl"):
+        xyz, ini = frame_cloud(name)
+        cfg = Config(ini, ransac_refinement=1)
+        ocfg = to_oracle_cfg(oracle_mod, cfg)
+        ex = PlaneExtractor(480, 640, cfg)
+        default = ex.process(xyz)
+        assert np.array_equal(default, oracle_mod.process(480, 640, ocfg, xyz))
+        ex.set_rng_compat("libstdc++10")
+        legacy = ex.process(xyz)
+        try:
+            oracle_mod.set_uniform_int_variant(1)
+            want = oracle_mod.process(480, 640, ocfg, xyz)
+        finally:
+            oracle_mod.set_uniform_int_variant(0)
+        assert np.array_equal(legacy, want)
+        assert (legacy != default).any()
+        ex.set_rng_compat("libstdc++11")
+        assert np.array_equal(ex.process(xyz), default)
