@@ -44,7 +44,6 @@ constexpr unsigned kAlive = 1u << 20;
 constexpr unsigned kClaimIdle = 0x7ffu << 21;
 constexpr int kRecFloats = kSegFloats;  // region / plane records use the segs layout
 
-constexpr int kWin = 8;        // modes 1/2: sorted-key entries cached per bin in shared memory
 constexpr int kRing = 1024;    // modes 1/2: most recent queue entries mirrored in shared memory (power of two)
 
 struct CtaPlan {
@@ -53,6 +52,7 @@ struct CtaPlan {
   int rec_cap;       // region / plane records held in shared memory (the rest spill to the global segs table)
   int adj_bytes;     // bytes available to the adjacency bit matrix
   int merge_smem;    // merge labels in shared memory (else in the global merge table)
+  int win;           // sorted-key entries cached per bin in shared memory (32, 16 or 8: what fits)
   size_t bytes;
 };
 
@@ -219,7 +219,8 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
   int* bin_off = bin_end;  // mode 0: start of the bin's member run
   int* run_end = cursor;   // mode 0: end of its still-unassigned members
   const float* mse_g = args.tables.mse + fc;
-  unsigned long long* win = reinterpret_cast<unsigned long long*>(smem + plan.off_win);       // modes 1/2: [K][kWin]
+  unsigned long long* win = reinterpret_cast<unsigned long long*>(smem + plan.off_win);       // sorted modes: [K][plan.win]
+  const int kw = plan.win;                                                   // entries per window
   int* wpos = reinterpret_cast<int*>(smem + plan.off_wpos);                  // modes 1/2: [K] sorted position of win[slot][0]
   int* wend = reinterpret_cast<int*>(smem + plan.off_wend);                  // modes 1/2: [K] end of the window's valid entries
   float* recs = reinterpret_cast<float*>(smem + plan.off_recs);              // [rec_cap][24]
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
                 // the bin's window in shared memory holds sorted entries [wb, we)
                 const int i = pos + lane;
                 const bool in = i < we;
-                const unsigned long long k = in ? win[bslot * kWin + (i - wb)] : 0ull;
+                const unsigned long long k = in ? win[bslot * kw + (i - wb)] : 0ull;
                 const int c = static_cast<int>(k & kSeedCellMask);
                 const bool alive = in && (cw[c] & kAliveW) != 0;
                 const unsigned am = __ballot_sync(kFull, alive);
@@ -488,10 +489,10 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
                 const int i = pos + 32 * u + lane;
-                if (i > fpos && i <= fpos + kWin && i < loaded_end) win[bslot * kWin + (i - fpos - 1)] = k[u];
+                if (i > fpos && i <= fpos + kw && i < loaded_end) win[bslot * kw + (i - fpos - 1)] = k[u];
               }
               wb = fpos + 1;
-              we = min(fpos + 1 + kWin, loaded_end);
+              we = min(fpos + 1 + kw, loaded_end);
               if (lane == 0) {
                 wpos[bslot] = wb;
                 wend[bslot] = we;
@@ -969,7 +970,17 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
 }
 
 // Shared-memory layout of the CTA kernel; bytes == 0 means "does not fit, try the next mode / the generic kernel".
+inline CtaPlan region_grow_cta_plan_w(const Geometry& g, const Thresholds& th, int mode, int win);
 inline CtaPlan region_grow_cta_plan(const Geometry& g, const Thresholds& th, int mode) {
+  if (mode == 0) return region_grow_cta_plan_w(g, th, 0, 0);
+  // the widest key window per bin that fits: a window serves that many seeds of a bin per trip to the L2
+  for (int win = 32; win >= 8; win /= 2) {
+    const CtaPlan p = region_grow_cta_plan_w(g, th, mode, win);
+    if (p.bytes > 0) return p;
+  }
+  return CtaPlan{};
+}
+inline CtaPlan region_grow_cta_plan_w(const Geometry& g, const Thresholds& th, int mode, int win) {
   CtaPlan p{};
   auto align16 = [](size_t v) { return (v + 15) & ~static_cast<size_t>(15); };
   const size_t B2 = static_cast<size_t>(th.histogram_bins_per_coord) * th.histogram_bins_per_coord;
@@ -991,7 +1002,8 @@ inline CtaPlan region_grow_cta_plan(const Geometry& g, const Thresholds& th, int
   if (mode == 0) {
     p.off_keys = static_cast<int>(off);  off = align16(off + C * 8);  // member runs: cell ids + their MSE
   } else {
-    p.off_win = static_cast<int>(off);   off = align16(off + B2 * kWin * 8);
+    p.win = win;
+    p.off_win = static_cast<int>(off);   off = align16(off + B2 * static_cast<size_t>(win) * 8);
     p.off_wpos = static_cast<int>(off);  off = align16(off + B2 * 4);
     p.off_wend = static_cast<int>(off);  off = align16(off + B2 * 4);
   }
