@@ -410,6 +410,12 @@ def sharded_sequence(a, dev, rank, world, lay, barrier, all_reduce_max):
     barrier()
     ms = all_reduce_max(e0.elapsed_time(e1))
     launches = pipe.kernel_launches() - launches0
+    if world > 1:
+        # NCCL sets up its point-to-point channels on first use: one small exchange of the same pattern first
+        warm = torch.zeros((world, 8), dtype=torch.int32, device=dev)
+        sharding.gather_labels(warm[rank:rank + 1], world, dst=0, out=warm if rank == 0 else None)
+        torch.cuda.synchronize()
+        barrier()
     t0 = time.perf_counter()
     full = sharding.gather_labels(local, T, dst=0, out=result)
     torch.cuda.synchronize()
