@@ -3,7 +3,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdeplex_b200.so")
+# DPX_LIB_PATH: an explicit alternative build of the same library (the debug build with the kernels' own bounds checks,
+# `make -C deplex_b200/csrc debug`); there is still no fallback of any kind
+LIB_PATH = os.environ.get("DPX_LIB_PATH") or os.path.join(_HERE, "libdeplex_b200.so")
 
 DPX_OK, DPX_ERR_RUNTIME, DPX_ERR_UNSUPPORTED, DPX_ERR_CUDA, DPX_ERR_ARGUMENT = range(5)
 LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR = 0, 1

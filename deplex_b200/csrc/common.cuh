@@ -13,6 +13,23 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+// Bounds / invariant checks of the debug build (make -C deplex_b200/csrc debug -> libdeplex_b200_dbg.so, loaded through
+// DPX_LIB_PATH).  compute-sanitizer is not available on the B200 pool this was developed on, so the kernels with
+// data-dependent indexing (region growing, seed sort, labeling) carry their own checks: a violated one prints the
+// expression and traps, which surfaces as a CUDA error on the host.  Compiled out of the product build.
+#ifdef DPX_DEBUG_CHECKS
+#include <cstdio>
+#define DPX_CHECK(cond)                                                                                   \
+  do {                                                                                                    \
+    if (!(cond)) {                                                                                        \
+      printf("DPX_CHECK failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__, blockIdx.x, threadIdx.x); \
+      __trap();                                                                                           \
+    }                                                                                                     \
+  } while (0)
+#else
+#define DPX_CHECK(cond) do { } while (0)
+#endif
+
 namespace dpx {
 
 constexpr int kLayoutColMajor = 0;

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(kLabelThreads) labeling_kernel(const LabelArgs
   int32_t* out = args.labels + static_cast<long long>(frame) * g.n_points +
                  static_cast<long long>(cell_row) * p * g.width + col;
 
+  DPX_CHECK(frame >= 0 && frame < args.n_frames && cell_row < g.nv);
   int cq = col / p;
   int rem = col - cq * p;
   int lab[4];

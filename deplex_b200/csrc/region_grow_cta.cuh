@@ -102,7 +102,7 @@ __device__ long long g_wide_probe[8];
 #endif
 template <bool RING>
 __device__ __noinline__ int2 bfs_wide_step(const QueueT<RING> qs, int base, unsigned* cw, unsigned* hkey, int32_t* sink, int head,
-                                           int tail, int lane, int nh, int bslot) {
+                                           int tail, int lane, int nh, int bslot, int n_cells) {
 #ifdef DPX_BFS_PROBE
   long long wp_t = clock64();
 #endif
@@ -118,6 +118,7 @@ __device__ __noinline__ int2 bfs_wide_step(const QueueT<RING> qs, int base, unsi
   for (int sl4 = 0; sl4 < 4; ++sl4) {
     const int dl = (sl4 == 0) ? -nh : (sl4 == 1) ? nh : (sl4 == 2) ? -1 : 1;
     vv[sl4] = u + dl;
+    DPX_CHECK(!((pk >> (24 + sl4)) & 1u) || (vv[sl4] >= 0 && vv[sl4] < n_cells));
     ww[sl4] = ((pk >> (24 + sl4)) & 1u) ? cw[vv[sl4]] : 0u;
     if (ww[sl4] & kAlive) passm |= 1u << sl4;
   }
@@ -142,6 +143,7 @@ __device__ __noinline__ int2 bfs_wide_step(const QueueT<RING> qs, int base, unsi
   const unsigned b0 = __ballot_sync(kFull, nwin & 1u), b1 = __ballot_sync(kFull, nwin & 2u), b2 = __ballot_sync(kFull, nwin & 4u);
   int pos = tail + __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
   const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+  DPX_CHECK(base + tail + total <= n_cells);
   WIDE_PROBE(2);
   int same = 0;
   // branch-free: slots that did not win write to a private sink (see the narrow step)
@@ -446,7 +448,8 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
                 // the bin's window in shared memory holds sorted entries [wb, we)
                 const int i = pos + lane;
                 const bool in = i < we;
-                const unsigned long long k = in ? win[bslot * kw + (i - wb)] : 0ull;
+                DPX_CHECK(!in || (i - wb >= 0 && i - wb < kw && i < C));
+              const unsigned long long k = in ? win[bslot * kw + (i - wb)] : 0ull;
                 const int c = static_cast<int>(k & kSeedCellMask);
                 const bool alive = in && (cw[c] & kAliveW) != 0;
                 const unsigned am = __ballot_sync(kFull, alive);
@@ -466,7 +469,8 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
                 const int i = pos + 32 * u + lane;
-                k[u] = i < end ? __ldg(skeys_g + i) : 0ull;
+                DPX_CHECK(end <= C);
+              k[u] = i < end ? __ldg(skeys_g + i) : 0ull;
               }
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
@@ -508,6 +512,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
       // no candidate with mse < INT_MAX: the reference reads an uninitialised seed id here.  (double)lm < 2147483647.0
       // is lm < 2^31 for a float: the largest float below 2^31 is 2^31 - 128.
       if (seed == kNoSeed || !(lm < 2147483648.0f)) break;
+      DPX_CHECK(seed >= 0 && seed < C && (cw[seed] & kAliveW) != 0 && bslot < misc[4] && list_off < C);
       if (prof) { const long long t = clock64(); t_seed += t - t_mark; t_mark = t; ++n_seeds; }
 
       // growSeed (plane_extractor.cpp:349-392): batched FIFO BFS into list[list_off ...)
@@ -550,7 +555,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
         // (32-bit words of large frames only: the instantiation for small frames keeps the narrow step's tighter code)
         if ((MODE == 1 || MODE == 2) && tail - head > kWideThreshold) {
           const long long tw0 = prof ? clock64() : 0;
-          const int2 r = bfs_wide_step<RING>(qs, list_off, reinterpret_cast<unsigned*>(cw), hkey, dummy, head, tail, lane, nh, bslot);
+          const int2 r = bfs_wide_step<RING>(qs, list_off, reinterpret_cast<unsigned*>(cw), hkey, dummy, head, tail, lane, nh, bslot, C);
           head += min(32, tail - head);
           tail += r.x;
           same += r.y;
@@ -567,6 +572,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
         const bool edge_ok = ((pk >> (24 + slot4)) & 1u) != 0;
         const int v = static_cast<int>(pk & 0xffffffu) + delta;
         unsigned w = 0;
+        DPX_CHECK(!edge_ok || (v >= 0 && v < C));
         if (edge_ok) w = cw[v];
         const bool pass = (w & kAliveW) != 0;  // edge test passed, still unassigned, not yet activated
         const unsigned pm = __ballot_sync(kFull, pass);
@@ -603,6 +609,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
         const unsigned sl = w & kSlotMask;
         const bool other_bin = win && sl != static_cast<unsigned>(bslot);
         const int wpos_q = list_off + tail + __popc(wm & lt_mask);
+        DPX_CHECK(!win || (wpos_q < C && (w & kSlotMask) < static_cast<unsigned>(misc[4])));
         const int entry = v | static_cast<int>(((w >> kEdgeShift) & 0xfu) << 24);
         word_t* cdst = win ? cw + v : reinterpret_cast<word_t*>(dummy + lane);
         if (RING) {
@@ -626,6 +633,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
       remaining -= tail;
       if (prof) { const long long t = clock64(); t_bfs += t - t_mark; t_mark = t; }
       if (static_cast<unsigned long long>(tail) < th.min_cells_activated) { __syncwarp(); continue; }  // :329-331
+      DPX_CHECK(list_off + tail <= C && remaining >= 0);
       if (n_regions < g.plane_cap) {
         if (RING) {
           flush_to(list_off + tail);

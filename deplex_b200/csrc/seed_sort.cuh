@@ -218,7 +218,11 @@ __global__ void __launch_bounds__(kSortThreads) seed_chunk_sort_kernel(const int
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < kSortItems; ++j)
-      if (valid[j]) nxt[s.sub_offs[j][dg[j]] + s.wrank[j * kSortWarps + warp][dg[j]] + rank[j]] = key[j];
+      if (valid[j]) {
+        const uint32_t o = s.sub_offs[j][dg[j]] + s.wrank[j * kSortWarps + warp][dg[j]] + rank[j];
+        DPX_CHECK(o < static_cast<uint32_t>(n));
+        nxt[o] = key[j];
+      }
     SORT_PROBE(4);  // scatter
     __syncthreads();
     unsigned long long* t = cur;
@@ -254,6 +258,7 @@ __global__ void __launch_bounds__(kMergeThreads) seed_rank_merge_kernel(const un
     }
     pos += lo;
   }
+  DPX_CHECK(pos >= 0 && pos < n_cells);
   keys_out[fc + pos] = key;
 }
 
