@@ -432,3 +432,23 @@ def test_seed_order_is_the_sorted_cell_list(hw, patch):
     small.process_batch_device(torch.from_numpy(synth.make_batch(480, 640, 1, 1, "rowmajor")).cuda(), LAYOUT_ROWMAJOR)
     with pytest.raises(UnsupportedError):
         small.seed_order(0)
+
+
+# cells whose fit outputs (normal, d, mse, score) are not bit-identical to the oracle's although their moments are:
+# the only source is CUDA's fp64 sin / cos / atan2 differing from glibc's in the last ulp inside the 3x3 eigensolver.
+# Pinned per frame so that a drift of either libm (or of the kernel) shows up here long before a label flips.
+_LAST_ULP_CELLS = {"tum": 2, "icl": 10}  # observed on the B200 (CUDA 12.9 libdevice vs glibc 2.39): 0 and 5
+
+
+@pytest.mark.parametrize("name", ["tum", "icl"])
+def test_last_ulp_fit_differences_are_counted(oracle_mod, name):
+    from deplex_b200 import Config, PlaneExtractor
+    xyz, ini = frame_cloud(name)
+    cfg = Config(ini)
+    ex = PlaneExtractor(480, 640, cfg)
+    ex.process(xyz)
+    _, dbg = oracle_mod.process(480, 640, to_oracle_cfg(oracle_mod, cfg), xyz, debug=True)
+    report = _compare_cells(ex.cells(0), dbg)
+    differing = max(report[k] for k in ("normal", "d", "mse", "score"))
+    print(f"{name}: cells with last-ulp fit differences: {report}")
+    assert differing <= _LAST_ULP_CELLS[name], report
