@@ -267,8 +267,34 @@ def latency_mode(dev, calls, cpu_base):
                                    "sample": f"{n_cpu} process() calls on this frame, 1 thread (methodology of "
                                              f"examples/process_cloud.cpp:24-36), {dt:.1f} s"}
             rec["speedup_vs_cpu"] = {"host_ptr": rec["host_ptr_fps"] / v, "device_resident": rec["device_resident_fps"] / v}
-        out[name] = rec
         ex.close()
+        # the same frame with the shipped ini's RANSAC refinement switched on (plane_extractor.cpp:265-267, 472-509): stage 4
+        rcfg = Config(os.path.join(golden, cfgname + ".ini"), ransac_refinement=1)
+        rex = PlaneExtractor(h, w, rcfg, device=dev.index)
+        for _ in range(3):
+            rex.process_batch_device(d_xyz, LAYOUT_ROWMAJOR, d_lab)
+        torch.cuda.synchronize()
+        rex.set_profiling(True)
+        racc, n_ref = {}, 10
+        for _ in range(n_ref):
+            rex.process_batch_device(d_xyz, LAYOUT_ROWMAJOR, d_lab)
+            torch.cuda.synchronize()
+            for kk, v in rex.stage_ms().items():
+                racc[kk] = racc.get(kk, 0.0) + v / n_ref
+        rex.set_profiling(False)
+        labelled = int((d_lab != 0).sum().item())
+        rrec = {"refine_ms": racc["refine"], "device_resident_us": sum(racc.values()) * 1e3,
+                "labelled_pixels_after": labelled,
+                "note": "stage 4 is latency-bound (hundreds of rounds of 32 hypotheses, three cluster barriers each), not "
+                        "bandwidth-bound: each round re-reads the label's points (12 B each) from L2"}
+        if cpu_base:
+            v, dt, kind = cpu_path(h, w, oracle_config_like(rcfg), cloud[None], 1, 1, passes=30)
+            rrec["cpu_baseline"] = {"value": v, "unit": UNIT, "us_per_frame": 1e6 / v, "cores": 1, "kind": kind,
+                                    "sample": f"30 process() calls on this frame with ransacRefinement=1, 1 thread, {dt:.1f} s"}
+            rrec["speedup_vs_cpu"] = (1e6 / rrec["device_resident_us"]) / v
+        rex.close()
+        rec["with_refinement"] = rrec
+        out[name] = rec
     return out
 
 

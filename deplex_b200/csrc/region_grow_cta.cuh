@@ -817,6 +817,35 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
 
   // ---- findMergedLabels (plane_extractor.cpp:402-423) ---------------------------------------------------
   const double min_cos = static_cast<double>(th.min_cos_angle_merge);
+  // The merge loop is sequential over the rows, but almost all of its work is not: row r tests plane a = merge[r] against
+  // its adjacent planes t > r with a's normal as it was when the row started and with t's record, which nothing has
+  // touched yet (t > r has not been anybody's target).  While a == r -- plane r has not been merged into an earlier one --
+  // that normal is r's original one too, so those tests are evaluated for all rows up front by all threads (pass0);
+  // the loop then only walks the bits that passed.  Rows whose plane was merged away earlier (a < r: a's record has been
+  // refit since) are tested live, as the reference does.
+  const bool pre_ok = nseg > 1 && adj_fits && 2ll * nseg * words * 4 <= plan.adj_bytes;
+  unsigned* pass0 = adj + nseg * words;
+  if (pre_ok) {
+    for (int i = tid; i < nseg * words; i += kCtaThreads) {
+      const int r = i / words, w = i - r * words;
+      unsigned bits = adj[i], out = 0;
+      if (bits) {
+        const float* rr = rec_ptr(r);
+        const float an0 = rr[kSegNormal], an1 = rr[kSegNormal + 1], an2 = rr[kSegNormal + 2], ad = rr[kSegD];
+        while (bits) {
+          const int b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const float* rt = rec_ptr(w * 32 + b);
+          const double cos_angle = static_cast<double>(dot3(an0, an1, an2, rt[kSegNormal], rt[kSegNormal + 1], rt[kSegNormal + 2]));
+          const float df = __fadd_rn(dot3(an0, an1, an2, rt[kSegMean], rt[kSegMean + 1], rt[kSegMean + 2]), ad);
+          const double distance = __dmul_rn(static_cast<double>(df), static_cast<double>(df));
+          if (cos_angle > min_cos && distance < static_cast<double>(th.max_merge_dist)) out |= 1u << b;
+        }
+      }
+      pass0[i] = out;
+    }
+    __syncthreads();
+  }
   if (nseg > 1) {
     for (int r = 0; r < nseg; ++r) {
       if (!adj_fits) {
@@ -842,12 +871,13 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
         __syncthreads();
       }
       if (warp != 0) continue;
-      const unsigned* row = adj_fits ? adj + r * words : rowbits;
+      const int a = merge[r];
+      const bool pretested = pre_ok && a == r;
+      const unsigned* row = pretested ? pass0 + r * words : adj_fits ? adj + r * words : rowbits;
       bool any = false;
       for (int w = lane; w < words; w += 32) any |= row[w] != 0;
       if (!__any_sync(kFull, any)) continue;
 
-      const int a = merge[r];
       float* ra = rec_ptr(a);
       Moments ma;
       ma.n = __float_as_int(ra[kSegN]);
@@ -864,10 +894,14 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
           const int t = w * 32 + __ffs(bits) - 1;
           bits &= bits - 1;
           const float* rt = rec_ptr(t);
-          const double cos_angle = static_cast<double>(dot3(an0, an1, an2, rt[kSegNormal], rt[kSegNormal + 1], rt[kSegNormal + 2]));
-          const float df = __fadd_rn(dot3(an0, an1, an2, rt[kSegMean], rt[kSegMean + 1], rt[kSegMean + 2]), ad);
-          const double distance = __dmul_rn(static_cast<double>(df), static_cast<double>(df));
-          if (cos_angle > min_cos && distance < static_cast<double>(th.max_merge_dist)) {
+          bool pass = pretested;
+          if (!pretested) {
+            const double cos_angle = static_cast<double>(dot3(an0, an1, an2, rt[kSegNormal], rt[kSegNormal + 1], rt[kSegNormal + 2]));
+            const float df = __fadd_rn(dot3(an0, an1, an2, rt[kSegMean], rt[kSegMean + 1], rt[kSegMean + 2]), ad);
+            const double distance = __dmul_rn(static_cast<double>(df), static_cast<double>(df));
+            pass = cos_angle > min_cos && distance < static_cast<double>(th.max_merge_dist);
+          }
+          if (pass) {
             ma.n += __float_as_int(rt[kSegN]);
 #pragma unroll
             for (int i = 0; i < 3; ++i) ma.s[i] = __fadd_rn(ma.s[i], rt[kSegS + i]);
