@@ -108,8 +108,19 @@ __device__ __noinline__ int2 bfs_wide_step(const QueueT<RING> qs, int base, unsi
 #endif
   const int nbw = min(32, tail - head);
   const bool in_ring = tail - head <= kRing - 128;
+  // (the list pointer reaches this out-of-line function as a generic pointer: when the list is in shared memory, address it
+  // as such -- a generic load / store is slower and, for a lone warp, that is latency on the chain)
+  const unsigned list_s = RING ? 0u : static_cast<unsigned>(__cvta_generic_to_shared(qs.list + base));
+  const unsigned ring_s = RING ? static_cast<unsigned>(__cvta_generic_to_shared(qs.ring)) : 0u;
   unsigned pk = 0;
-  if (lane < nbw) pk = qs.read(base + head + lane, in_ring);
+  if (RING) {
+    if (lane < nbw) {
+      if (in_ring) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pk) : "r"(ring_s + 4u * static_cast<unsigned>((base + head + lane) & (kRing - 1))));
+      else pk = static_cast<unsigned>(__ldcg(qs.list + base + head + lane));
+    }
+  } else {
+    if (lane < nbw) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pk) : "r"(list_s + 4u * static_cast<unsigned>(head + lane)));
+  }
   const int u = static_cast<int>(pk & 0xffffffu);
   int vv[4];
   unsigned ww[4];
@@ -126,10 +137,11 @@ __device__ __noinline__ int2 bfs_wide_step(const QueueT<RING> qs, int base, unsi
   WIDE_PROBE(0);
   unsigned winm = passm;
   if (anyp & (anyp - 1u)) {  // at least two entries have candidates: they may clash
+    // (branch-free: a slot without a candidate posts into the lane's private sink)
 #pragma unroll
     for (int sl4 = 0; sl4 < 4; ++sl4)
-      if (passm & (1u << sl4))
-        atomicMin(&cw[vv[sl4]], (ww[sl4] & ~kClaimIdle) | (static_cast<unsigned>(lane * 4 + sl4) << 21));
+      atomicMin((passm & (1u << sl4)) ? &cw[vv[sl4]] : reinterpret_cast<unsigned*>(sink) + lane,
+                (ww[sl4] & ~kClaimIdle) | (static_cast<unsigned>(lane * 4 + sl4) << 21));
     __syncwarp();
 #pragma unroll
     for (int sl4 = 0; sl4 < 4; ++sl4)
@@ -156,11 +168,13 @@ __device__ __noinline__ int2 bfs_wide_step(const QueueT<RING> qs, int base, unsi
     unsigned* cdst = won ? cw + vv[sl4] : reinterpret_cast<unsigned*>(sink) + lane;
     if (RING) {
       // large frames: the step writes the shared-memory ring only; the caller copies the ring to the global list in bulk
-      unsigned* rdst = won ? qs.ring + ((base + pos) & (kRing - 1)) : reinterpret_cast<unsigned*>(sink) + lane;
-      *rdst = static_cast<unsigned>(entry);
+      const unsigned rdst = won ? ring_s + 4u * static_cast<unsigned>((base + pos) & (kRing - 1))
+                                : static_cast<unsigned>(__cvta_generic_to_shared(sink + lane));
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(rdst), "r"(entry) : "memory");
     } else {
-      int32_t* qdst = won ? qs.list + base + pos : sink + lane;
-      *qdst = entry;
+      const unsigned qdst = won ? list_s + 4u * static_cast<unsigned>(pos)
+                                : static_cast<unsigned>(__cvta_generic_to_shared(sink + lane));
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(qdst), "r"(entry) : "memory");
     }
     *cdst = ww[sl4] & ~kAlive;
     pos += won ? 1 : 0;
