@@ -361,6 +361,9 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
       }
       key = __reduce_max_sync(kFull, key);
       const int bc = static_cast<int>(key >> 15), bslot = static_cast<int>(0x7fffu - (key & 0x7fffu));
+#ifdef DPX_SEED_PROBE
+      if (prof) t_wide += clock64() - t_mark;
+#endif
       const unsigned long long n_cand = bc > 0 ? static_cast<unsigned long long>(bc) : 0ull;
       if (n_cand < th.min_candidate_size) break;  // plane_extractor.cpp:305-307
 
@@ -529,9 +532,23 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
       DPX_CHECK(seed >= 0 && seed < C && (cw[seed] & kAliveW) != 0 && bslot < misc[4] && list_off < C);
       if (prof) { const long long t = clock64(); t_seed += t - t_mark; t_mark = t; ++n_seeds; }
 
+      const unsigned seed_w = cw[seed];
+      if (!ALL_SMEM && ((seed_w >> kEdgeShift) & 0xfu) == 0 && th.min_cells_activated > 1ull) {
+        // Isolated seed (no passing edge): its region is the seed alone and is rejected (plane_extractor.cpp:329-331), so
+        // all that happens is removePoint + unassigned_mask[seed] = false.  On noisy fine grids this is the common case
+        // (tens of thousands per frame): skip the queue, the BFS set-up and the histogram reduction.
+        __syncwarp();
+        if (lane == 0) {
+          cw[seed] = static_cast<word_t>(seed_w & ~kAliveW);
+          hkey[bslot] -= 1u << 15;
+        }
+        --remaining;
+        __syncwarp();
+        continue;
+      }
+
       // growSeed (plane_extractor.cpp:349-392): batched FIFO BFS into list[list_off ...)
       int same = 0;  // cells of the seed's bin activated by this lane (histogram is settled after the BFS)
-      const unsigned seed_w = cw[seed];
       __syncwarp();
       {
         const int entry = seed | static_cast<int>(((seed_w >> kEdgeShift) & 0xfu) << 24);
