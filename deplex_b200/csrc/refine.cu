@@ -192,6 +192,14 @@ __device__ __forceinline__ float plane_error(const float (&m)[4], float x, float
   return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], x), __fmul_rn(m[1], y)), __fmul_rn(m[2], z)), m[3]);
 }
 
+#ifdef DPX_REFINE_PROBE
+// probe builds only (make NVFLAGS_EXTRA=-DDPX_REFINE_PROBE, tools/refine_probe.py): cycles of the leader's thread 0 per phase
+__device__ long long g_refine_probe[8];
+#define REF_PROBE(slot) do { if (leader && tid == 0 && blockIdx.x < kRefCluster) { const long long t__ = clock64(); g_refine_probe[slot] += t__ - rp_t; rp_t = t__; } } while (0)
+#else
+#define REF_PROBE(slot) do { } while (0)
+#endif
+
 template <int LAYOUT>
 __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs args) {
   __shared__ RefShared s;
@@ -202,6 +210,9 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
   const Geometry& g = args.geom;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int frame = blockIdx.x / kRefCluster;
+#ifdef DPX_REFINE_PROBE
+  long long rp_t = clock64();
+#endif
   const int C = g.n_cells, p = g.patch, p2 = p * p, nh = g.nh;
   const long long fc = static_cast<long long>(frame) * C;
   const int nseg = args.tables.n_planes[frame];
@@ -313,6 +324,7 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
 
     // ---- FindBest (RANSAC.hpp:25-51), 32 hypotheses per round -------------------------------------------------
     while (go_on) {
+      REF_PROBE(6);
       if (leader) {
         if (warp == 0) {
           // The samples of 32 consecutive iterations (RANSAC.hpp:81-87).  Almost always every iteration takes exactly
@@ -417,6 +429,7 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
         }
         if (tid < kHyp) s.loss[tid] = 0;
         __syncthreads();
+        REF_PROBE(0);  // sampling
         if (tid < kHyp * 3) s.pix[tid / 3][tid % 3] = kth_pixel(lc, rows_ok ? s.rowstart : nullptr, s.rank[tid / 3][tid % 3], p, nh, g.width);
         __syncthreads();
         if (tid < kHyp) {
@@ -436,7 +449,9 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
           s.model[tid][0] = (a / l).v; s.model[tid][1] = (b / l).v; s.model[tid][2] = (c / l).v; s.model[tid][3] = (d / l).v;
         }
       }
+      REF_PROBE(1);  // ranks -> pixels, models
       cluster.sync();  // (1) the 32 models and the zeroed losses are in the leader's shared memory
+      REF_PROBE(2);
       {
         // EvaluateModel (RANSAC.hpp:89-98): lane g scores hypothesis g; loss += (fabs(error) >= threshold)
         float m[4];
@@ -473,7 +488,9 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
           if (v) atomicAdd(&lead->loss[lane], v);
         }
       }
+      REF_PROBE(3);  // scoring
       cluster.sync();  // (2) every CTA's counts are in
+      REF_PROBE(4);
       if (leader) {
         if (warp == 1) {
           // The reference's sequential loop over these hypotheses (RANSAC.hpp:33-46), evaluated by one warp: lane h owns
@@ -544,6 +561,7 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
           }
         }
       }
+      REF_PROBE(5);  // evaluate + generator
       cluster.sync();  // (3) the decision is visible
       go_on = lead->go_on;
     }
@@ -583,6 +601,20 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
 }
 
 }  // namespace
+
+#ifdef DPX_REFINE_PROBE
+}  // namespace dpx
+extern "C" __attribute__((visibility("default"))) int dpx_debug_refine_probe(long long* out, int reset) {
+  cudaDeviceSynchronize();
+  if (out) cudaMemcpyFromSymbol(out, dpx::g_refine_probe, sizeof(long long) * 8);
+  if (reset) {
+    long long zero[8] = {};
+    cudaMemcpyToSymbol(dpx::g_refine_probe, zero, sizeof(zero));
+  }
+  return 0;
+}
+namespace dpx {
+#endif
 
 void mt19937_default_state(uint32_t out[kMtN]) {
   out[0] = 5489u;

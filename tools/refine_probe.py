@@ -1,0 +1,22 @@
+"""Probe build only (make -C deplex_b200/csrc NVFLAGS_EXTRA=-DDPX_REFINE_PROBE): where a refinement round's cycles go
+(leader CTA, thread 0) on the TUM frame."""
+import ctypes as C, os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from conftest import frame_cloud
+from deplex_b200 import Config, PlaneExtractor, _capi, LAYOUT_ROWMAJOR
+lib = _capi.load()
+for name in ("tum", "icl"):
+    xyz, ini = frame_cloud(name)
+    ex = PlaneExtractor(480, 640, Config(ini, ransac_refinement=1))
+    d = torch.from_numpy(xyz).cuda()
+    for _ in range(2):
+        ex.process_batch_device(d, LAYOUT_ROWMAJOR)
+    buf = (C.c_longlong * 8)()
+    lib.dpx_debug_refine_probe(buf, 1)
+    ex.process_batch_device(d, LAYOUT_ROWMAJOR)
+    lib.dpx_debug_refine_probe(buf, 0)
+    names = ["sampling", "pixels+models", "barrier 1", "scoring", "barrier 2", "evaluate+generator", "barrier 3 + loop"]
+    tot = sum(buf[:7])
+    print(name, "cycles:", {n: int(v) for n, v in zip(names, buf[:7])}, "total", tot, "= %.2f ms" % (tot / 1.965e6))
