@@ -271,13 +271,33 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
   if (tid < 4) hkey[B2 + tid] = 0;  // the vectorised scan may read up to three entries past the last bin
   if (tid < 8 + kCtaWarps) misc[tid] = 0;
   __syncthreads();
-  for (int c = tid; c < C; c += kCtaThreads) {
-    const int b = static_cast<int>(__ldg(bin_in + c));
-    const unsigned e = static_cast<unsigned>(__ldg(edge_in + c));
+  // (eight consecutive cells per thread and round when the tables allow 16-byte loads: with 128 threads the loop is
+  // bound by the latency of its global loads, one round trip per round)
+  const bool vec8 = (C & 7) == 0;
+  auto init_cell = [&](int c, int b, unsigned e) {
     const unsigned w0 = b >= 0 ? (static_cast<unsigned>(b) | (e << kEdgeShift) | kAliveW | (CW16 ? 0u : kClaimIdle)) : 0u;
     cw[c] = static_cast<word_t>(w0);
-    seg_label[c] = 0;
     if (b >= 0) atomicAdd(&hist_tmp[b], 1);
+  };
+  if (vec8) {
+    for (int c0 = tid * 8; c0 < C; c0 += kCtaThreads * 8) {
+      const uint4 b8 = __ldg(reinterpret_cast<const uint4*>(bin_in + c0));
+      const uint2 e8 = __ldg(reinterpret_cast<const uint2*>(edge_in + c0));
+      reinterpret_cast<int4*>(seg_label + c0)[0] = make_int4(0, 0, 0, 0);
+      reinterpret_cast<int4*>(seg_label + c0)[1] = make_int4(0, 0, 0, 0);
+      const unsigned bw[4] = {b8.x, b8.y, b8.z, b8.w};
+      const unsigned ew[2] = {e8.x, e8.y};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int b = static_cast<int>(static_cast<int16_t>((bw[k >> 1] >> (16 * (k & 1))) & 0xffffu));
+        init_cell(c0 + k, b, (ew[k >> 2] >> (8 * (k & 3))) & 0xffu);
+      }
+    }
+  } else {
+    for (int c = tid; c < C; c += kCtaThreads) {
+      seg_label[c] = 0;
+      init_cell(c, static_cast<int>(__ldg(bin_in + c)), static_cast<unsigned>(__ldg(edge_in + c)));
+    }
   }
   __syncthreads();
   // compact the non-empty bins; their runs in the sorted keys follow each other in bin order (warp 0)
@@ -315,7 +335,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
     }
   }
   __syncthreads();
-  for (int c = tid; c < C; c += kCtaThreads) {
+  auto slot_cell = [&](int c, float mse) {
     const unsigned w = cw[c];
     if (w & kAliveW) {
       const unsigned slot = static_cast<unsigned>(binslot[w & kSlotMask]);
@@ -324,9 +344,20 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
         // small frames: the bin's members in arrival order; the seed search scans (and compacts) the run
         const int pos = atomicAdd(&cursor[slot], 1);
         members[pos] = c;
-        msem[pos] = __ldg(mse_g + c);
+        msem[pos] = mse;
       }
     }
+  };
+  if (ALL_SMEM && vec8) {
+    for (int c0 = tid * 8; c0 < C; c0 += kCtaThreads * 8) {
+      // (the MSE table is written for valid cells only; entries of the others are never used)
+      const float4 m0 = __ldg(reinterpret_cast<const float4*>(mse_g + c0)), m1 = __ldg(reinterpret_cast<const float4*>(mse_g + c0) + 1);
+      const float mv[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) slot_cell(c0 + k, mv[k]);
+    }
+  } else {
+    for (int c = tid; c < C; c += kCtaThreads) slot_cell(c, ALL_SMEM ? __ldg(mse_g + c) : 0.f);
   }
   __syncthreads();  // (hist_tmp aliases the list / the windows: nobody touches those before this barrier)
 
