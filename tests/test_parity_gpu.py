@@ -452,3 +452,17 @@ def test_last_ulp_fit_differences_are_counted(oracle_mod, name):
     differing = max(report[k] for k in ("normal", "d", "mse", "score"))
     print(f"{name}: cells with last-ulp fit differences: {report}")
     assert differing <= _LAST_ULP_CELLS[name], report
+
+
+def test_process_rejects_arrays_that_are_not_n_by_3():
+    """the reference's pybind Eigen caster takes an (N, 3) array and nothing else; a (3, N), flat or (H, W, 3)
+    array must be a TypeError here too, not a silent reshape into scrambled points."""
+    from deplex_b200 import Config, PlaneExtractor
+    ex = PlaneExtractor(480, 640, Config())
+    n = 480 * 640
+    for bad in (np.zeros((3, n), np.float32), np.zeros(3 * n, np.float32), np.zeros((480, 640, 3), np.float32)):
+        with pytest.raises(TypeError):
+            ex.process(bad)
+    assert ex.process(np.zeros((n, 3), np.float64)).shape == (n,)   # any numeric dtype converts, like the caster
+    with pytest.raises(RuntimeError, match="Number of points doesn't match image shape"):
+        ex.process(np.zeros((n - 1, 3), np.float32))
