@@ -43,6 +43,7 @@ constexpr int kCtaWarps = kCtaThreads / 32;
 constexpr unsigned kAlive = 1u << 20;
 constexpr unsigned kClaimIdle = 0x7ffu << 21;
 constexpr int kRecFloats = kSegFloats;  // region / plane records use the segs layout
+constexpr int kSegDirty = 21;           // merge phase: the plane's moments have grown since its last fit (see findMergedLabels)
 
 constexpr int kRing = 1024;    // modes 1/2: most recent queue entries mirrored in shared memory (power of two)
 
@@ -821,6 +822,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
       rec[kSegScore] = fit.score;
       rec[kSegOff] = __int_as_float(off);
       rec[kSegCnt] = __int_as_float(cnt);
+      rec[kSegDirty] = 0.f;
       merge[id] = id;
     }
     nseg += total;
@@ -947,6 +949,26 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
       for (int i = 0; i < 3; ++i) ma.s[i] = ra[kSegS + i];
 #pragma unroll
       for (int i = 0; i < 6; ++i) ma.v[i] = ra[kSegV + i];
+      // The reference refits plane a after every row that expanded it (:422).  The fit (an fp64 eigensolve on one lane) is
+      // only ever looked at again if a later row is tested against a's normal -- i.e. if a later plane was merged into a
+      // and has neighbours of its own -- so it is deferred: an expanded plane is marked dirty, refit here when its normal
+      // is needed, and all planes still dirty after the loop are refit in parallel, one thread each.  Same final records.
+      if (ra[kSegDirty] != 0.f) {
+        PlaneFit fa;
+        fit_plane_call(ma, fa);
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) ra[kSegMean + i] = fa.mean[i];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) ra[kSegNormal + i] = fa.normal[i];
+          ra[kSegD] = fa.d;
+          ra[kSegMse] = fa.mse;
+          ra[kSegScore] = fa.score;
+          ra[kSegDirty] = 0.f;
+        }
+        __syncwarp();
+      }
       // normal/d of `a` are the ones it had when the row started (stats are refit after the row)
       const float an0 = ra[kSegNormal], an1 = ra[kSegNormal + 1], an2 = ra[kSegNormal + 2], ad = ra[kSegD];
       bool expanded = false;
@@ -974,29 +996,40 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
           }
         }
       }
-      if (expanded) {
-        PlaneFit fa;
-        fit_plane_call(ma, fa);
-        __syncwarp();
-        if (lane == 0) {
-          ra[kSegN] = __int_as_float(ma.n);
+      if (expanded && lane == 0) {
+        ra[kSegN] = __int_as_float(ma.n);
 #pragma unroll
-          for (int i = 0; i < 3; ++i) ra[kSegS + i] = ma.s[i];
+        for (int i = 0; i < 3; ++i) ra[kSegS + i] = ma.s[i];
 #pragma unroll
-          for (int i = 0; i < 6; ++i) ra[kSegV + i] = ma.v[i];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) ra[kSegMean + i] = fa.mean[i];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) ra[kSegNormal + i] = fa.normal[i];
-          ra[kSegD] = fa.d;
-          ra[kSegMse] = fa.mse;
-          ra[kSegScore] = fa.score;
-        }
+        for (int i = 0; i < 6; ++i) ra[kSegV + i] = ma.v[i];
+        ra[kSegDirty] = 1.f;
       }
       __syncwarp();
     }
   }
   __threadfence_block();
+  __syncthreads();
+  for (int i = tid; i < nseg; i += kCtaThreads) {
+    float* ri = rec_ptr(i);
+    if (ri[kSegDirty] != 0.f) {
+      Moments mi;
+      mi.n = __float_as_int(ri[kSegN]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) mi.s[k] = ri[kSegS + k];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) mi.v[k] = ri[kSegV + k];
+      PlaneFit fi;
+      fit_plane_call(mi, fi);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) ri[kSegMean + k] = fi.mean[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) ri[kSegNormal + k] = fi.normal[k];
+      ri[kSegD] = fi.d;
+      ri[kSegMse] = fi.mse;
+      ri[kSegScore] = fi.score;
+      ri[kSegDirty] = 0.f;
+    }
+  }
   __syncthreads();
   const long long t_merge_end = prof ? clock64() : 0;
 

@@ -39,6 +39,27 @@ def run(kind, env):
     ex.close()
 
 
+pin_out16 = torch.empty((frames, h * w), dtype=torch.int16).pin_memory()
+
+
+def run_u16(env):
+    """raw depth in, uint16 labels out (dpx_process_depth_batch_host_u16)"""
+    for key in ("DPX_LABEL_TRANSPORT", "DPX_HOST_THREADS", "DPX_HOST_CHUNK"):
+        os.environ.pop(key, None)
+    os.environ.update(env)
+    ex = PlaneExtractor(h, w, Config(), max_batch=frames)
+    call = lambda: ex.process_depth_batch_host_ptr(pin_depth.data_ptr(), frames, k, pin_out16.data_ptr(), labels_u16=True)
+    call(); call()
+    t0 = time.perf_counter()
+    for _ in range(passes):
+        call()
+    dt = time.perf_counter() - t0
+    print(f"depth, u16 labels out {str(env):50s} {passes * frames / dt:9.0f} frames/s", flush=True)
+    ex.close()
+
+
+for c in (8, 16, 24, 34, 48, 64):
+    run_u16({"DPX_HOST_CHUNK": str(c)})
 run("depth", {"DPX_LABEL_TRANSPORT": "i32"})
 for t in (2, 4, 8, 12, 16):
     run("depth", {"DPX_LABEL_TRANSPORT": "u16", "DPX_HOST_THREADS": str(t)})
