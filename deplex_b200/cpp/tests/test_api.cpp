@@ -7,7 +7,10 @@
 #include <stdexcept>
 #include <string>
 
+#include <algorithm>
+
 #include <deplex/deplex.h>
+#include <deplex_b200.h>
 
 namespace {
 int g_failed = 0;
@@ -107,6 +110,42 @@ int main(int argc, char** argv) {
     Config c{std::string(argv[3])};
     Config d;
     CHECK(c.patch_size == 12 && c.histogram_bins_per_coord == d.histogram_bins_per_coord && c.max_merge_dist == d.max_merge_dist);
+  }
+  {  // BatchPipeline / SequenceExtractor (additions): the same labels as process(), frame by frame
+    PlaneExtractor single(h, w);
+    const auto want = single.process(points.data(), n, PointLayout::RowMajor);
+    const int frames = 5;
+    std::vector<float> clouds(points.size() * frames);
+    for (int f = 0; f < frames; ++f) std::copy(points.begin(), points.end(), clouds.begin() + f * points.size());
+    std::vector<int32_t> got(static_cast<size_t>(n) * frames, -1);
+    deplex::SequenceExtractor seq(h, w, Config(), {}, /*max_batch=*/2);
+    CHECK(seq.deviceCount() >= 1);
+    seq.process(clouds.data(), frames, PointLayout::RowMajor, got.data());
+    for (int f = 0; f < frames; ++f) CHECK(std::equal(want.begin(), want.end(), got.begin() + static_cast<size_t>(f) * n));
+    int64_t b = -1, e = -1;
+    seq.frameRange(frames, 0, &b, &e);
+    CHECK(b == 0 && e >= 1 && e <= frames);
+    // device-resident batches through a two-lane pipeline (device memory through the C-ABI helpers, no CUDA headers here)
+    void *d_in = nullptr, *d_out = nullptr;
+    CHECK(dpx_device_alloc(0, &d_in, clouds.size() * sizeof(float)) == DPX_OK);
+    CHECK(dpx_device_alloc(0, &d_out, got.size() * sizeof(int32_t)) == DPX_OK);
+    CHECK(dpx_memcpy_to_device(0, d_in, clouds.data(), clouds.size() * sizeof(float)) == DPX_OK);
+    {
+      deplex::BatchPipeline pipe(h, w, Config(), /*max_batch=*/2, /*lanes=*/2, /*device=*/0);
+      CHECK(pipe.lanes() == 2);
+      for (int f = 0; f < frames; f += 2) {
+        const int nf = std::min(2, frames - f);
+        pipe.submit(static_cast<const float*>(d_in) + static_cast<size_t>(f) * n * 3, nf, PointLayout::RowMajor,
+                    static_cast<int32_t*>(d_out) + static_cast<size_t>(f) * n);
+      }
+      pipe.synchronize();
+      CHECK(throws_runtime_error([&] { pipe.submit(static_cast<const float*>(d_in), 3, PointLayout::RowMajor, static_cast<int32_t*>(d_out)); }));
+    }
+    std::fill(got.begin(), got.end(), -1);
+    CHECK(dpx_memcpy_to_host(0, got.data(), d_out, got.size() * sizeof(int32_t)) == DPX_OK);
+    for (int f = 0; f < frames; ++f) CHECK(std::equal(want.begin(), want.end(), got.begin() + static_cast<size_t>(f) * n));
+    dpx_device_free(0, d_in);
+    dpx_device_free(0, d_out);
   }
   {  // ReadImage: invalid files throw
     CHECK(throws_runtime_error([&] { deplex::utils::DepthImage bad{std::string(argv[3])}; }));
