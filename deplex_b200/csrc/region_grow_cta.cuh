@@ -236,8 +236,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
   int* bin_off = bin_end;  // mode 0: start of the bin's member run
   int* run_end = cursor;   // mode 0: end of its still-unassigned members
   const float* mse_g = args.tables.mse + fc;
-  unsigned long long* win = reinterpret_cast<unsigned long long*>(smem + plan.off_win);       // sorted modes: [K][plan.win]
-  const int kw = plan.win;                                                   // entries per window
+  unsigned long long* win = reinterpret_cast<unsigned long long*>(smem + plan.off_win);       // sorted modes: [K][kw], kw below
   int* wpos = reinterpret_cast<int*>(smem + plan.off_wpos);                  // modes 1/2: [K] sorted position of win[slot][0]
   int* wend = reinterpret_cast<int*>(smem + plan.off_wend);                  // modes 1/2: [K] end of the window's valid entries
   float* recs = reinterpret_cast<float*>(smem + plan.off_recs);              // [rec_cap][24]
@@ -371,6 +370,13 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
     // ================= the sequential chain: createPlaneSegments (plane_extractor.cpp:302-331) ==========
     int remaining = misc[3];
     const int K4 = (misc[4] + 3) / 4;
+    // entries per key window: the window storage is sized for B2 bins of plan.win entries, but only the K non-empty bins
+    // need one -- they share it (a power of two, at most 32 = one warp-wide probe)
+    int kw = plan.win;
+    if (!ALL_SMEM) {
+      const int room = (B2 * plan.win) / max(misc[4], 1);
+      while (kw < 32 && 2 * kw <= room) kw *= 2;
+    }
     int n_regions = 0, list_off = 0;
     const int slot4 = lane & 3;
     const int delta = (slot4 == 0) ? -nh : (slot4 == 1) ? nh : (slot4 == 2) ? -1 : 1;
