@@ -363,6 +363,10 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
 
   const int cell_pts = g.patch * g.patch;
   long long t_seed = 0, t_bfs = 0, t_mark = 0, t_wide = 0;
+#ifdef DPX_SEED_PROBE
+  long long t_pick_probe = 0;
+  int n_refills_probe = 0;
+#endif
   int n_seeds = 0, n_steps = 0;
   const long long t_init = prof ? clock64() - t_kernel0 : 0;
 
@@ -518,7 +522,10 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
                 pos = we;
                 continue;
               }
-              // 128 entries from the L2-resident sorted keys; the entries behind the seed refill the window
+  #ifdef DPX_SEED_PROBE
+            ++n_refills_probe;
+#endif
+            // 128 entries from the L2-resident sorted keys; the entries behind the seed refill the window
               unsigned long long k[4];
               unsigned am[4];
 #pragma unroll
@@ -566,6 +573,9 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
       }
       // no candidate with mse < INT_MAX: the reference reads an uninitialised seed id here.  (double)lm < 2147483647.0
       // is lm < 2^31 for a float: the largest float below 2^31 is 2^31 - 128.
+#ifdef DPX_SEED_PROBE
+      if (prof) t_pick_probe += clock64() - t_mark;
+#endif
       if (seed == kNoSeed || !(lm < 2147483648.0f)) break;
       DPX_CHECK(seed >= 0 && seed < C && (cw[seed] & kAliveW) != 0 && bslot < misc[4] && list_off < C);
       if (prof) { const long long t = clock64(); t_seed += t - t_mark; t_mark = t; ++n_seeds; }
@@ -1105,6 +1115,10 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
     o[5] = t_fit_end - t_grow_end;     // plane fits + label painting
     o[6] = t_merge_end - t_fit_end;    // adjacency + merging
     o[7] = t_end - t_merge_end;        // final labels
+#ifdef DPX_SEED_PROBE
+    o[7] = t_pick_probe;               // probe builds: cycles from the top of the seed loop to the seed being known
+    o[6] = n_refills_probe;            // probe builds: trips to the L2-resident sorted keys
+#endif
     o[8] = n_seeds;
     o[9] = n_steps;
     o[10] = n_regions;
