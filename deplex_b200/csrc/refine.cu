@@ -37,7 +37,8 @@ namespace {
 
 constexpr int kRefThreads = 512;
 constexpr int kRefWarps = kRefThreads / 32;
-constexpr int kHyp = 32;  // hypotheses evaluated per round = lanes of a warp
+constexpr int kSub = 4;          // groups of 32 hypotheses per round
+constexpr int kHyp = 32 * kSub;  // hypotheses evaluated per round (one cluster-wide pass over the label's points)
 constexpr int kRefCluster = 8;  // CTAs per frame (portable cluster size limit)
 constexpr int kTape = 128;      // generator outputs prepared per round (32 hypotheses x 3 draws + slack)
 constexpr int kMaxRows = 1023;  // cell rows the per-label row table can hold
@@ -48,7 +49,7 @@ constexpr unsigned kFullMask = 0xffffffffu;
 struct RefShared {
   uint32_t mt[kMtN];
   uint32_t mt_bak[kMtN];
-  float model[kHyp][4];
+  alignas(16) float model[kHyp][4];  // the round's hypotheses: computed by the leader, pushed into every CTA's copy
   unsigned loss[kHyp];        // leader: the cluster's totals
   unsigned loss_cta[kHyp];    // this CTA's share of a round
   int draws_cum[kHyp];        // generator draws used up to and including hypothesis g
@@ -56,7 +57,7 @@ struct RefShared {
   long long pix[kHyp][3];     // their pixels
   float best[4];
   double bestloss;            // HUGE_VAL until a hypothesis has been accepted
-  int iteration, consumed, go_on, fast_round;
+  int iteration, consumed, go_on;
   int max_inlier_pix;
   float4 stage[kRefWarps][32];
   uint32_t tape[kTape];       // tempered generator outputs of this round, in draw order
@@ -223,7 +224,9 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
   int* lab_end = reinterpret_cast<int*>(args.tables.pairs + 2 * fc);          // [nseg] end of each label's run
   const float* xyz = args.xyz + static_cast<long long>(frame) * 3 * g.n_points;
   int32_t* labels = args.labels + static_cast<long long>(frame) * g.n_points;
-  const double thr = static_cast<double>(args.threshold);      // SetParamThreshold(double) <- float config value
+  // SetParamThreshold(double) <- float config value: the threshold is a float widened to double, and errors are floats
+  // widened to double, so every comparison against it is exact in fp32
+  const float thr_f = args.threshold;
   const double ratio = static_cast<double>(args.inliers_ratio);
   // this thread's share of a label's points: chunks of 32 points, dealt round-robin over the cluster's warps
   const int gwarp = static_cast<int>(crank) * kRefWarps + warp;
@@ -322,109 +325,125 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
     cluster.sync();
     int go_on = lead->go_on;
 
-    // ---- FindBest (RANSAC.hpp:25-51), 32 hypotheses per round -------------------------------------------------
+    // ---- FindBest (RANSAC.hpp:25-51), kHyp hypotheses per round ------------------------------------------------
     while (go_on) {
       REF_PROBE(6);
       if (leader) {
         if (warp == 0) {
-          // The samples of 32 consecutive iterations (RANSAC.hpp:81-87).  Almost always every iteration takes exactly
-          // three draws (a rejection in the distribution or a repeated sample has probability ~3/n), so the next 96
-          // generator outputs are tempered in parallel and lane h takes outputs 3h..3h+2; any lane that sees a
-          // rejection or a repeat sends the whole round down the sequential path.
-          const int idx0 = mt_idx;
-          bool twisted = false;
-          if (idx0 + kTape > kMtN) {
-            // the tape runs into the next block of the generator: keep the current one for a possible rewind
-            for (int i = lane; i < kMtN; i += 32) s.mt_bak[i] = s.mt[i];
-            __syncwarp();
-          }
-          {
-            const int avail = max(0, min(kTape, kMtN - idx0));
-            for (int j = lane; j < avail; j += 32) s.tape[j] = mt_temper(s.mt[idx0 + j]);
-            if (avail < kTape) {
-              __syncwarp();
-              mt_twist_warp(s.mt, lane);
-              twisted = true;
-              for (int j = avail + lane; j < kTape; j += 32) s.tape[j] = mt_temper(s.mt[j - avail]);
-            }
-            __syncwarp();
-          }
+          // The samples of the next kHyp iterations (RANSAC.hpp:81-87), kSub groups of 32 one after the other.  The
+          // generator is saved first: when the search stops inside the round it is rewound and advanced by exactly the
+          // draws the reference would have made.
+          for (int i = lane; i < kMtN; i += 32) s.mt_bak[i] = s.mt[i];
+          mt_idx_bak = mt_idx;
+          __syncwarp();
           const UniformMap umap = make_uniform_map(static_cast<uint32_t>(n), args.uniform_variant);
-          // Lane h consumes tape entries from 3h + (extra draws of the hypotheses before it) until it holds three distinct
-          // accepted values.  The extra draws (a rejection in the distribution, a repeated sample: probability ~3/n per
-          // hypothesis) shift everything behind them, so the offsets are iterated to a fixed point: a prefix sum of the
-          // lanes' extra draws per pass, normally one pass, one more per anomaly in a row.
-          int off = 0, extra = 0, a = 0, b = 0, c = 0;
-          bool ok = false;
-          for (int pass = 0; pass < 6; ++pass) {
-            int pos = 3 * lane + off, cnt = 0;
-            a = b = c = -1;
-            while (cnt < 3 && pos < kTape) {
-              int vv;
-              if (!accept_draw(umap, s.tape[pos++], vv)) continue;  // the distribution draws again
-              if (vv == a || vv == b || vv == c) continue;  // std::set already holds it
-              if (cnt == 0) a = vv;
-              else if (cnt == 1) { if (vv < a) { b = a; a = vv; } else b = vv; }
-              else {
-                if (vv < a) { c = b; b = a; a = vv; }
-                else if (vv < b) { c = b; b = vv; }
-                else c = vv;
+          int draws_base = 0;          // draws of the groups before this one
+          bool twisted_round = false;  // the generator has left the block saved in mt_bak
+          for (int sub = 0; sub < kSub; ++sub) {
+            // Almost always every iteration takes exactly three draws (a rejection in the distribution or a repeated
+            // sample has probability ~3/n), so the next kTape generator outputs are tempered in parallel and lane h takes
+            // outputs from 3h on.  Only while the tape stays inside the generator's current block; the group that
+            // crosses into the next block (one in six or seven) draws one value at a time instead.
+            const int idx0 = mt_idx;
+            const int avail = max(0, min(kTape, kMtN - idx0));  // tape entries the current block still holds
+            int off = 0, extra = 0, a = 0, b = 0, c = 0;
+            bool ok = false, twisted = false;
+            if (avail == kTape || !twisted_round) {
+              for (int j = lane; j < avail; j += 32) s.tape[j] = mt_temper(s.mt[idx0 + j]);
+              if (avail < kTape) {
+                // the tape runs into the generator's next block (mt_bak still holds the current one: first twist of
+                // the round)
+                __syncwarp();
+                mt_twist_warp(s.mt, lane);
+                twisted = true;
+                for (int j = avail + lane; j < kTape; j += 32) s.tape[j] = mt_temper(s.mt[j - avail]);
               }
-              ++cnt;
-            }
-            const bool complete = cnt == 3;
-            extra = pos - (3 * lane + off) - 3;
-            int incl = extra;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-              const int t = __shfl_up_sync(kFullMask, incl, o);
-              if (lane >= o) incl += t;
-            }
-            const int new_off = incl - extra;
-            const bool stable = __all_sync(kFullMask, complete && new_off == off);
-            off = new_off;
-            if (stable) {
-              ok = true;
-              break;
-            }
-            if (!__all_sync(kFullMask, complete)) break;  // ran off the tape: take the sequential path
-          }
-          if (ok) {
-            s.rank[lane][0] = a; s.rank[lane][1] = b; s.rank[lane][2] = c;
-            s.draws_cum[lane] = 3 * (lane + 1) + off + extra;
-            if (lane == 0) s.fast_round = 1 | (twisted ? 2 : 0);
-            mt_idx_bak = idx0;  // position before this round; the position after it is settled once `consumed` is known
-          } else {
-            // sequential path from the state at the start of the round
-            if (twisted) {
-              for (int i = lane; i < kMtN; i += 32) s.mt[i] = s.mt_bak[i];
               __syncwarp();
-            }
-            mt_idx = idx0;
-            for (int i = lane; i < kMtN; i += 32) s.mt_bak[i] = s.mt[i];
-            mt_idx_bak = mt_idx;
-            __syncwarp();
-            int draws = 0;
-            for (int h = 0; h < kHyp; ++h) {
-              int a = -1, b = -1, c = -1, cnt = 0;  // the std::set<int>, kept sorted
-              while (cnt < 3) {
-                const int vv = uniform_below_warp(s, lane, mt_idx, umap, draws);
-                if (vv == a || vv == b || vv == c) continue;
-                if (cnt == 0) a = vv;
-                else if (cnt == 1) { if (vv < a) { b = a; a = vv; } else b = vv; }
-                else {
-                  if (vv < a) { c = b; b = a; a = vv; }
-                  else if (vv < b) { c = b; b = vv; }
-                  else c = vv;
+              // Lane h consumes tape entries from 3h + (extra draws of the hypotheses before it) until it holds three
+              // distinct accepted values.  The extra draws shift everything behind them, so the offsets are iterated to
+              // a fixed point: a prefix sum of the lanes' extra draws per pass, normally one pass.
+              for (int pass = 0; pass < 6; ++pass) {
+                int pos = 3 * lane + off, cnt = 0;
+                a = b = c = -1;
+                while (cnt < 3 && pos < kTape) {
+                  int vv;
+                  if (!accept_draw(umap, s.tape[pos++], vv)) continue;  // the distribution draws again
+                  if (vv == a || vv == b || vv == c) continue;          // std::set already holds it
+                  if (cnt == 0) a = vv;
+                  else if (cnt == 1) { if (vv < a) { b = a; a = vv; } else b = vv; }
+                  else {
+                    if (vv < a) { c = b; b = a; a = vv; }
+                    else if (vv < b) { c = b; b = vv; }
+                    else c = vv;
+                  }
+                  ++cnt;
                 }
-                ++cnt;
-              }
-              if (lane == 0) {
-                s.rank[h][0] = a; s.rank[h][1] = b; s.rank[h][2] = c;
-                s.draws_cum[h] = draws;
+                const bool complete = cnt == 3;
+                extra = pos - (3 * lane + off) - 3;
+                int incl = extra;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                  const int t = __shfl_up_sync(kFullMask, incl, o);
+                  if (lane >= o) incl += t;
+                }
+                const int new_off = incl - extra;
+                const bool stable = __all_sync(kFullMask, complete && new_off == off);
+                off = new_off;
+                if (stable) {
+                  ok = true;
+                  break;
+                }
+                if (!__all_sync(kFullMask, complete)) break;  // ran off the tape: take the sequential path
               }
             }
-            if (lane == 0) s.fast_round = 0;
+            if (ok) {
+              const int h = 32 * sub + lane;
+              s.rank[h][0] = a; s.rank[h][1] = b; s.rank[h][2] = c;
+              const int cum = 3 * (lane + 1) + off + extra;  // draws of this group up to and including hypothesis `lane`
+              s.draws_cum[h] = draws_base + cum;
+              const int used = __shfl_sync(kFullMask, cum, 31);
+              if (!twisted) {
+                mt_idx = idx0 + used;
+              } else if (used > avail) {
+                mt_idx = used - avail;  // inside the block the tape has already generated
+                twisted_round = true;
+              } else {
+                // the draws end inside the old block after all: back to it
+                for (int i = lane; i < kMtN; i += 32) s.mt[i] = s.mt_bak[i];
+                __syncwarp();
+                mt_idx = idx0 + used;
+              }
+              draws_base += used;
+            } else {
+              if (twisted) {
+                for (int i = lane; i < kMtN; i += 32) s.mt[i] = s.mt_bak[i];
+                __syncwarp();
+              }
+              int draws = 0;
+              for (int hh = 0; hh < 32; ++hh) {
+                int sa = -1, sb = -1, sc = -1, cnt = 0;  // the std::set<int>, kept sorted
+                while (cnt < 3) {
+                  const int vv = uniform_below_warp(s, lane, mt_idx, umap, draws);
+                  if (vv == sa || vv == sb || vv == sc) continue;
+                  if (cnt == 0) sa = vv;
+                  else if (cnt == 1) { if (vv < sa) { sb = sa; sa = vv; } else sb = vv; }
+                  else {
+                    if (vv < sa) { sc = sb; sb = sa; sa = vv; }
+                    else if (vv < sb) { sc = sb; sb = vv; }
+                    else sc = vv;
+                  }
+                  ++cnt;
+                }
+                if (lane == 0) {
+                  const int h = 32 * sub + hh;
+                  s.rank[h][0] = sa; s.rank[h][1] = sb; s.rank[h][2] = sc;
+                  s.draws_cum[h] = draws_base + draws;
+                }
+              }
+              draws_base += draws;
+              if (mt_idx < idx0) twisted_round = true;  // the generator moved on to its next block
+            }
+            __syncwarp();
           }
         }
         if (tid < kHyp) s.loss[tid] = 0;
@@ -446,18 +465,26 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
           const f32 c(-1.0f);
           // `sqrt(float)` in Plane.hpp:36 resolves to ::sqrt(double): double square root, rounded to float on assignment
           const f32 l(__double2float_rn(__dsqrt_rn(static_cast<double>((a * a + b * b + c * c).v))));
-          s.model[tid][0] = (a / l).v; s.model[tid][1] = (b / l).v; s.model[tid][2] = (c / l).v; s.model[tid][3] = (d / l).v;
+          // pushed into every CTA's shared memory (fire-and-forget stores, visible after the cluster barrier): 1024
+          // threads per CTA fetching them from the leader afterwards queue up on its distributed-shared-memory port
+          const float4 mv = make_float4((a / l).v, (b / l).v, (c / l).v, (d / l).v);
+#pragma unroll
+          for (int r = 0; r < kRefCluster; ++r) *reinterpret_cast<float4*>(cluster.map_shared_rank(&s.model[tid][0], r)) = mv;
         }
       }
       REF_PROBE(1);  // ranks -> pixels, models
-      cluster.sync();  // (1) the 32 models and the zeroed losses are in the leader's shared memory
+      cluster.sync();  // (1) the kHyp models and the zeroed losses are in the leader's shared memory
       REF_PROBE(2);
       {
-        // EvaluateModel (RANSAC.hpp:89-98): lane g scores hypothesis g; loss += (fabs(error) >= threshold)
-        float m[4];
+        // EvaluateModel (RANSAC.hpp:89-98): lane g scores hypotheses g, g + 32, ...; loss += (fabs(error) >= threshold)
+        float m[kSub][4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) m[k] = lead->model[lane][k];
-        unsigned loss = 0;
+        for (int j = 0; j < kSub; ++j)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) m[j][k] = s.model[32 * j + lane][k];
+        unsigned loss[kSub];
+#pragma unroll
+        for (int j = 0; j < kSub; ++j) loss[j] = 0;
         for (int e0 = gwarp * 32; e0 < n; e0 += kStride) {
           const int e = e0 + lane;
           float x = 0.f, y = 0.f, z = 0.f;
@@ -473,19 +500,24 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
           const int cnt = min(32, n - e0);
           for (int k = 0; k < cnt; ++k) {
             const float4 pt = s.stage[warp][k];
-            const double err = static_cast<double>(plane_error(m, pt.x, pt.y, pt.z));
-            loss += (::fabs(err) >= thr) ? 1u : 0u;
+#pragma unroll
+            for (int j = 0; j < kSub; ++j) {
+              // the reference compares fabs(double(error)) with double(float threshold): the same predicate in fp32
+              loss[j] += (::fabsf(plane_error(m[j], pt.x, pt.y, pt.z)) >= thr_f) ? 1u : 0u;
+            }
           }
           __syncwarp();
         }
         // per-warp counts -> this CTA's totals -> one distributed-shared-memory atomic per hypothesis and CTA
-        // (128 warps adding straight into the leader's 32 counters serialise there)
-        if (loss) atomicAdd(&s.loss_cta[lane], loss);
+        // (128 warps adding straight into the leader's counters serialise there)
+#pragma unroll
+        for (int j = 0; j < kSub; ++j)
+          if (loss[j]) atomicAdd(&s.loss_cta[32 * j + lane], loss[j]);
         __syncthreads();
-        if (warp == 0) {
-          const unsigned v = s.loss_cta[lane];
-          s.loss_cta[lane] = 0;
-          if (v) atomicAdd(&lead->loss[lane], v);
+        if (tid < kHyp) {
+          const unsigned v = s.loss_cta[tid];
+          s.loss_cta[tid] = 0;
+          if (v) atomicAdd(&lead->loss[tid], v);
         }
       }
       REF_PROBE(3);  // scoring
@@ -493,77 +525,78 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
       REF_PROBE(4);
       if (leader) {
         if (warp == 1) {
-          // The reference's sequential loop over these hypotheses (RANSAC.hpp:33-46), evaluated by one warp: lane h owns
-          // hypothesis h.  The best-so-far loss before hypothesis h is a prefix minimum; the loop runs while IsContinued
-          // holds, which is monotone (the best loss only falls, the iteration count only grows), so the number of
-          // iterations really run is the number of hypotheses whose check passes.
+          // The reference's sequential loop over these hypotheses (RANSAC.hpp:33-46), evaluated by one warp, 32 at a time:
+          // lane h owns hypothesis h of the group.  The best-so-far loss before hypothesis h is a prefix minimum; the loop
+          // runs while IsContinued holds, which is monotone (the best loss only falls, the iteration count only grows), so
+          // the number of iterations really run is the number of hypotheses whose check passes.
           const double inf = HUGE_VAL;
-          const double best0 = s.bestloss;
-          const int iter0 = s.iteration;
-          const double mine = static_cast<double>(s.loss[lane]);
-          double incl = mine;
+          double best0 = s.bestloss;
+          int iter0 = s.iteration;
+          int consumed_all = 0;
+          for (int sub = 0; sub < kSub; ++sub) {
+            const double mine = static_cast<double>(s.loss[32 * sub + lane]);
+            double incl = mine;
 #pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const double t = __shfl_up_sync(kFullMask, incl, o);
-            if (lane >= o) incl = ::fmin(incl, t);
-          }
-          double before = __shfl_up_sync(kFullMask, incl, 1);
-          if (lane == 0) before = inf;
-          before = ::fmin(before, best0);
-          const int inl = ::isinf(before) ? INT_MIN : static_cast<int>(n - before);
-          const bool go_h = (iter0 + lane < args.max_iterations) && (static_cast<double>(inl) < ratio * n);
-          const int consumed = __popc(__ballot_sync(kFullMask, go_h));
-          // best loss over the iterations really run, and the first of them that reaches it (strict '<' updates)
-          double best = lane < consumed ? mine : inf;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) best = ::fmin(best, __shfl_xor_sync(kFullMask, best, o));
-          const unsigned hit = __ballot_sync(kFullMask, lane < consumed && mine == best);
-          if (lane == 0) {
-            double bl = best0;
-            if (hit && best < best0) {
-              const int winner = __ffs(hit) - 1;
-              s.best[0] = s.model[winner][0]; s.best[1] = s.model[winner][1]; s.best[2] = s.model[winner][2]; s.best[3] = s.model[winner][3];
-              bl = best;
+            for (int o = 1; o < 32; o <<= 1) {
+              const double t = __shfl_up_sync(kFullMask, incl, o);
+              if (lane >= o) incl = ::fmin(incl, t);
             }
-            s.bestloss = bl;
-            s.iteration = iter0 + consumed;
-            bool go = consumed == kHyp;
+            double before = __shfl_up_sync(kFullMask, incl, 1);
+            if (lane == 0) before = inf;
+            before = ::fmin(before, best0);
+            const int inl = ::isinf(before) ? INT_MIN : static_cast<int>(n - before);
+            const bool go_h = (iter0 + lane < args.max_iterations) && (static_cast<double>(inl) < ratio * n);
+            const int consumed = __popc(__ballot_sync(kFullMask, go_h));
+            // best loss over the iterations really run, and the first of them that reaches it (strict '<' updates)
+            double best = lane < consumed ? mine : inf;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) best = ::fmin(best, __shfl_xor_sync(kFullMask, best, o));
+            const unsigned hit = __ballot_sync(kFullMask, lane < consumed && mine == best);
+            if (hit && best < best0) {
+              if (lane == 0) {
+                const int winner = 32 * sub + __ffs(hit) - 1;
+                s.best[0] = s.model[winner][0]; s.best[1] = s.model[winner][1]; s.best[2] = s.model[winner][2]; s.best[3] = s.model[winner][3];
+              }
+              best0 = best;
+            }
+            iter0 += consumed;
+            consumed_all += consumed;
+            if (consumed < 32) break;
+          }
+          if (lane == 0) {
+            s.bestloss = best0;
+            s.iteration = iter0;
+            bool go = consumed_all == kHyp;
             if (go) {
-              const int inl2 = ::isinf(bl) ? INT_MIN : static_cast<int>(n - bl);
+              const int inl2 = ::isinf(best0) ? INT_MIN : static_cast<int>(n - best0);
               go = (s.iteration < args.max_iterations) && (static_cast<double>(inl2) < ratio * n);
             }
-            s.consumed = consumed;
-            s.go_on = go ? 1 : 0;
+            s.consumed = consumed_all;
+            for (int r = 0; r < kRefCluster; ++r) *cluster.map_shared_rank(&s.go_on, r) = go ? 1 : 0;
           }
         }
         __syncthreads();
-        if (warp == 0) {
-          // leave the generator just after the last iteration the reference would have run
-          const int redo = s.consumed > 0 ? s.draws_cum[s.consumed - 1] : 0;
-          if (s.fast_round & 1) {
-            const bool twisted = (s.fast_round & 2) != 0;
-            if (mt_idx_bak + redo <= kMtN) {
-              // the consumed draws end inside the block the round started in
-              if (twisted) {
-                for (int i = lane; i < kMtN; i += 32) s.mt[i] = s.mt_bak[i];
-                __syncwarp();
-              }
-              mt_idx = mt_idx_bak + redo;
-            } else {
-              // they run into the next block, which the tape has already generated (kTape >= 96 draws)
-              mt_idx = mt_idx_bak + redo - kMtN;
+        if (warp == 0 && s.consumed < kHyp) {
+          // the search stopped inside the round: leave the generator just after the last iteration the reference ran
+          for (int i = lane; i < kMtN; i += 32) s.mt[i] = s.mt_bak[i];
+          mt_idx = mt_idx_bak;
+          __syncwarp();
+          int redo = s.consumed > 0 ? s.draws_cum[s.consumed - 1] : 0;
+          while (redo > 0) {  // advancing the generator is moving its position, block by block
+            if (mt_idx >= kMtN) {
+              mt_twist_warp(s.mt, lane);
+              __syncwarp();
+              mt_idx = 0;
             }
-          } else if (s.consumed < kHyp) {
-            for (int i = lane; i < kMtN; i += 32) s.mt[i] = s.mt_bak[i];
-            mt_idx = mt_idx_bak;
-            __syncwarp();
-            for (int k = 0; k < redo; ++k) (void)mt_next_warp(s, lane, mt_idx);
+            const int step = min(redo, kMtN - mt_idx);
+            mt_idx += step;
+            redo -= step;
           }
         }
       }
       REF_PROBE(5);  // evaluate + generator
       cluster.sync();  // (3) the decision is visible
-      go_on = lead->go_on;
+      go_on = s.go_on;
     }
 
     // ---- FindInliers + relabelling (RANSAC.hpp:53-62, plane_extractor.cpp:498-507) ---------------------------
@@ -582,7 +615,7 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
         const long long pix = static_cast<long long>(r * p + i) * g.width + q * p + j;
         float x, y, z;
         load_point<LAYOUT>(xyz, g.n_points, pix, x, y, z);
-        const bool inlier = ::fabs(static_cast<double>(plane_error(m, x, y, z))) < thr;
+        const bool inlier = ::fabsf(plane_error(m, x, y, z)) < thr_f;
         if (pass == 0) {
           if (inlier) local_max = max(local_max, static_cast<int>(pix));
         } else if (!inlier && pix < last) {
