@@ -9,21 +9,27 @@
 //   libstdc++'s std::uniform_int_distribution<int> (GCC >= 11: Lemire's multiply-shift with rejection)
 //
 // One thread-block cluster (8 CTAs of 512 threads, distributed shared memory) per frame; CTA 0 of the cluster leads.
-// The reference's loop is sequential twice over -- labels share one random stream, and each
-// label's iterations stop as soon as a hypothesis reaches the target inlier ratio -- so the CTA walks the labels in
-// order and evaluates the next 32 hypotheses of the current label speculatively and at once:
-//   warp 0     (leader) draws the sample ranks of 32 hypotheses: the next generator outputs are tempered in parallel
-//              into a tape and lane h takes outputs 3h..3h+2; a rejection or a repeated sample sends the round down the
-//              exact sequential path.  The draws each hypothesis took are remembered;
-//   96 threads turn (hypothesis, sample) ranks into pixels: the k-th pixel of a label in image order follows
-//              from the label's cells sorted by cell id (cells are painted whole), no per-pixel index lists;
-//   32 threads build the plane models (fp32, the reference's expression order);
-//   all warps  of all 8 CTAs score: a warp stages 32 points in shared memory, then lane g scores hypothesis g on each
-//              of them (the loss is a count, so the order of the points is free); per-warp counts go to the leader's
-//              shared memory with distributed-shared-memory atomics;
-//   one warp   replays the reference's sequential loop over the 32 losses as a prefix minimum (best-so-far,
-//              IsContinued) and reports how many hypotheses were really consumed; warp 0 leaves the generator at
-//              exactly that point.
+// The reference's loop is sequential twice over -- labels share one random stream, and each label's iterations stop as
+// soon as a hypothesis reaches the target inlier ratio -- so the cluster walks the labels in order and evaluates the
+// next kHyp = 128 hypotheses of the current label speculatively and at once.  A round is a two-stage pipeline: while
+// the cluster scores round r, four producer warps of the leader prepare round r + 1 as if round r ran to its end.
+//   producers  (leader, warps 0-3).  Warp 0 draws the sample ranks, 32 hypotheses at a time: the next generator outputs
+//              are tempered in parallel into a tape and lane h takes outputs from 3h on; rejections of the distribution
+//              and repeated samples shift the lanes behind them (a prefix sum, iterated to a fixed point), and a group
+//              that does not settle takes the exact draw-by-draw path.  The draws each hypothesis took are remembered.
+//              The generator's blocks of 624 words live in a ring of three, each twisted out of place from the one
+//              before, so any position of the last ~1200 draws can be returned to by resetting a counter.
+//              Then 128 threads turn (hypothesis, sample) ranks into pixels -- the k-th pixel of a label in image
+//              order follows from the label's cells sorted by cell id (cells are painted whole), no per-pixel index
+//              lists -- build the plane models (fp32, the reference's expression order) and push them into every
+//              CTA's shared memory;
+//   scorers    (every other warp of the 8 CTAs).  A warp stages 32 points in shared memory, then lane g scores
+//              hypotheses g, g + 32, g + 64, g + 96 on each of them (the loss is a count, so the order of the points
+//              is free); per-warp counts are summed per CTA and go to the leader with one distributed-shared-memory
+//              atomic per hypothesis;
+//   warp 0     replays the reference's sequential loop over the 128 losses as a prefix minimum (best-so-far,
+//              IsContinued), finds how many hypotheses were really run, and leaves the generator just after the last
+//              of them when the search stops (the round prepared ahead is dropped).
 // FindInliers + the relabelling loop (which stops at the last inlier, plane_extractor.cpp:500-507) become two
 // passes: the largest inlier pixel index, then "non-inlier before it -> 0".
 #include "refine.cuh"
@@ -46,49 +52,47 @@ constexpr int kCellCache = 4096;  // cells of one label cached in shared memory 
 namespace cg = cooperative_groups;
 constexpr unsigned kFullMask = 0xffffffffu;
 
+constexpr int kProdWarps = 4;  // the leader's producer warps (kProdWarps * 32 == kHyp)
+constexpr unsigned kNoLoss = 0xffffffffu;  // "no hypothesis accepted yet" (the reference's HUGE_VAL best loss)
+
 struct RefShared {
-  uint32_t mt[kMtN];
-  uint32_t mt_bak[kMtN];
-  alignas(16) float model[kHyp][4];  // the round's hypotheses: computed by the leader, pushed into every CTA's copy
-  unsigned loss[kHyp];        // leader: the cluster's totals
+  uint32_t mtb[3][kMtN];      // leader: generator block b (the state after b twists of the seeded state) in slot b % 3
+  alignas(16) float model[2][kHyp][4];  // the hypotheses of the round being scored / being prepared, in every CTA
+  alignas(16) unsigned loss[kHyp];      // leader: the cluster's totals
   unsigned loss_cta[kHyp];    // this CTA's share of a round
-  int draws_cum[kHyp];        // generator draws used up to and including hypothesis g
-  int rank[kHyp][3];          // sample ranks, ascending (std::set order)
-  long long pix[kHyp][3];     // their pixels
+  int draws_cum[2][kHyp];     // generator draws of the round up to and including hypothesis g
+  int rank[kHyp][3];          // sample ranks, ascending (std::set order): hand-over of the exact sequential path
+  int grp_start[kSub], grp_used[kSub];  // per group of 32 hypotheses: assumed offset into the round's draws, draws taken
   float best[4];
-  double bestloss;            // HUGE_VAL until a hypothesis has been accepted
-  int iteration, consumed, go_on;
+  unsigned bestloss;          // kNoLoss until a hypothesis has been accepted
+  int iteration, go_on;
+  int prod_gp0;               // leader: stream position the round being prepared starts at
   int max_inlier_pix;
   float4 stage[kRefWarps][32];
-  uint32_t tape[kTape];       // tempered generator outputs of this round, in draw order
+  uint32_t tape[kProdWarps][kTape];  // per producer warp: tempered generator outputs of a group of 32 hypotheses, in draw order
   int rowstart[kMaxRows + 1]; // per label: index of the first of its cells in each cell row (cells are sorted)
   int32_t cells[kCellCache];  // per label, every CTA: a copy of the label's sorted cell list when it fits
 };
 
-// ---- std::mt19937, executed by warp 0 (all lanes compute the same values; lane 0 owns the stores) ----------
-__device__ __forceinline__ void mt_twist_warp(uint32_t* mt, int lane) {
-  // new[i] = old[(i + 397) % 624] ^ f(old[i], old[i + 1]); entries i >= 227 read already updated entries,
-  // so the update runs in waves of 227 (dependency distance) with a warp barrier in between.
+// ---- std::mt19937, executed by warp 0 of the leader (all lanes compute the same values) -----------------------
+// The next block of 624 words from the current one, out of place:
+//   next[i] = (i < 227 ? cur[i + 397] : next[i - 227]) ^ f(cur[i], i < 623 ? cur[i + 1] : next[0]);
+// entries i >= 227 read entries of the new block, so the update runs in waves of 224 (<= 227, a multiple of 32).
+__device__ __forceinline__ void mt_next_block_warp(uint32_t* next, const uint32_t* cur, int lane) {
   auto f = [](uint32_t a, uint32_t b) {
     const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
     return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
   };
-  for (int base = 0; base < kMtN; base += 224) {  // 224 <= 227, multiple of 32
+  for (int base = 0; base < kMtN; base += 224) {
     const int end = min(base + 224, kMtN);
-    uint32_t v[7];
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
       const int i = base + k * 32 + lane;
       if (i < end) {
-        const uint32_t nxt = mt[(i + 1) % kMtN];  // for i = 623 this is the already updated mt[0], as in the reference
-        v[k] = mt[(i + 397) % kMtN] ^ f(mt[i], nxt);
+        const uint32_t far = i < 227 ? cur[i + 397] : next[i - 227];
+        const uint32_t nxt = i < kMtN - 1 ? cur[i + 1] : next[0];
+        next[i] = far ^ f(cur[i], nxt);
       }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < 7; ++k) {
-      const int i = base + k * 32 + lane;
-      if (i < end) mt[i] = v[k];
     }
     __syncwarp();
   }
@@ -102,13 +106,25 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
   return y;
 }
 
-// `idx` is the generator's position, held in a register by every lane of warp 0 (all lanes agree)
-__device__ __forceinline__ uint32_t mt_next_warp(RefShared& s, int lane, int& idx) {
-  if (idx >= kMtN) {
-    mt_twist_warp(s.mt, lane);
-    idx = 0;
+// The generator as a stream: draw number t (counted from the seeded state, whose own 624 words are "used up", so the
+// first real draw is t = 624) is word t % 624 of block t / 624.  Blocks gen_hi - 2 .. gen_hi are in the ring; a block
+// ahead is generated on demand, a block that has left the ring is regenerated from the seed (never in practice: a round
+// would have to take several hundred draws more than its 384).  `gen_hi` lives in a register of every lane of warp 0.
+__device__ __forceinline__ void gen_cover(RefShared& s, const uint32_t* mt_init, int lane, int& gen_hi, int t_lo, int t_hi) {
+  const int b_lo = t_lo / kMtN, b_hi = t_hi / kMtN;
+  if (b_lo < gen_hi - 2) {
+    for (int i = lane; i < kMtN; i += 32) s.mtb[0][i] = mt_init[i];
+    __syncwarp();
+    gen_hi = 0;
   }
-  return mt_temper(s.mt[idx++]);
+  while (gen_hi < b_hi) {
+    mt_next_block_warp(s.mtb[(gen_hi + 1) % 3], s.mtb[gen_hi % 3], lane);
+    ++gen_hi;
+  }
+}
+__device__ __forceinline__ uint32_t gen_word(const RefShared& s, int t) {
+  const int b = t / kMtN;
+  return mt_temper(s.mtb[b % 3][t - b * kMtN]);
 }
 
 // std::uniform_int_distribution<int>(0, n - 1)(gen) over std::mt19937.  The mapping is implementation-defined and
@@ -139,12 +155,15 @@ __device__ __forceinline__ bool accept_draw(const UniformMap& m, uint32_t u, int
   value = static_cast<int>(product >> 32);
   return static_cast<uint32_t>(product) >= m.threshold;  // (low < n && low < threshold) rejects; threshold < n always
 }
-// `draws` counts generator calls.
-__device__ __forceinline__ int uniform_below_warp(RefShared& s, int lane, int& idx, const UniformMap& m, int& draws) {
+// one value of the distribution, drawn word by word from position t on (t is advanced past the words used)
+__device__ __forceinline__ int uniform_below_warp(RefShared& s, const uint32_t* mt_init, int lane, int& gen_hi, int& t, const UniformMap& m) {
   int value;
+  uint32_t u;
   do {
-    ++draws;
-  } while (!accept_draw(m, mt_next_warp(s, lane, idx), value));
+    if (t / kMtN > gen_hi || t / kMtN < gen_hi - 2) gen_cover(s, mt_init, lane, gen_hi, t, t);
+    u = gen_word(s, t);
+    ++t;
+  } while (!accept_draw(m, u, value));
   return value;
 }
 
@@ -195,8 +214,8 @@ __device__ __forceinline__ float plane_error(const float (&m)[4], float x, float
 
 #ifdef DPX_REFINE_PROBE
 // probe builds only (make NVFLAGS_EXTRA=-DDPX_REFINE_PROBE, tools/refine_probe.py): cycles of the leader's thread 0 per phase
-__device__ long long g_refine_probe[8];
-#define REF_PROBE(slot) do { if (leader && tid == 0 && blockIdx.x < kRefCluster) { const long long t__ = clock64(); g_refine_probe[slot] += t__ - rp_t; rp_t = t__; } } while (0)
+__device__ long long g_refine_probe[24];  // [0, 12): the leader's thread 0 (a producer); [12, 24): its first scoring thread
+#define REF_PROBE(slot) do { if (leader && (tid == 0 || tid == kProdWarps * 32) && blockIdx.x < kRefCluster) { const long long t__ = clock64(); g_refine_probe[(tid ? 12 : 0) + slot] += t__ - rp_t; rp_t = t__; } } while (0)
 #else
 #define REF_PROBE(slot) do { } while (0)
 #endif
@@ -231,14 +250,19 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
   // this thread's share of a label's points: chunks of 32 points, dealt round-robin over the cluster's warps
   const int gwarp = static_cast<int>(crank) * kRefWarps + warp;
   constexpr int kStride = kRefCluster * kRefThreads;
+  // during the search the leader's producer warps do not score: the other warps of the cluster share the points
+  const bool producer = leader && warp < kProdWarps;
+  const int swarp = gwarp - kProdWarps;
+  constexpr int kScoreStride = kStride - kProdWarps * 32;
 
-  int mt_idx = kMtN, mt_idx_bak = kMtN;  // generator position; meaningful in warp 0 of the leader only
+  // the generator (warp 0 of the leader): position of the next draw in the stream, newest block in the ring
+  int gp = kMtN, gen_hi = 0;
   if (tid < kHyp) s.loss_cta[tid] = 0;
   __syncthreads();
   if (leader) {
     // ---- labels_indices (plane_extractor.cpp:473-478), per cell instead of per pixel ---------------------
     for (int i = tid; i < nseg; i += kRefThreads) lab_end[i] = 0;
-    for (int i = tid; i < kMtN; i += kRefThreads) s.mt[i] = args.mt_init[i];
+    for (int i = tid; i < kMtN; i += kRefThreads) s.mtb[0][i] = args.mt_init[i];
     __syncthreads();
     for (int c = tid; c < C; c += kRefThreads) {
       const int l = cell_label[c];
@@ -316,7 +340,7 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
     }
     if (leader && tid == 0) {
       s.best[0] = s.best[1] = s.best[2] = s.best[3] = 0.f;  // Eigen::Vector4f::Zero()
-      s.bestloss = HUGE_VAL;
+      s.bestloss = kNoLoss;
       s.iteration = 0;
       s.max_inlier_pix = -1;
       // IsContinued(0, N - HUGE_VAL, N): int(-inf) is INT_MIN on x86-64
@@ -326,104 +350,115 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
     int go_on = lead->go_on;
 
     // ---- FindBest (RANSAC.hpp:25-51), kHyp hypotheses per round ------------------------------------------------
-    while (go_on) {
-      REF_PROBE(6);
-      if (leader) {
-        if (warp == 0) {
-          // The samples of the next kHyp iterations (RANSAC.hpp:81-87), kSub groups of 32 one after the other.  The
-          // generator is saved first: when the search stops inside the round it is rewound and advanced by exactly the
-          // draws the reference would have made.
-          for (int i = lane; i < kMtN; i += 32) s.mt_bak[i] = s.mt[i];
-          mt_idx_bak = mt_idx;
-          __syncwarp();
-          const UniformMap umap = make_uniform_map(static_cast<uint32_t>(n), args.uniform_variant);
-          int draws_base = 0;          // draws of the groups before this one
-          bool twisted_round = false;  // the generator has left the block saved in mt_bak
-          for (int sub = 0; sub < kSub; ++sub) {
-            // Almost always every iteration takes exactly three draws (a rejection in the distribution or a repeated
-            // sample has probability ~3/n), so the next kTape generator outputs are tempered in parallel and lane h takes
-            // outputs from 3h on.  Only while the tape stays inside the generator's current block; the group that
-            // crosses into the next block (one in six or seven) draws one value at a time instead.
-            const int idx0 = mt_idx;
-            const int avail = max(0, min(kTape, kMtN - idx0));  // tape entries the current block still holds
-            int off = 0, extra = 0, a = 0, b = 0, c = 0;
-            bool ok = false, twisted = false;
-            if (avail == kTape || !twisted_round) {
-              for (int j = lane; j < avail; j += 32) s.tape[j] = mt_temper(s.mt[idx0 + j]);
-              if (avail < kTape) {
-                // the tape runs into the generator's next block (mt_bak still holds the current one: first twist of
-                // the round)
-                __syncwarp();
-                mt_twist_warp(s.mt, lane);
-                twisted = true;
-                for (int j = avail + lane; j < kTape; j += 32) s.tape[j] = mt_temper(s.mt[j - avail]);
-              }
-              __syncwarp();
-              // Lane h consumes tape entries from 3h + (extra draws of the hypotheses before it) until it holds three
-              // distinct accepted values.  The extra draws shift everything behind them, so the offsets are iterated to
-              // a fixed point: a prefix sum of the lanes' extra draws per pass, normally one pass.
-              for (int pass = 0; pass < 6; ++pass) {
-                int pos = 3 * lane + off, cnt = 0;
-                a = b = c = -1;
-                while (cnt < 3 && pos < kTape) {
-                  int vv;
-                  if (!accept_draw(umap, s.tape[pos++], vv)) continue;  // the distribution draws again
-                  if (vv == a || vv == b || vv == c) continue;          // std::set already holds it
-                  if (cnt == 0) a = vv;
-                  else if (cnt == 1) { if (vv < a) { b = a; a = vv; } else b = vv; }
-                  else {
-                    if (vv < a) { c = b; b = a; a = vv; }
-                    else if (vv < b) { c = b; b = vv; }
-                    else c = vv;
-                  }
-                  ++cnt;
-                }
-                const bool complete = cnt == 3;
-                extra = pos - (3 * lane + off) - 3;
-                int incl = extra;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                  const int t = __shfl_up_sync(kFullMask, incl, o);
-                  if (lane >= o) incl += t;
-                }
-                const int new_off = incl - extra;
-                const bool stable = __all_sync(kFullMask, complete && new_off == off);
-                off = new_off;
-                if (stable) {
-                  ok = true;
-                  break;
-                }
-                if (!__all_sync(kFullMask, complete)) break;  // ran off the tape: take the sequential path
-              }
+    // The producers' work for one round: samples -> pixels -> models of hypotheses [0, kHyp) drawn from position gp0 of
+    // the generator's stream, into buffer `buf`.  Returns the draws taken (warp 0).
+    auto produce = [&](const int buf, const int gp_w0) -> int {  // gp_w0: the stream position, known to warp 0
+      const UniformMap umap = make_uniform_map(static_cast<uint32_t>(n), args.uniform_variant);
+      // One group of 32 hypotheses from the stream position t_first (RANSAC.hpp:81-87).  Almost always every
+      // iteration takes exactly three draws (a rejection in the distribution or a repeated sample has probability ~3/n),
+      // so the next kTape generator outputs are tempered in parallel and lane h takes outputs from 3h on.  Lane h
+      // consumes tape entries from 3h + (extra draws of the hypotheses before it) until it holds three distinct accepted
+      // values; the extra draws shift everything behind them, so the offsets are iterated to a fixed point: a prefix sum
+      // of the lanes' extra draws per pass, normally one pass.  Returns the draws the group took, or -1 if it did not
+      // settle inside the tape; `cum` = draws up to and including this lane's hypothesis.
+      auto sample_group = [&](const int t_first, int& a, int& b, int& c, int& cum) -> int {
+        uint32_t* tape = s.tape[warp];
+        for (int j = lane; j < kTape; j += 32) tape[j] = gen_word(s, t_first + j);
+        __syncwarp();
+        int off = 0, extra = 0;
+        bool ok = false;
+        for (int pass = 0; pass < 6; ++pass) {
+          int pos = 3 * lane + off, cnt = 0;
+          a = b = c = -1;
+          while (cnt < 3 && pos < kTape) {
+            int vv;
+            if (!accept_draw(umap, tape[pos++], vv)) continue;  // the distribution draws again
+            if (vv == a || vv == b || vv == c) continue;        // std::set already holds it
+            if (cnt == 0) a = vv;
+            else if (cnt == 1) { if (vv < a) { b = a; a = vv; } else b = vv; }
+            else {
+              if (vv < a) { c = b; b = a; a = vv; }
+              else if (vv < b) { c = b; b = vv; }
+              else c = vv;
             }
-            if (ok) {
+            ++cnt;
+          }
+          const bool complete = cnt == 3;
+          extra = pos - (3 * lane + off) - 3;
+          int incl = extra;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= o) incl += t;
+          }
+          const int new_off = incl - extra;
+          const bool stable = __all_sync(kFullMask, complete && new_off == off);
+          off = new_off;
+          if (stable) {
+            ok = true;
+            break;
+          }
+          if (!__all_sync(kFullMask, complete)) break;  // ran off the tape
+        }
+        __syncwarp();
+        cum = 3 * (lane + 1) + off + extra;
+        return ok ? __shfl_sync(kFullMask, cum, 31) : -1;
+      };
+      auto prod_bar = [] { asm volatile("bar.sync 1, %0;" ::"n"(kProdWarps * 32) : "memory"); };
+
+      // The four groups of the round are sampled side by side, one per producer warp, group w assuming that the groups
+      // before it took exactly 96 draws each.  Where that turns out wrong (a group with extra draws) the groups behind
+      // it go again from their true offsets; group w is certainly right after pass w.
+      if (warp == 0) {
+        gen_cover(s, args.mt_init, lane, gen_hi, gp_w0, gp_w0 + kSub * kTape - 1);
+        if (lane == 0) s.prod_gp0 = gp_w0;
+      }
+      prod_bar();
+      const int gp0 = s.prod_gp0;
+      int start = 96 * warp, used = 0, a = -1, b = -1, c = -1, cum = 0;
+      bool settled = false, serial = false;
+      for (int it = 0; it < kSub && !settled; ++it) {
+        if (it == 0 || s.grp_start[warp] != start) {
+          used = sample_group(gp0 + start, a, b, c, cum);
+          if (lane == 0) {
+            s.grp_start[warp] = start;
+            s.grp_used[warp] = used;
+          }
+        }
+        prod_bar();
+        int sum = 0, mine_start = 0;
+        settled = true;
+#pragma unroll
+        for (int w = 0; w < kSub; ++w) {
+          const int u = s.grp_used[w];
+          if (w == warp) mine_start = sum;
+          if (u < 0) serial = true;
+          if (s.grp_start[w] != sum) settled = false;
+          sum += u;
+        }
+        prod_bar();  // everybody has read the table before the next pass rewrites it
+        if (serial) break;
+        start = mine_start;
+        used = sum;  // total of the round (final once settled)
+      }
+      if (serial || !settled) {
+        // exact path: warp 0 walks the groups in order, a group that does not settle draw by draw
+        if (warp == 0) {
+          int t0 = gp0;
+          for (int sub = 0; sub < kSub; ++sub) {
+            gen_cover(s, args.mt_init, lane, gen_hi, t0, t0 + kTape - 1);
+            int ga, gb, gc, gcum;
+            const int gused = sample_group(t0, ga, gb, gc, gcum);
+            if (gused >= 0) {
               const int h = 32 * sub + lane;
-              s.rank[h][0] = a; s.rank[h][1] = b; s.rank[h][2] = c;
-              const int cum = 3 * (lane + 1) + off + extra;  // draws of this group up to and including hypothesis `lane`
-              s.draws_cum[h] = draws_base + cum;
-              const int used = __shfl_sync(kFullMask, cum, 31);
-              if (!twisted) {
-                mt_idx = idx0 + used;
-              } else if (used > avail) {
-                mt_idx = used - avail;  // inside the block the tape has already generated
-                twisted_round = true;
-              } else {
-                // the draws end inside the old block after all: back to it
-                for (int i = lane; i < kMtN; i += 32) s.mt[i] = s.mt_bak[i];
-                __syncwarp();
-                mt_idx = idx0 + used;
-              }
-              draws_base += used;
+              s.rank[h][0] = ga; s.rank[h][1] = gb; s.rank[h][2] = gc;
+              s.draws_cum[buf][h] = t0 - gp0 + gcum;
+              t0 += gused;
             } else {
-              if (twisted) {
-                for (int i = lane; i < kMtN; i += 32) s.mt[i] = s.mt_bak[i];
-                __syncwarp();
-              }
-              int draws = 0;
               for (int hh = 0; hh < 32; ++hh) {
                 int sa = -1, sb = -1, sc = -1, cnt = 0;  // the std::set<int>, kept sorted
                 while (cnt < 3) {
-                  const int vv = uniform_below_warp(s, lane, mt_idx, umap, draws);
+                  const int vv = uniform_below_warp(s, args.mt_init, lane, gen_hi, t0, umap);
                   if (vv == sa || vv == sb || vv == sc) continue;
                   if (cnt == 0) sa = vv;
                   else if (cnt == 1) { if (vv < sa) { sb = sa; sa = vv; } else sb = vv; }
@@ -437,166 +472,174 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
                 if (lane == 0) {
                   const int h = 32 * sub + hh;
                   s.rank[h][0] = sa; s.rank[h][1] = sb; s.rank[h][2] = sc;
-                  s.draws_cum[h] = draws_base + draws;
+                  s.draws_cum[buf][h] = t0 - gp0;
                 }
               }
-              draws_base += draws;
-              if (mt_idx < idx0) twisted_round = true;  // the generator moved on to its next block
             }
             __syncwarp();
           }
+          used = t0 - gp0;
         }
-        if (tid < kHyp) s.loss[tid] = 0;
-        __syncthreads();
-        REF_PROBE(0);  // sampling
-        if (tid < kHyp * 3) s.pix[tid / 3][tid % 3] = kth_pixel(lc, rows_ok ? s.rowstart : nullptr, s.rank[tid / 3][tid % 3], p, nh, g.width);
-        __syncthreads();
-        if (tid < kHyp) {
-          // PlaneEstimator::ComputeModel (Plane.hpp:13-43), fp32 in the reference's expression order
-          float x0, y0, z0, x1, y1, z1, x2, y2, z2;
-          load_point<LAYOUT>(xyz, g.n_points, s.pix[tid][0], x0, y0, z0);
-          load_point<LAYOUT>(xyz, g.n_points, s.pix[tid][1], x1, y1, z1);
-          load_point<LAYOUT>(xyz, g.n_points, s.pix[tid][2], x2, y2, z2);
-          const f32 X0(x0), X1(x1), X2(x2), Y0(y0), Y1(y1), Y2(y2), Z0(z0), Z1(z1), Z2(z2);
-          const f32 D = X0 * Y1 - X1 * Y0 - X0 * Y2 + X2 * Y0 + X1 * Y2 - X2 * Y1;
-          const f32 a = (Z0 * (Y1 - Y2)) / D - (Z1 * (Y0 - Y2)) / D + (Z2 * (Y0 - Y1)) / D;
-          const f32 b = (Z1 * (X0 - X2)) / D - (Z0 * (X1 - X2)) / D - (Z2 * (X0 - X1)) / D;
-          const f32 d = (Z2 * (X0 * Y1 - X1 * Y0)) / D - (Z1 * (X0 * Y2 - X2 * Y0)) / D + (Z0 * (X1 * Y2 - X2 * Y1)) / D;
-          const f32 c(-1.0f);
-          // `sqrt(float)` in Plane.hpp:36 resolves to ::sqrt(double): double square root, rounded to float on assignment
-          const f32 l(__double2float_rn(__dsqrt_rn(static_cast<double>((a * a + b * b + c * c).v))));
-          // pushed into every CTA's shared memory (fire-and-forget stores, visible after the cluster barrier): 1024
-          // threads per CTA fetching them from the leader afterwards queue up on its distributed-shared-memory port
-          const float4 mv = make_float4((a / l).v, (b / l).v, (c / l).v, (d / l).v);
+        prod_bar();
+        a = s.rank[tid][0]; b = s.rank[tid][1]; c = s.rank[tid][2];
+      } else {
+        s.draws_cum[buf][tid] = start + cum;
+      }
+      REF_PROBE(0);  // sampling
+      // this thread's hypothesis: ranks -> pixels -> model
+      const int* rs = rows_ok ? s.rowstart : nullptr;
+      const long long pa = kth_pixel(lc, rs, a, p, nh, g.width), pb = kth_pixel(lc, rs, b, p, nh, g.width), pc = kth_pixel(lc, rs, c, p, nh, g.width);
+      {
+        // PlaneEstimator::ComputeModel (Plane.hpp:13-43), fp32 in the reference's expression order
+        float x0, y0, z0, x1, y1, z1, x2, y2, z2;
+        load_point<LAYOUT>(xyz, g.n_points, pa, x0, y0, z0);
+        load_point<LAYOUT>(xyz, g.n_points, pb, x1, y1, z1);
+        load_point<LAYOUT>(xyz, g.n_points, pc, x2, y2, z2);
+        const f32 X0(x0), X1(x1), X2(x2), Y0(y0), Y1(y1), Y2(y2), Z0(z0), Z1(z1), Z2(z2);
+        const f32 D = X0 * Y1 - X1 * Y0 - X0 * Y2 + X2 * Y0 + X1 * Y2 - X2 * Y1;
+        const f32 a = (Z0 * (Y1 - Y2)) / D - (Z1 * (Y0 - Y2)) / D + (Z2 * (Y0 - Y1)) / D;
+        const f32 b = (Z1 * (X0 - X2)) / D - (Z0 * (X1 - X2)) / D - (Z2 * (X0 - X1)) / D;
+        const f32 d = (Z2 * (X0 * Y1 - X1 * Y0)) / D - (Z1 * (X0 * Y2 - X2 * Y0)) / D + (Z0 * (X1 * Y2 - X2 * Y1)) / D;
+        const f32 c(-1.0f);
+        // `sqrt(float)` in Plane.hpp:36 resolves to ::sqrt(double): double square root, rounded to float on assignment
+        const f32 l(__double2float_rn(__dsqrt_rn(static_cast<double>((a * a + b * b + c * c).v))));
+        // pushed into every CTA's shared memory (fire-and-forget stores, visible after the next cluster barrier): 512
+        // threads per CTA fetching them from the leader afterwards queue up on its distributed-shared-memory port
+        const float4 mv = make_float4((a / l).v, (b / l).v, (c / l).v, (d / l).v);
 #pragma unroll
-          for (int r = 0; r < kRefCluster; ++r) *reinterpret_cast<float4*>(cluster.map_shared_rank(&s.model[tid][0], r)) = mv;
-        }
+        for (int r = 0; r < kRefCluster; ++r) *reinterpret_cast<float4*>(cluster.map_shared_rank(&s.model[buf][tid][0], r)) = mv;
       }
       REF_PROBE(1);  // ranks -> pixels, models
-      cluster.sync();  // (1) the kHyp models and the zeroed losses are in the leader's shared memory
-      REF_PROBE(2);
-      {
-        // EvaluateModel (RANSAC.hpp:89-98): lane g scores hypotheses g, g + 32, ...; loss += (fabs(error) >= threshold)
-        float m[kSub][4];
+      return used;
+    };
+
+    if (go_on) {
+      int buf = 0, draws_cur = 0, draws_next = 0;
+      REF_PROBE(6);
+      if (producer) draws_cur = produce(0, gp);  // the first round of a label has nothing to hide behind
+      if (leader && tid < kHyp) s.loss[tid] = 0;
+      cluster.sync();  // round 0's models are in every CTA, the leader's counters are zero
+      REF_PROBE(7);
+      for (;;) {
+        if (producer) {
+          // the next round, as if this one ran all its iterations (it does, except the last round of a label)
+          draws_next = produce(buf ^ 1, gp + draws_cur);
+        } else {
+          // EvaluateModel (RANSAC.hpp:89-98): lane g scores hypotheses g, g + 32, ...; loss += (fabs(error) >= threshold)
+          float m[kSub][4];
 #pragma unroll
-        for (int j = 0; j < kSub; ++j)
+          for (int j = 0; j < kSub; ++j)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) m[j][k] = s.model[32 * j + lane][k];
-        unsigned loss[kSub];
+            for (int k = 0; k < 4; ++k) m[j][k] = s.model[buf][32 * j + lane][k];
+          unsigned loss[kSub];
 #pragma unroll
-        for (int j = 0; j < kSub; ++j) loss[j] = 0;
-        for (int e0 = gwarp * 32; e0 < n; e0 += kStride) {
-          const int e = e0 + lane;
-          float x = 0.f, y = 0.f, z = 0.f;
-          if (e < n) {
-            const int t = e / p2, in = e - t * p2;
-            const int cell = lc.cells[t];
-            const int r = cell / nh, q = cell - r * nh;
-            const int i = in / p, j = in - i * p;
-            load_point<LAYOUT>(xyz, g.n_points, static_cast<long long>(r * p + i) * g.width + q * p + j, x, y, z);
-          }
-          s.stage[warp][lane] = make_float4(x, y, z, 0.f);
-          __syncwarp();
-          const int cnt = min(32, n - e0);
-          for (int k = 0; k < cnt; ++k) {
-            const float4 pt = s.stage[warp][k];
-#pragma unroll
-            for (int j = 0; j < kSub; ++j) {
-              // the reference compares fabs(double(error)) with double(float threshold): the same predicate in fp32
-              loss[j] += (::fabsf(plane_error(m[j], pt.x, pt.y, pt.z)) >= thr_f) ? 1u : 0u;
+          for (int j = 0; j < kSub; ++j) loss[j] = 0;
+          for (int e0 = swarp * 32; e0 < n; e0 += kScoreStride) {
+            const int e = e0 + lane;
+            float x = 0.f, y = 0.f, z = 0.f;
+            if (e < n) {
+              const int t = e / p2, in = e - t * p2;
+              const int cell = lc.cells[t];
+              const int r = cell / nh, q = cell - r * nh;
+              const int i = in / p, j = in - i * p;
+              load_point<LAYOUT>(xyz, g.n_points, static_cast<long long>(r * p + i) * g.width + q * p + j, x, y, z);
             }
-          }
-          __syncwarp();
-        }
-        // per-warp counts -> this CTA's totals -> one distributed-shared-memory atomic per hypothesis and CTA
-        // (128 warps adding straight into the leader's counters serialise there)
+            s.stage[warp][lane] = make_float4(x, y, z, 0.f);
+            __syncwarp();
+            const int cnt = min(32, n - e0);
+            for (int k = 0; k < cnt; ++k) {
+              const float4 pt = s.stage[warp][k];
 #pragma unroll
-        for (int j = 0; j < kSub; ++j)
-          if (loss[j]) atomicAdd(&s.loss_cta[32 * j + lane], loss[j]);
+              for (int j = 0; j < kSub; ++j) {
+                // the reference compares fabs(double(error)) with double(float threshold): the same predicate in fp32
+                loss[j] += (::fabsf(plane_error(m[j], pt.x, pt.y, pt.z)) >= thr_f) ? 1u : 0u;
+              }
+            }
+            __syncwarp();
+          }
+          // per-warp counts -> this CTA's totals -> one distributed-shared-memory atomic per hypothesis and CTA
+          // (all warps adding straight into the leader's counters serialise there)
+#pragma unroll
+          for (int j = 0; j < kSub; ++j)
+            if (loss[j]) atomicAdd(&s.loss_cta[32 * j + lane], loss[j]);
+          REF_PROBE(8);  // scoring (the leader's first scoring warp)
+        }
         __syncthreads();
+        REF_PROBE(2);  // producers: waiting for the scorers; scorers: waiting for the CTA
         if (tid < kHyp) {
           const unsigned v = s.loss_cta[tid];
           s.loss_cta[tid] = 0;
           if (v) atomicAdd(&lead->loss[tid], v);
         }
-      }
-      REF_PROBE(3);  // scoring
-      cluster.sync();  // (2) every CTA's counts are in
-      REF_PROBE(4);
-      if (leader) {
-        if (warp == 1) {
-          // The reference's sequential loop over these hypotheses (RANSAC.hpp:33-46), evaluated by one warp, 32 at a time:
-          // lane h owns hypothesis h of the group.  The best-so-far loss before hypothesis h is a prefix minimum; the loop
-          // runs while IsContinued holds, which is monotone (the best loss only falls, the iteration count only grows), so
-          // the number of iterations really run is the number of hypotheses whose check passes.
-          const double inf = HUGE_VAL;
-          double best0 = s.bestloss;
-          int iter0 = s.iteration;
-          int consumed_all = 0;
-          for (int sub = 0; sub < kSub; ++sub) {
-            const double mine = static_cast<double>(s.loss[32 * sub + lane]);
-            double incl = mine;
+        cluster.sync();  // (1) every CTA's counts are in
+        REF_PROBE(3);
+        if (leader && warp == 0) {
+          // The reference's sequential loop over these hypotheses (RANSAC.hpp:33-46), evaluated by one warp: lane l owns
+          // hypotheses 4l .. 4l+3.  The best-so-far loss before a hypothesis is a prefix minimum; the loop runs while
+          // IsContinued holds, which is monotone (the best loss only falls, the iteration count only grows), so the number
+          // of iterations really run is the number of hypotheses whose check passes.  Losses are counts: the reference's
+          // doubles hold the same integers, HUGE_VAL is kNoLoss here.
+          const unsigned best0 = s.bestloss;
+          const int iter0 = s.iteration;
+          const uint4 v4 = *reinterpret_cast<const uint4*>(&s.loss[4 * lane]);
+          *reinterpret_cast<uint4*>(&s.loss[4 * lane]) = make_uint4(0, 0, 0, 0);  // for the next round
+          const unsigned mine[4] = {v4.x, v4.y, v4.z, v4.w};
+          const unsigned p0 = mine[0], p1 = min(p0, mine[1]), p2m = min(p1, mine[2]), p3 = min(p2m, mine[3]);
+          unsigned incl = p3;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-              const double t = __shfl_up_sync(kFullMask, incl, o);
-              if (lane >= o) incl = ::fmin(incl, t);
-            }
-            double before = __shfl_up_sync(kFullMask, incl, 1);
-            if (lane == 0) before = inf;
-            before = ::fmin(before, best0);
-            const int inl = ::isinf(before) ? INT_MIN : static_cast<int>(n - before);
-            const bool go_h = (iter0 + lane < args.max_iterations) && (static_cast<double>(inl) < ratio * n);
-            const int consumed = __popc(__ballot_sync(kFullMask, go_h));
-            // best loss over the iterations really run, and the first of them that reaches it (strict '<' updates)
-            double best = lane < consumed ? mine : inf;
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= o) incl = min(incl, t);
+          }
+          unsigned ex = __shfl_up_sync(kFullMask, incl, 1);
+          if (lane == 0) ex = kNoLoss;
+          ex = min(ex, best0);
+          const unsigned before[4] = {ex, min(ex, p0), min(ex, p1), min(ex, p2m)};
+          const double target = ratio * n;
+          int consumed = 0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) best = ::fmin(best, __shfl_xor_sync(kFullMask, best, o));
-            const unsigned hit = __ballot_sync(kFullMask, lane < consumed && mine == best);
-            if (hit && best < best0) {
-              if (lane == 0) {
-                const int winner = 32 * sub + __ffs(hit) - 1;
-                s.best[0] = s.model[winner][0]; s.best[1] = s.model[winner][1]; s.best[2] = s.model[winner][2]; s.best[3] = s.model[winner][3];
-              }
-              best0 = best;
-            }
-            iter0 += consumed;
-            consumed_all += consumed;
-            if (consumed < 32) break;
+          for (int j = 0; j < 4; ++j) {
+            // IsContinued(iteration, N - best loss, N); int(N - HUGE_VAL) is INT_MIN on x86-64
+            const int inl = before[j] == kNoLoss ? INT_MIN : n - static_cast<int>(before[j]);
+            const bool go_h = (iter0 + 4 * lane + j < args.max_iterations) && (static_cast<double>(inl) < target);
+            consumed += __popc(__ballot_sync(kFullMask, go_h));
+          }
+          // best loss over the iterations really run, and the first of them that reaches it (strict '<' updates)
+          unsigned cand = kNoLoss;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (4 * lane + j < consumed) cand = min(cand, mine[j]);
+          const unsigned best = __reduce_min_sync(kFullMask, cand);
+          unsigned bl = best0;
+          if (best < best0) {
+            unsigned first = kNoLoss;
+#pragma unroll
+            for (int j = 3; j >= 0; --j)
+              if (4 * lane + j < consumed && mine[j] == best) first = 4 * lane + j;
+            const unsigned winner = __reduce_min_sync(kFullMask, first);
+            if (lane < 4) s.best[lane] = s.model[buf][winner][lane];
+            bl = best;
+          }
+          bool go = consumed == kHyp;
+          if (go) {
+            const int inl2 = bl == kNoLoss ? INT_MIN : n - static_cast<int>(bl);
+            go = (iter0 + consumed < args.max_iterations) && (static_cast<double>(inl2) < target);
           }
           if (lane == 0) {
-            s.bestloss = best0;
-            s.iteration = iter0;
-            bool go = consumed_all == kHyp;
-            if (go) {
-              const int inl2 = ::isinf(best0) ? INT_MIN : static_cast<int>(n - best0);
-              go = (s.iteration < args.max_iterations) && (static_cast<double>(inl2) < ratio * n);
-            }
-            s.consumed = consumed_all;
-            for (int r = 0; r < kRefCluster; ++r) *cluster.map_shared_rank(&s.go_on, r) = go ? 1 : 0;
+            s.bestloss = bl;
+            s.iteration = iter0 + consumed;
           }
+          // the generator stops just after the last iteration the reference ran; the round prepared ahead is dropped
+          gp += consumed > 0 ? s.draws_cum[buf][consumed - 1] : 0;
+          if (lane < kRefCluster) *cluster.map_shared_rank(&s.go_on, lane) = go ? 1 : 0;
         }
-        __syncthreads();
-        if (warp == 0 && s.consumed < kHyp) {
-          // the search stopped inside the round: leave the generator just after the last iteration the reference ran
-          for (int i = lane; i < kMtN; i += 32) s.mt[i] = s.mt_bak[i];
-          mt_idx = mt_idx_bak;
-          __syncwarp();
-          int redo = s.consumed > 0 ? s.draws_cum[s.consumed - 1] : 0;
-          while (redo > 0) {  // advancing the generator is moving its position, block by block
-            if (mt_idx >= kMtN) {
-              mt_twist_warp(s.mt, lane);
-              __syncwarp();
-              mt_idx = 0;
-            }
-            const int step = min(redo, kMtN - mt_idx);
-            mt_idx += step;
-            redo -= step;
-          }
-        }
+        REF_PROBE(4);  // evaluate
+        cluster.sync();  // (2) the decision is visible
+        REF_PROBE(5);
+        if (!s.go_on) break;
+        buf ^= 1;
+        draws_cur = draws_next;
       }
-      REF_PROBE(5);  // evaluate + generator
-      cluster.sync();  // (3) the decision is visible
-      go_on = s.go_on;
     }
 
     // ---- FindInliers + relabelling (RANSAC.hpp:53-62, plane_extractor.cpp:498-507) ---------------------------
@@ -639,9 +682,9 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
 }  // namespace dpx
 extern "C" __attribute__((visibility("default"))) int dpx_debug_refine_probe(long long* out, int reset) {
   cudaDeviceSynchronize();
-  if (out) cudaMemcpyFromSymbol(out, dpx::g_refine_probe, sizeof(long long) * 8);
+  if (out) cudaMemcpyFromSymbol(out, dpx::g_refine_probe, sizeof(long long) * 24);
   if (reset) {
-    long long zero[8] = {};
+    long long zero[24] = {};
     cudaMemcpyToSymbol(dpx::g_refine_probe, zero, sizeof(zero));
   }
   return 0;

@@ -13,10 +13,12 @@ for name in ("tum", "icl"):
     d = torch.from_numpy(xyz).cuda()
     for _ in range(2):
         ex.process_batch_device(d, LAYOUT_ROWMAJOR)
-    buf = (C.c_longlong * 8)()
+    buf = (C.c_longlong * 24)()
     lib.dpx_debug_refine_probe(buf, 1)
     ex.process_batch_device(d, LAYOUT_ROWMAJOR)
     lib.dpx_debug_refine_probe(buf, 0)
-    names = ["sampling", "pixels+models", "barrier 1", "scoring", "barrier 2", "evaluate+generator", "barrier 3 + loop"]
-    tot = sum(buf[:7])
-    print(name, "cycles:", {n: int(v) for n, v in zip(names, buf[:7])}, "total", tot, "= %.2f ms" % (tot / 1.965e6))
+    names = ["sampling", "pixels+models", "wait for the CTA", "flush + barrier 1", "evaluate", "barrier 2", "label setup",
+             "first-round barrier", "scoring"]
+    for who, off in (("producer thread 0", 0), ("first scoring thread", 12)):
+        tot = sum(buf[off:off + 9])
+        print(name, who, "cycles:", {n: int(v) for n, v in zip(names, buf[off:off + 9]) if v}, "total", tot, "= %.2f ms" % (tot / 1.965e6))
