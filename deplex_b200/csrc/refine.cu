@@ -34,6 +34,8 @@
 // passes: the largest inlier pixel index, then "non-inlier before it -> 0".
 #include "refine.cuh"
 
+#include <cstdio>
+
 #include <cooperative_groups.h>
 
 #include "exact_math.cuh"
@@ -74,28 +76,40 @@ struct RefShared {
   int32_t cells[kCellCache];  // per label, every CTA: a copy of the label's sorted cell list when it fits
 };
 
+#ifdef DPX_REFINE_PROBE
+__device__ long long g_refine_probe_cnt[2];  // twists, reseeds (frame 0)
+#endif
 // ---- std::mt19937, executed by warp 0 of the leader (all lanes compute the same values) -----------------------
 // The next block of 624 words from the current one, out of place:
 //   next[i] = (i < 227 ? cur[i + 397] : next[i - 227]) ^ f(cur[i], i < 623 ? cur[i + 1] : next[0]);
 // entries i >= 227 read entries of the new block, so the update runs in waves of 224 (<= 227, a multiple of 32).
-__device__ __forceinline__ void mt_next_block_warp(uint32_t* next, const uint32_t* cur, int lane) {
-  auto f = [](uint32_t a, uint32_t b) {
-    const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
-    return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-  };
-  for (int base = 0; base < kMtN; base += 224) {
-    const int end = min(base + 224, kMtN);
+template <int BASE>
+__device__ __forceinline__ void mt_wave(uint32_t* next, const uint32_t* cur, int lane) {
+  constexpr int END = BASE + 224 < kMtN ? BASE + 224 : kMtN;
+  uint32_t v[7];
+  // branch-free: the operand addresses are selected, every load is unconditional (lanes past the end compute a value they
+  // do not store), and all the loads of a wave come before its stores
 #pragma unroll
-    for (int k = 0; k < 7; ++k) {
-      const int i = base + k * 32 + lane;
-      if (i < end) {
-        const uint32_t far = i < 227 ? cur[i + 397] : next[i - 227];
-        const uint32_t nxt = i < kMtN - 1 ? cur[i + 1] : next[0];
-        next[i] = far ^ f(cur[i], nxt);
-      }
-    }
-    __syncwarp();
+  for (int k = 0; k < 7; ++k) {
+    if (BASE + k * 32 >= END) continue;
+    const int i = min(BASE + k * 32 + lane, kMtN - 1);
+    const uint32_t* far = BASE + k * 32 + 31 < 227 ? cur + i + 397 : BASE + k * 32 >= 227 ? next + i - 227 : (i < 227 ? cur + i + 397 : next + i - 227);
+    const uint32_t* nxt = BASE + k * 32 + 31 < kMtN - 1 ? cur + i + 1 : (i < kMtN - 1 ? cur + i + 1 : next);
+    const uint32_t y = (cur[i] & 0x80000000u) | (*nxt & 0x7fffffffu);
+    v[k] = *far ^ (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu);
   }
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    if (BASE + k * 32 >= END) continue;
+    const int i = BASE + k * 32 + lane;
+    if (i < END) next[i] = v[k];
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void mt_next_block_warp(uint32_t* next, const uint32_t* cur, int lane) {
+  mt_wave<0>(next, cur, lane);
+  mt_wave<224>(next, cur, lane);
+  mt_wave<448>(next, cur, lane);
 }
 
 __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
@@ -116,10 +130,16 @@ __device__ __forceinline__ void gen_cover(RefShared& s, const uint32_t* mt_init,
     for (int i = lane; i < kMtN; i += 32) s.mtb[0][i] = mt_init[i];
     __syncwarp();
     gen_hi = 0;
+#ifdef DPX_REFINE_PROBE
+    if (threadIdx.x == 0 && blockIdx.x == 0) g_refine_probe_cnt[1] += 1;
+#endif
   }
   while (gen_hi < b_hi) {
     mt_next_block_warp(s.mtb[(gen_hi + 1) % 3], s.mtb[gen_hi % 3], lane);
     ++gen_hi;
+#ifdef DPX_REFINE_PROBE
+    if (threadIdx.x == 0 && blockIdx.x == 0) g_refine_probe_cnt[0] += 1;
+#endif
   }
 }
 __device__ __forceinline__ uint32_t gen_word(const RefShared& s, int t) {
@@ -215,13 +235,17 @@ __device__ __forceinline__ float plane_error(const float (&m)[4], float x, float
 #ifdef DPX_REFINE_PROBE
 // probe builds only (make NVFLAGS_EXTRA=-DDPX_REFINE_PROBE, tools/refine_probe.py): cycles of the leader's thread 0 per phase
 __device__ long long g_refine_probe[24];  // [0, 12): the leader's thread 0 (a producer); [12, 24): its first scoring thread
-#define REF_PROBE(slot) do { if (leader && (tid == 0 || tid == kProdWarps * 32) && blockIdx.x < kRefCluster) { const long long t__ = clock64(); g_refine_probe[(tid ? 12 : 0) + slot] += t__ - rp_t; rp_t = t__; } } while (0)
+// (accumulated in registers and written once at the end: a global read-modify-write per probe would cost more than most phases)
+#define REF_PROBE(slot) do { const long long t__ = clock64(); rp_acc[slot] += t__ - rp_t; rp_t = t__; } while (0)
 #else
 #define REF_PROBE(slot) do { } while (0)
 #endif
 
-template <int LAYOUT>
-__global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs args) {
+// MINB = CTAs per SM the register budget is set for: 1 (~125 registers, nothing spilled) when the launch has no more CTAs
+// than the GPU has SMs -- the latency case -- and 2 (64 registers) for batches, where a second resident cluster per SM
+// fills the first one's barriers and serial phases.
+template <int LAYOUT, int MINB>
+__global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineArgs args) {
   __shared__ RefShared s;
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned crank = cluster.block_rank();
@@ -232,6 +256,7 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
   const int frame = blockIdx.x / kRefCluster;
 #ifdef DPX_REFINE_PROBE
   long long rp_t = clock64();
+  long long rp_acc[12] = {};
 #endif
   const int C = g.n_cells, p = g.patch, p2 = p * p, nh = g.nh;
   const long long fc = static_cast<long long>(frame) * C;
@@ -253,7 +278,7 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
   // during the search the leader's producer warps do not score: the other warps of the cluster share the points
   const bool producer = leader && warp < kProdWarps;
   const int swarp = gwarp - kProdWarps;
-  constexpr int kScoreStride = kStride - kProdWarps * 32;
+  constexpr int kScoreWarps = kRefCluster * kRefWarps - kProdWarps;
 
   // the generator (warp 0 of the leader): position of the next draw in the stream, newest block in the ring
   int gp = kMtN, gen_hi = 0;
@@ -362,6 +387,22 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
       // of the lanes' extra draws per pass, normally one pass.  Returns the draws the group took, or -1 if it did not
       // settle inside the tape; `cum` = draws up to and including this lane's hypothesis.
       auto sample_group = [&](const int t_first, int& a, int& b, int& c, int& cum) -> int {
+        {
+          // the common case first, straight from the generator's block: every lane's three outputs are accepted and
+          // distinct, so the group takes exactly 96 draws
+          int v0, v1, v2;
+          const bool k0 = accept_draw(umap, gen_word(s, t_first + 3 * lane), v0);
+          const bool k1 = accept_draw(umap, gen_word(s, t_first + 3 * lane + 1), v1);
+          const bool k2 = accept_draw(umap, gen_word(s, t_first + 3 * lane + 2), v2);
+          if (__all_sync(kFullMask, k0 && k1 && k2 && v0 != v1 && v0 != v2 && v1 != v2)) {
+            const int lo = min(v0, v1), hi = max(v0, v1);
+            a = min(lo, v2);
+            c = max(hi, v2);
+            b = max(lo, min(hi, v2));
+            cum = 3 * (lane + 1);
+            return 96;
+          }
+        }
         uint32_t* tape = s.tape[warp];
         for (int j = lane; j < kTape; j += 32) tape[j] = gen_word(s, t_first + j);
         __syncwarp();
@@ -409,10 +450,12 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
       // The four groups of the round are sampled side by side, one per producer warp, group w assuming that the groups
       // before it took exactly 96 draws each.  Where that turns out wrong (a group with extra draws) the groups behind
       // it go again from their true offsets; group w is certainly right after pass w.
+      REF_PROBE(11);
       if (warp == 0) {
         gen_cover(s, args.mt_init, lane, gen_hi, gp_w0, gp_w0 + kSub * kTape - 1);
         if (lane == 0) s.prod_gp0 = gp_w0;
       }
+      REF_PROBE(9);  // generator blocks
       prod_bar();
       const int gp0 = s.prod_gp0;
       int start = 96 * warp, used = 0, a = -1, b = -1, c = -1, cum = 0;
@@ -426,6 +469,7 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
           }
         }
         prod_bar();
+        REF_PROBE(10);  // group sampling
         int sum = 0, mine_start = 0;
         settled = true;
 #pragma unroll
@@ -534,10 +578,14 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
           unsigned loss[kSub];
 #pragma unroll
           for (int j = 0; j < kSub; ++j) loss[j] = 0;
-          for (int e0 = swarp * 32; e0 < n; e0 += kScoreStride) {
+          // an equal share of the label's points for every scoring warp (dealing whole chunks of 32 leaves some warps a
+          // chunk more than others: a quarter of the round idle on a 13 000-point label)
+          const int e_lo = static_cast<int>(static_cast<long long>(swarp) * n / kScoreWarps);
+          const int e_hi = static_cast<int>(static_cast<long long>(swarp + 1) * n / kScoreWarps);
+          for (int e0 = e_lo; e0 < e_hi; e0 += 32) {
             const int e = e0 + lane;
             float x = 0.f, y = 0.f, z = 0.f;
-            if (e < n) {
+            if (e < e_hi) {
               const int t = e / p2, in = e - t * p2;
               const int cell = lc.cells[t];
               const int r = cell / nh, q = cell - r * nh;
@@ -546,7 +594,7 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
             }
             s.stage[warp][lane] = make_float4(x, y, z, 0.f);
             __syncwarp();
-            const int cnt = min(32, n - e0);
+            const int cnt = min(32, e_hi - e0);
             for (int k = 0; k < cnt; ++k) {
               const float4 pt = s.stage[warp][k];
 #pragma unroll
@@ -674,6 +722,10 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
     cluster.sync();  // nobody still reads this label's state when the leader resets it for the next one
   }
   cluster.sync();  // no CTA leaves while another may still touch its shared memory
+#ifdef DPX_REFINE_PROBE
+  if (leader && (tid == 0 || tid == kProdWarps * 32) && blockIdx.x < kRefCluster)
+    for (int i = 0; i < 12; ++i) g_refine_probe[(tid ? 12 : 0) + i] += rp_acc[i];
+#endif
 }
 
 }  // namespace
@@ -683,6 +735,11 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const RefineArgs ar
 extern "C" __attribute__((visibility("default"))) int dpx_debug_refine_probe(long long* out, int reset) {
   cudaDeviceSynchronize();
   if (out) cudaMemcpyFromSymbol(out, dpx::g_refine_probe, sizeof(long long) * 24);
+  {
+    long long cnt[2];
+    cudaMemcpyFromSymbol(cnt, dpx::g_refine_probe_cnt, sizeof(cnt));
+    fprintf(stderr, "[refine probe] twists %lld reseeds %lld (since load)\n", cnt[0], cnt[1]);
+  }
   if (reset) {
     long long zero[24] = {};
     cudaMemcpyToSymbol(dpx::g_refine_probe, zero, sizeof(zero));
@@ -711,8 +768,16 @@ cudaError_t launch_refine(const RefineArgs& args, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (args.layout == kLayoutRowMajor) return cudaLaunchKernelEx(&cfg, refine_kernel<kLayoutRowMajor>, args);
-  return cudaLaunchKernelEx(&cfg, refine_kernel<kLayoutColMajor>, args);
+  static const int n_sm = [] {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v;
+  }();
+  const bool one_per_sm = args.n_frames * kRefCluster <= n_sm;
+  if (args.layout == kLayoutRowMajor)
+    return one_per_sm ? cudaLaunchKernelEx(&cfg, refine_kernel<kLayoutRowMajor, 1>, args) : cudaLaunchKernelEx(&cfg, refine_kernel<kLayoutRowMajor, 2>, args);
+  return one_per_sm ? cudaLaunchKernelEx(&cfg, refine_kernel<kLayoutColMajor, 1>, args) : cudaLaunchKernelEx(&cfg, refine_kernel<kLayoutColMajor, 2>, args);
 }
 
 }  // namespace dpx

@@ -18,7 +18,7 @@ for name in ("tum", "icl"):
     ex.process_batch_device(d, LAYOUT_ROWMAJOR)
     lib.dpx_debug_refine_probe(buf, 0)
     names = ["sampling", "pixels+models", "wait for the CTA", "flush + barrier 1", "evaluate", "barrier 2", "label setup",
-             "first-round barrier", "scoring"]
+             "first-round barrier", "scoring", "generator blocks", "group sampling + producer barriers", "round entry"]
     for who, off in (("producer thread 0", 0), ("first scoring thread", 12)):
-        tot = sum(buf[off:off + 9])
-        print(name, who, "cycles:", {n: int(v) for n, v in zip(names, buf[off:off + 9]) if v}, "total", tot, "= %.2f ms" % (tot / 1.965e6))
+        tot = sum(buf[off:off + 12])
+        print(name, who, "cycles:", {n: int(v) for n, v in zip(names, buf[off:off + 12]) if v}, "total", tot, "= %.2f ms" % (tot / 1.965e6))
