@@ -54,6 +54,9 @@ constexpr int kCellCache = 4096;  // cells of one label cached in shared memory 
 namespace cg = cooperative_groups;
 constexpr unsigned kFullMask = 0xffffffffu;
 
+#ifndef DPX_LEADER_IDLE
+#define DPX_LEADER_IDLE 4
+#endif
 constexpr int kProdWarps = 4;  // the leader's producer warps (kProdWarps * 32 == kHyp)
 constexpr unsigned kNoLoss = 0xffffffffu;  // "no hypothesis accepted yet" (the reference's HUGE_VAL best loss)
 
@@ -192,13 +195,44 @@ struct LabelCells {
   int count;             // number of cells
 };
 
+// Division by a number fixed for the whole kernel (patch size, cells per row): multiply-shift with a round-up multiplier,
+// exact for dividends in [0, 2^31) (Granlund-Montgomery: m = ceil(2^(31+l) / d), l = ceil(log2 d), fits 32 bits).
+// The index arithmetic of this kernel is divisions, and an integer division by a run-time value is ~25 instructions.
+struct FastDiv {
+  uint32_t mul;
+  int shift;
+};
+__device__ __forceinline__ FastDiv make_fastdiv(int d) {
+  const int l = 32 - __clz(static_cast<unsigned>(d) - 1u);
+  FastDiv f;
+  f.mul = static_cast<uint32_t>(((1ull << (31 + l)) + static_cast<unsigned>(d) - 1ull) / static_cast<unsigned>(d));
+  f.shift = 31 + l;
+  return f;
+}
+__device__ __forceinline__ int fdiv(int x, const FastDiv& f) {
+  return static_cast<int>((static_cast<unsigned long long>(static_cast<unsigned>(x)) * f.mul) >> f.shift);
+}
+// u / m for 0 <= u, 0 < m, both below 2^24 when `small`: the fp32 quotient is off by at most one, fixed up exactly
+__device__ __forceinline__ int div_small(int u, int m, bool small) {
+  if (!small) return u / m;
+  int q = static_cast<int>(__fmul_rn(static_cast<float>(u), __frcp_rn(static_cast<float>(m))));
+  const int rem = u - q * m;
+  if (rem < 0) --q;
+  else if (rem >= m) ++q;
+  return q;
+}
+struct IndexMath {
+  FastDiv by_p2, by_nh, by_p;
+  int p, p2, nh, width;
+  bool narrow;  // width < 2^24
+};
+
 // The k-th pixel (image order) among the pixels of a label whose cells are `lc` (plane_extractor.cpp:473-478 builds
 // this list explicitly).  A cell row holding m of the label's cells contributes p image rows of m*p pixels each.
 // rowstart[r] = index of the label's first cell in cell row r (rowstart[nv] = count), or nullptr to search.
-__device__ __forceinline__ long long kth_pixel(const LabelCells& lc, const int* rowstart, int k, int p, int nh, int width) {
-  const int p2 = p * p;
-  const int t = k / p2;
-  const int r = lc.cells[t] / nh;  // cell row containing rank k
+__device__ __forceinline__ long long kth_pixel(const LabelCells& lc, const int* rowstart, int k, const IndexMath& im) {
+  const int t = fdiv(k, im.by_p2);
+  const int r = fdiv(lc.cells[t], im.by_nh);  // cell row containing rank k
   int s, e;
   if (rowstart) {
     s = rowstart[r];
@@ -206,16 +240,16 @@ __device__ __forceinline__ long long kth_pixel(const LabelCells& lc, const int* 
   } else {
     s = t;
     e = t + 1;
-    while (s > 0 && lc.cells[s - 1] / nh == r) --s;
-    while (e < lc.count && lc.cells[e] / nh == r) ++e;
+    while (s > 0 && fdiv(lc.cells[s - 1], im.by_nh) == r) --s;
+    while (e < lc.count && fdiv(lc.cells[e], im.by_nh) == r) ++e;
   }
   const int m = e - s;
-  const int kk = k - s * p2;
-  const int i = kk / (p * m), rem = kk - i * (p * m);
-  const int j = rem / p, xo = rem - j * p;
+  const int kk = k - s * im.p2;          // rank inside the row: kk = (i * m + j) * p + xo
+  const int u = fdiv(kk, im.by_p), xo = kk - u * im.p;
+  const int i = div_small(u, m, im.narrow), j = u - i * m;  // u < m * p <= width
   const int cell = lc.cells[s + j];
-  const int q = cell - r * nh;
-  return static_cast<long long>(r * p + i) * width + q * p + xo;
+  const int q = cell - r * im.nh;
+  return static_cast<long long>(r * im.p + i) * im.width + q * im.p + xo;
 }
 
 template <int LAYOUT>
@@ -260,6 +294,10 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
 #endif
   const int C = g.n_cells, p = g.patch, p2 = p * p, nh = g.nh;
   const long long fc = static_cast<long long>(frame) * C;
+  IndexMath im;
+  im.by_p2 = make_fastdiv(p2); im.by_nh = make_fastdiv(nh); im.by_p = make_fastdiv(p);
+  im.p = p; im.p2 = p2; im.nh = nh; im.width = g.width;
+  im.narrow = g.width < (1 << 24);
   const int nseg = args.tables.n_planes[frame];
   if (nseg <= 0) return;  // no plane: nothing is labelled (plane_extractor.cpp:230-232); the whole cluster leaves
 
@@ -277,8 +315,9 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
   constexpr int kStride = kRefCluster * kRefThreads;
   // during the search the leader's producer warps do not score: the other warps of the cluster share the points
   const bool producer = leader && warp < kProdWarps;
-  const int swarp = gwarp - kProdWarps;
-  constexpr int kScoreWarps = kRefCluster * kRefWarps - kProdWarps;
+  constexpr int kLeaderIdle = DPX_LEADER_IDLE;  // leader warps [0, kLeaderIdle) do not score
+  constexpr int kScoreWarps = kRefCluster * kRefWarps - kLeaderIdle;
+  const int swarp = gwarp - kLeaderIdle;
 
   // the generator (warp 0 of the leader): position of the next draw in the stream, newest block in the ring
   int gp = kMtN, gen_hi = 0;
@@ -532,13 +571,18 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
       REF_PROBE(0);  // sampling
       // this thread's hypothesis: ranks -> pixels -> model
       const int* rs = rows_ok ? s.rowstart : nullptr;
-      const long long pa = kth_pixel(lc, rs, a, p, nh, g.width), pb = kth_pixel(lc, rs, b, p, nh, g.width), pc = kth_pixel(lc, rs, c, p, nh, g.width);
+      const long long pa = kth_pixel(lc, rs, a, im), pb = kth_pixel(lc, rs, b, im), pc = kth_pixel(lc, rs, c, im);
+      REF_PROBE(2);
       {
         // PlaneEstimator::ComputeModel (Plane.hpp:13-43), fp32 in the reference's expression order
         float x0, y0, z0, x1, y1, z1, x2, y2, z2;
         load_point<LAYOUT>(xyz, g.n_points, pa, x0, y0, z0);
         load_point<LAYOUT>(xyz, g.n_points, pb, x1, y1, z1);
         load_point<LAYOUT>(xyz, g.n_points, pc, x2, y2, z2);
+#ifdef DPX_REFINE_PROBE
+        if (x0 + x1 + x2 + y0 + y1 + y2 + z0 + z1 + z2 == 12345.678f) rp_t += 1;  // wait for the loads
+        REF_PROBE(4);
+#endif
         const f32 X0(x0), X1(x1), X2(x2), Y0(y0), Y1(y1), Y2(y2), Z0(z0), Z1(z1), Z2(z2);
         const f32 D = X0 * Y1 - X1 * Y0 - X0 * Y2 + X2 * Y0 + X1 * Y2 - X2 * Y1;
         const f32 a = (Z0 * (Y1 - Y2)) / D - (Z1 * (Y0 - Y2)) / D + (Z2 * (Y0 - Y1)) / D;
@@ -568,7 +612,7 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
         if (producer) {
           // the next round, as if this one ran all its iterations (it does, except the last round of a label)
           draws_next = produce(buf ^ 1, gp + draws_cur);
-        } else {
+        } else if (swarp >= 0) {
           // EvaluateModel (RANSAC.hpp:89-98): lane g scores hypotheses g, g + 32, ...; loss += (fabs(error) >= threshold)
           float m[kSub][4];
 #pragma unroll
@@ -586,10 +630,10 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
             const int e = e0 + lane;
             float x = 0.f, y = 0.f, z = 0.f;
             if (e < e_hi) {
-              const int t = e / p2, in = e - t * p2;
+              const int t = fdiv(e, im.by_p2), in = e - t * p2;
               const int cell = lc.cells[t];
-              const int r = cell / nh, q = cell - r * nh;
-              const int i = in / p, j = in - i * p;
+              const int r = fdiv(cell, im.by_nh), q = cell - r * nh;
+              const int i = fdiv(in, im.by_p), j = in - i * p;
               load_point<LAYOUT>(xyz, g.n_points, static_cast<long long>(r * p + i) * g.width + q * p + j, x, y, z);
             }
             s.stage[warp][lane] = make_float4(x, y, z, 0.f);
@@ -699,10 +743,10 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
       if (pass == 1 && last < 0) break;  // no inlier at all: the relabelling loop never runs (same in every CTA)
       int local_max = -1;
       for (int e = gwarp * 32 + lane; e < n; e += kStride - 0) {
-        const int t = e / p2, in = e - t * p2;
+        const int t = fdiv(e, im.by_p2), in = e - t * p2;
         const int cell = lc.cells[t];
-        const int r = cell / nh, q = cell - r * nh;
-        const int i = in / p, j = in - i * p;
+        const int r = fdiv(cell, im.by_nh), q = cell - r * nh;
+        const int i = fdiv(in, im.by_p), j = in - i * p;
         const long long pix = static_cast<long long>(r * p + i) * g.width + q * p + j;
         float x, y, z;
         load_point<LAYOUT>(xyz, g.n_points, pix, x, y, z);
