@@ -50,6 +50,7 @@ constexpr int kHyp = 32 * kSub;  // hypotheses evaluated per round (one cluster-
 constexpr int kRefCluster = 8;  // CTAs per frame (portable cluster size limit)
 constexpr int kTape = 128;      // generator outputs prepared per round (32 hypotheses x 3 draws + slack)
 constexpr int kMaxRows = 1023;  // cell rows the per-label row table can hold
+constexpr int kSortLabels = 256;  // labels the shared-memory label sort handles (kRefWarps * kSortLabels <= kCellCache)
 constexpr int kCellCache = 4096;  // cells of one label cached in shared memory (larger labels read the global list)
 namespace cg = cooperative_groups;
 constexpr unsigned kFullMask = 0xffffffffu;
@@ -68,7 +69,8 @@ struct RefShared {
   int draws_cum[2][kHyp];     // generator draws of the round up to and including hypothesis g
   int rank[kHyp][3];          // sample ranks, ascending (std::set order): hand-over of the exact sequential path
   int grp_start[kSub], grp_used[kSub];  // per group of 32 hypotheses: assumed offset into the round's draws, draws taken
-  float best[4];
+  alignas(16) float best[4];   // leader: best model of the label being searched
+  alignas(16) float dbest[4];  // every CTA: best model of the label whose inlier passes are pending
   unsigned bestloss;          // kNoLoss until a hypothesis has been accepted
   int iteration, go_on;
   int prod_gp0;               // leader: stream position the round being prepared starts at
@@ -325,8 +327,72 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
   __syncthreads();
   if (leader) {
     // ---- labels_indices (plane_extractor.cpp:473-478), per cell instead of per pixel ---------------------
-    for (int i = tid; i < nseg; i += kRefThreads) lab_end[i] = 0;
+    // lab_cells = the cells sorted by (label, cell id), lab_end[l] = end of label l's run: a stable counting sort.
     for (int i = tid; i < kMtN; i += kRefThreads) s.mtb[0][i] = args.mt_init[i];
+    if (nseg <= kSortLabels) {
+      // Every warp takes a contiguous sixteenth of the cells: per-(warp, label) counts in shared memory, a scan in
+      // (label, warp) order, then each warp places its cells in order behind its own cursors.
+      int* mat = s.cells;        // [kRefWarps][nseg] counts, then cursors relative to the label's run
+      int* lstart = s.rowstart;  // [nseg] totals, then run starts
+      for (int i = tid; i < kRefWarps * nseg; i += kRefThreads) mat[i] = 0;
+      __syncthreads();
+      const int chunk = ((C + kRefWarps - 1) / kRefWarps + 31) & ~31;
+      const int c_begin = min(C, warp * chunk), c_end = min(C, c_begin + chunk);
+      for (int c = c_begin + lane; c < c_end; c += 32) {
+        const int l = cell_label[c];
+        if (l > 0) atomicAdd(&mat[warp * nseg + l - 1], 1);
+      }
+      __syncthreads();
+      if (tid < nseg) {
+        int run = 0;
+        for (int w = 0; w < kRefWarps; ++w) {
+          const int t = mat[w * nseg + tid];
+          mat[w * nseg + tid] = run;
+          run += t;
+        }
+        lstart[tid] = run;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        int run = 0;
+        for (int b0 = 0; b0 < nseg; b0 += 32) {
+          const int i = b0 + lane;
+          const int cnt = i < nseg ? lstart[i] : 0;
+          int incl = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= o) incl += t;
+          }
+          if (i < nseg) {
+            lstart[i] = run + incl - cnt;
+            lab_end[i] = run + incl;
+          }
+          run += __shfl_sync(kFullMask, incl, 31);
+        }
+      }
+      __syncthreads();
+      int l_next = c_begin + lane < c_end ? cell_label[c_begin + lane] : 0;
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+        const int c = c0 + lane;
+        const int l = l_next;
+        l_next = c + 32 < c_end ? cell_label[c + 32] : 0;  // in flight while this batch is placed
+        const unsigned act = __ballot_sync(kFullMask, l > 0);
+        if (l > 0) {
+          const unsigned grp = __match_any_sync(act, l);
+          const int ldr = __ffs(grp) - 1;
+          int base = 0;
+          if (lane == ldr) {
+            base = mat[warp * nseg + l - 1];
+            mat[warp * nseg + l - 1] = base + __popc(grp);
+          }
+          base = __shfl_sync(grp, base, ldr);
+          lab_cells[lstart[l - 1] + base + __popc(grp & ((1u << lane) - 1u))] = c;
+        }
+        __syncwarp();
+      }
+    } else {
+    for (int i = tid; i < nseg; i += kRefThreads) lab_end[i] = 0;
     __syncthreads();
     for (int c = tid; c < C; c += kRefThreads) {
       const int l = cell_label[c];
@@ -367,17 +433,59 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
         __syncwarp();
       }
     }
+    }
     __threadfence();
   }
   cluster.sync();  // the label runs (global memory) are visible to the whole cluster
 
   // ---- one label after the other (plane_extractor.cpp:486-508) ----------------------------------------------
+  // FindInliers + relabelling of a label (RANSAC.hpp:53-62, plane_extractor.cpp:498-507) run one label late, by the
+  // scoring warps, while the producers prepare the first round of the next label: pass 0 (largest inlier pixel) before
+  // that round's barrier, pass 1 (non-inliers before it -> 0; points after the last inlier keep their label, as in the
+  // reference's loop) right after it.  The pending label's cells are read from the global list (the shared-memory
+  // copy already holds the next label's), its best model from `dbest`.
+  bool pending = false;
+  LabelCells plc = {nullptr, 0};
+  int pn = 0;
+  auto inlier_pass = [&](const int pass, const int last) {
+    if (swarp < 0 || (pass == 1 && last < 0)) return;  // no inlier at all: the relabelling loop never runs
+    const float m[4] = {s.dbest[0], s.dbest[1], s.dbest[2], s.dbest[3]};
+    const int e_lo = static_cast<int>(static_cast<long long>(swarp) * pn / kScoreWarps);
+    const int e_hi = static_cast<int>(static_cast<long long>(swarp + 1) * pn / kScoreWarps);
+    int local_max = -1;
+    for (int e = e_lo + lane; e < e_hi; e += 32) {
+      const int t = fdiv(e, im.by_p2), in = e - t * p2;
+      const int cell = __ldg(plc.cells + t);
+      const int r = fdiv(cell, im.by_nh), q = cell - r * nh;
+      const int i = fdiv(in, im.by_p), j = in - i * p;
+      const long long pix = static_cast<long long>(r * p + i) * g.width + q * p + j;
+      float x, y, z;
+      load_point<LAYOUT>(xyz, g.n_points, pix, x, y, z);
+      const bool inlier = ::fabsf(plane_error(m, x, y, z)) < thr_f;
+      if (pass == 0) {
+        if (inlier) local_max = max(local_max, static_cast<int>(pix));
+      } else if (!inlier && pix < last) {
+        labels[pix] = 0;
+      }
+    }
+    if (pass == 0) {
+      local_max = __reduce_max_sync(kFullMask, local_max);
+      if (lane == 0 && local_max >= 0) atomicMax(&lead->max_inlier_pix, local_max);
+    }
+  };
+  auto last_inlier = [&]() -> int {  // after the cluster barrier that follows pass 0
+    int v = 0;
+    if (lane == 0) v = lead->max_inlier_pix;
+    return __shfl_sync(kFullMask, v, 0);
+  };
+
   for (int L = 0; L < nseg; ++L) {
     const int start = L ? lab_end[L - 1] : 0;
     LabelCells lc;
     lc.cells = lab_cells + start;
     lc.count = lab_end[L] - start;
     if (lc.count == 0) continue;  // labels_indices[label].size() == 0 (the same decision in every CTA)
+    const LabelCells glc = lc;    // the global list
     const int n = lc.count * p2;
     // the label's cell list is read by every rank -> pixel lookup and by every scored point: keep it in shared memory
     __syncthreads();  // (the previous label's last readers of the cache are done)
@@ -406,7 +514,7 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
       s.best[0] = s.best[1] = s.best[2] = s.best[3] = 0.f;  // Eigen::Vector4f::Zero()
       s.bestloss = kNoLoss;
       s.iteration = 0;
-      s.max_inlier_pix = -1;
+      s.max_inlier_pix = -1;  // of the pending label: its pass 0 runs after the next barrier
       // IsContinued(0, N - HUGE_VAL, N): int(-inf) is INT_MIN on x86-64
       s.go_on = (0 < args.max_iterations) && (static_cast<double>(INT_MIN) < ratio * n);
     }
@@ -604,10 +712,13 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
     if (go_on) {
       int buf = 0, draws_cur = 0, draws_next = 0;
       REF_PROBE(6);
-      if (producer) draws_cur = produce(0, gp);  // the first round of a label has nothing to hide behind
+      if (producer) draws_cur = produce(0, gp);  // the first round of a label hides behind the previous label's pass 0
+      else if (pending) inlier_pass(0, -1);
       if (leader && tid < kHyp) s.loss[tid] = 0;
-      cluster.sync();  // round 0's models are in every CTA, the leader's counters are zero
+      cluster.sync();  // round 0's models are in every CTA, the leader's counters are zero, the pending label's last inlier is known
       REF_PROBE(7);
+      if (pending && !producer) inlier_pass(1, last_inlier());
+      pending = false;
       for (;;) {
         if (producer) {
           // the next round, as if this one ran all its iterations (it does, except the last round of a label)
@@ -724,6 +835,12 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
           // the generator stops just after the last iteration the reference ran; the round prepared ahead is dropped
           gp += consumed > 0 ? s.draws_cum[buf][consumed - 1] : 0;
           if (lane < kRefCluster) *cluster.map_shared_rank(&s.go_on, lane) = go ? 1 : 0;
+          if (!go) {
+            // the label's model goes to every CTA for the inlier passes
+            __syncwarp();
+            const float4 bm = *reinterpret_cast<const float4*>(s.best);
+            if (lane < kRefCluster) *reinterpret_cast<float4*>(cluster.map_shared_rank(&s.dbest[0], lane)) = bm;
+          }
         }
         REF_PROBE(4);  // evaluate
         cluster.sync();  // (2) the decision is visible
@@ -734,36 +851,27 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
       }
     }
 
-    // ---- FindInliers + relabelling (RANSAC.hpp:53-62, plane_extractor.cpp:498-507) ---------------------------
-    float m[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) m[k] = lead->best[k];
-    for (int pass = 0; pass < 2; ++pass) {
-      const int last = pass ? lead->max_inlier_pix : -1;
-      if (pass == 1 && last < 0) break;  // no inlier at all: the relabelling loop never runs (same in every CTA)
-      int local_max = -1;
-      for (int e = gwarp * 32 + lane; e < n; e += kStride - 0) {
-        const int t = fdiv(e, im.by_p2), in = e - t * p2;
-        const int cell = lc.cells[t];
-        const int r = fdiv(cell, im.by_nh), q = cell - r * nh;
-        const int i = fdiv(in, im.by_p), j = in - i * p;
-        const long long pix = static_cast<long long>(r * p + i) * g.width + q * p + j;
-        float x, y, z;
-        load_point<LAYOUT>(xyz, g.n_points, pix, x, y, z);
-        const bool inlier = ::fabsf(plane_error(m, x, y, z)) < thr_f;
-        if (pass == 0) {
-          if (inlier) local_max = max(local_max, static_cast<int>(pix));
-        } else if (!inlier && pix < last) {
-          labels[pix] = 0;  // points after the last inlier keep their label, as in the reference's loop
-        }
+    else {
+      // no search (ransacMaxIterations = 0): the model stays Eigen::Vector4f::Zero()
+      if (pending) {
+        inlier_pass(0, -1);
+        cluster.sync();
+        inlier_pass(1, last_inlier());
       }
-      if (pass == 0) {
-        local_max = __reduce_max_sync(kFullMask, local_max);
-        if (lane == 0 && local_max >= 0) atomicMax(&lead->max_inlier_pix, local_max);
-        cluster.sync();  // the largest inlier pixel of the whole label is known
-      }
+      __syncthreads();
+      if (tid < 4) s.dbest[tid] = 0.f;
+      __syncthreads();
     }
-    cluster.sync();  // nobody still reads this label's state when the leader resets it for the next one
+    pending = true;
+    plc = glc;
+    pn = n;
+  }
+  if (pending) {
+    if (leader && tid == 0) s.max_inlier_pix = -1;
+    cluster.sync();
+    inlier_pass(0, -1);
+    cluster.sync();  // the largest inlier pixel of the whole label is known
+    inlier_pass(1, last_inlier());
   }
   cluster.sync();  // no CTA leaves while another may still touch its shared memory
 #ifdef DPX_REFINE_PROBE
