@@ -68,7 +68,7 @@ struct RefShared {
   unsigned loss_cta[kHyp];    // this CTA's share of a round
   int draws_cum[2][kHyp];     // generator draws of the round up to and including hypothesis g
   int rank[kHyp][3];          // sample ranks, ascending (std::set order): hand-over of the exact sequential path
-  int grp_start[kSub], grp_used[kSub];  // per group of 32 hypotheses: assumed offset into the round's draws, draws taken
+  alignas(8) int2 grp[2][kSub];  // per group of 32 hypotheses: (assumed offset into the round's draws, draws taken)
   alignas(16) float best[4];   // leader: best model of the label being searched
   alignas(16) float dbest[4];  // every CTA: best model of the label whose inlier passes are pending
   unsigned bestloss;          // kNoLoss until a hypothesis has been accepted
@@ -151,6 +151,22 @@ __device__ __forceinline__ uint32_t gen_word(const RefShared& s, int t) {
   const int b = t / kMtN;
   return mt_temper(s.mtb[b % 3][t - b * kMtN]);
 }
+// The same for the next 624 draws from a fixed position on, without a division per word: the position's block and the
+// one after it.
+struct GenWindow {
+  const uint32_t* cur;   // block holding draw t0, already offset to it: cur[j] is draw t0 + j while j < left
+  const uint32_t* next;  // the block after, offset so that next[j] is draw t0 + j for j >= left
+  int left;              // draws left in the first block
+};
+__device__ __forceinline__ GenWindow gen_window(const RefShared& s, int t0) {
+  const int b = t0 / kMtN, off = t0 - b * kMtN, slot = b % 3;
+  GenWindow w;
+  w.left = kMtN - off;
+  w.cur = s.mtb[slot] + off;
+  w.next = s.mtb[slot == 2 ? 0 : slot + 1] - w.left;
+  return w;
+}
+__device__ __forceinline__ uint32_t gen_word(const GenWindow& w, int j) { return mt_temper(j < w.left ? w.cur[j] : w.next[j]); }
 
 // std::uniform_int_distribution<int>(0, n - 1)(gen) over std::mt19937.  The mapping is implementation-defined and
 // libstdc++ changed it (bits/uniform_int_dist.h), so both generations are here, selected by RefineArgs::uniform_variant:
@@ -534,13 +550,14 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
       // of the lanes' extra draws per pass, normally one pass.  Returns the draws the group took, or -1 if it did not
       // settle inside the tape; `cum` = draws up to and including this lane's hypothesis.
       auto sample_group = [&](const int t_first, int& a, int& b, int& c, int& cum) -> int {
+        const GenWindow win = gen_window(s, t_first);
         {
           // the common case first, straight from the generator's block: every lane's three outputs are accepted and
           // distinct, so the group takes exactly 96 draws
           int v0, v1, v2;
-          const bool k0 = accept_draw(umap, gen_word(s, t_first + 3 * lane), v0);
-          const bool k1 = accept_draw(umap, gen_word(s, t_first + 3 * lane + 1), v1);
-          const bool k2 = accept_draw(umap, gen_word(s, t_first + 3 * lane + 2), v2);
+          const bool k0 = accept_draw(umap, gen_word(win, 3 * lane), v0);
+          const bool k1 = accept_draw(umap, gen_word(win, 3 * lane + 1), v1);
+          const bool k2 = accept_draw(umap, gen_word(win, 3 * lane + 2), v2);
           if (__all_sync(kFullMask, k0 && k1 && k2 && v0 != v1 && v0 != v2 && v1 != v2)) {
             const int lo = min(v0, v1), hi = max(v0, v1);
             a = min(lo, v2);
@@ -551,7 +568,7 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
           }
         }
         uint32_t* tape = s.tape[warp];
-        for (int j = lane; j < kTape; j += 32) tape[j] = gen_word(s, t_first + j);
+        for (int j = lane; j < kTape; j += 32) tape[j] = gen_word(win, j);
         __syncwarp();
         int off = 0, extra = 0;
         bool ok = false;
@@ -606,28 +623,26 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
       prod_bar();
       const int gp0 = s.prod_gp0;
       int start = 96 * warp, used = 0, a = -1, b = -1, c = -1, cum = 0;
+      int grp_start = -1, used_own = 0;  // the offset this warp's current result was computed at, the draws it took
       bool settled = false, serial = false;
       for (int it = 0; it < kSub && !settled; ++it) {
-        if (it == 0 || s.grp_start[warp] != start) {
-          used = sample_group(gp0 + start, a, b, c, cum);
-          if (lane == 0) {
-            s.grp_start[warp] = start;
-            s.grp_used[warp] = used;
-          }
+        if (it == 0 || grp_start != start) {
+          used_own = sample_group(gp0 + start, a, b, c, cum);
+          grp_start = start;
         }
+        if (lane == 0) s.grp[it & 1][warp] = make_int2(grp_start, used_own);  // (two tables: one barrier per pass)
         prod_bar();
         REF_PROBE(10);  // group sampling
         int sum = 0, mine_start = 0;
         settled = true;
 #pragma unroll
         for (int w = 0; w < kSub; ++w) {
-          const int u = s.grp_used[w];
+          const int2 gw = s.grp[it & 1][w];
           if (w == warp) mine_start = sum;
-          if (u < 0) serial = true;
-          if (s.grp_start[w] != sum) settled = false;
-          sum += u;
+          if (gw.y < 0) serial = true;
+          if (gw.x != sum) settled = false;
+          sum += gw.y;
         }
-        prod_bar();  // everybody has read the table before the next pass rewrites it
         if (serial) break;
         start = mine_start;
         used = sum;  // total of the round (final once settled)
