@@ -47,7 +47,8 @@ constexpr int kRefThreads = 512;
 constexpr int kRefWarps = kRefThreads / 32;
 constexpr int kSub = 4;          // groups of 32 hypotheses per round
 constexpr int kHyp = 32 * kSub;  // hypotheses evaluated per round (one cluster-wide pass over the label's points)
-constexpr int kRefCluster = 8;  // CTAs per frame (portable cluster size limit)
+constexpr int kRefCluster = 8;   // CTAs per frame (portable cluster size limit) ...
+constexpr int kRefClusterWide = 16;  // ... or 16 (non-portable, opt-in) when the launch is a few frames only
 constexpr int kTape = 128;      // generator outputs prepared per round (32 hypotheses x 3 draws + slack)
 constexpr int kMaxRows = 1023;  // cell rows the per-label row table can hold
 constexpr int kSortLabels = 256;  // labels the shared-memory label sort handles (kRefWarps * kSortLabels <= kCellCache)
@@ -296,8 +297,9 @@ __device__ long long g_refine_probe[24];  // [0, 12): the leader's thread 0 (a p
 // MINB = CTAs per SM the register budget is set for: 1 (~125 registers, nothing spilled) when the launch has no more CTAs
 // than the GPU has SMs -- the latency case -- and 2 (64 registers) for batches, where a second resident cluster per SM
 // fills the first one's barriers and serial phases.
-template <int LAYOUT, int MINB>
+template <int LAYOUT, int MINB, int CL>
 __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineArgs args) {
+  constexpr int kRefCluster = CL;  // CTAs of this frame's cluster
   __shared__ RefShared s;
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned crank = cluster.block_rank();
@@ -330,7 +332,6 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
   const double ratio = static_cast<double>(args.inliers_ratio);
   // this thread's share of a label's points: chunks of 32 points, dealt round-robin over the cluster's warps
   const int gwarp = static_cast<int>(crank) * kRefWarps + warp;
-  constexpr int kStride = kRefCluster * kRefThreads;
   // during the search the leader's producer warps do not score: the other warps of the cluster share the points
   const bool producer = leader && warp < kProdWarps;
   constexpr int kLeaderIdle = DPX_LEADER_IDLE;  // leader warps [0, kLeaderIdle) do not score
@@ -921,30 +922,61 @@ void mt19937_default_state(uint32_t out[kMtN]) {
   for (int i = 1; i < kMtN; ++i) out[i] = 1812433253u * (out[i - 1] ^ (out[i - 1] >> 30)) + static_cast<uint32_t>(i);
 }
 
-cudaError_t launch_refine(const RefineArgs& args, cudaStream_t stream) {
-  if (args.n_frames == 0 || args.geom.n_cells == 0) return cudaSuccess;
+template <int LAYOUT, int MINB, int CL>
+cudaError_t launch_refine_as(const RefineArgs& args, cudaStream_t stream, bool probe_only) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(static_cast<unsigned>(args.n_frames) * kRefCluster, 1, 1);
+  cfg.gridDim = dim3(static_cast<unsigned>(args.n_frames) * CL, 1, 1);
   cfg.blockDim = dim3(kRefThreads, 1, 1);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kRefCluster;
+  attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (CL > 8) {
+    static const cudaError_t allowed = cudaFuncSetAttribute(refine_kernel<LAYOUT, MINB, CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (allowed != cudaSuccess) return allowed;
+  }
+  if (probe_only) {
+    // can this device place the clusters of the launch side by side at all?
+    int n_clusters = 0;
+    const cudaError_t e = cudaOccupancyMaxActiveClusters(&n_clusters, refine_kernel<LAYOUT, MINB, CL>, &cfg);
+    if (e != cudaSuccess) return e;
+    return n_clusters >= args.n_frames ? cudaSuccess : cudaErrorInvalidConfiguration;
+  }
+  return cudaLaunchKernelEx(&cfg, refine_kernel<LAYOUT, MINB, CL>, args);
+}
+
+cudaError_t launch_refine(const RefineArgs& args, cudaStream_t stream) {
+  if (args.n_frames == 0 || args.geom.n_cells == 0) return cudaSuccess;
   static const int n_sm = [] {
     int dev = 0, v = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
     return v;
   }();
-  const bool one_per_sm = args.n_frames * kRefCluster <= n_sm;
-  if (args.layout == kLayoutRowMajor)
-    return one_per_sm ? cudaLaunchKernelEx(&cfg, refine_kernel<kLayoutRowMajor, 1>, args) : cudaLaunchKernelEx(&cfg, refine_kernel<kLayoutRowMajor, 2>, args);
-  return one_per_sm ? cudaLaunchKernelEx(&cfg, refine_kernel<kLayoutColMajor, 1>, args) : cudaLaunchKernelEx(&cfg, refine_kernel<kLayoutColMajor, 2>, args);
+  const bool row = args.layout == kLayoutRowMajor;
+  // A handful of frames: 16 CTAs per frame halve the scoring time of a round (the clusters must all be resident at once
+  // for that to be a gain; asked of the occupancy calculator once per frame count).
+  if (args.n_frames * kRefClusterWide <= n_sm) {
+    static int wide_ok[16] = {};  // per frame count: 0 unknown, 1 yes, -1 no
+    int& ok = wide_ok[args.n_frames & 15];
+    if (ok == 0) {
+      const cudaError_t e = row ? launch_refine_as<kLayoutRowMajor, 1, kRefClusterWide>(args, stream, true)
+                                : launch_refine_as<kLayoutColMajor, 1, kRefClusterWide>(args, stream, true);
+      ok = e == cudaSuccess ? 1 : -1;
+      (void)cudaGetLastError();
+    }
+    if (ok > 0)
+      return row ? launch_refine_as<kLayoutRowMajor, 1, kRefClusterWide>(args, stream, false)
+                 : launch_refine_as<kLayoutColMajor, 1, kRefClusterWide>(args, stream, false);
+  }
+  if (args.n_frames * kRefCluster <= n_sm)
+    return row ? launch_refine_as<kLayoutRowMajor, 1, kRefCluster>(args, stream, false) : launch_refine_as<kLayoutColMajor, 1, kRefCluster>(args, stream, false);
+  return row ? launch_refine_as<kLayoutRowMajor, 2, kRefCluster>(args, stream, false) : launch_refine_as<kLayoutColMajor, 2, kRefCluster>(args, stream, false);
 }
 
 }  // namespace dpx
