@@ -45,8 +45,7 @@ namespace {
 
 constexpr int kRefThreads = 512;
 constexpr int kRefWarps = kRefThreads / 32;
-constexpr int kSub = 4;          // groups of 32 hypotheses per round
-constexpr int kHyp = 32 * kSub;  // hypotheses evaluated per round (one cluster-wide pass over the label's points)
+// groups of 32 hypotheses per round: KSUB, a template parameter; 4 -> 128 hypotheses per cluster-wide pass over the label's points
 constexpr int kRefCluster = 8;   // CTAs per frame (portable cluster size limit) ...
 constexpr int kRefClusterWide = 16;  // ... or 16 (non-portable, opt-in) when the launch is a few frames only
 constexpr int kTape = 128;      // generator outputs prepared per round (32 hypotheses x 3 draws + slack)
@@ -56,20 +55,19 @@ constexpr int kCellCache = 4096;  // cells of one label cached in shared memory 
 namespace cg = cooperative_groups;
 constexpr unsigned kFullMask = 0xffffffffu;
 
-#ifndef DPX_LEADER_IDLE
-#define DPX_LEADER_IDLE 4
-#endif
-constexpr int kProdWarps = 4;  // the leader's producer warps (kProdWarps * 32 == kHyp)
 constexpr unsigned kNoLoss = 0xffffffffu;  // "no hypothesis accepted yet" (the reference's HUGE_VAL best loss)
 
+template <int KSUB>
 struct RefShared {
-  uint32_t mtb[3][kMtN];      // leader: generator block b (the state after b twists of the seeded state) in slot b % 3
+  static constexpr int kHyp = 32 * KSUB;
+  static constexpr int kRing = KSUB > 4 ? 5 : 3;  // generator blocks kept: a round and the round prepared ahead of it always fit
+  uint32_t mtb[kRing][kMtN];  // leader: generator block b (the state after b twists of the seeded state) in slot b % kRing
   alignas(16) float model[2][kHyp][4];  // the hypotheses of the round being scored / being prepared, in every CTA
   alignas(16) unsigned loss[kHyp];      // leader: the cluster's totals
   unsigned loss_cta[kHyp];    // this CTA's share of a round
   int draws_cum[2][kHyp];     // generator draws of the round up to and including hypothesis g
   int rank[kHyp][3];          // sample ranks, ascending (std::set order): hand-over of the exact sequential path
-  alignas(8) int2 grp[2][kSub];  // per group of 32 hypotheses: (assumed offset into the round's draws, draws taken)
+  alignas(8) int2 grp[2][KSUB];  // per group of 32 hypotheses: (assumed offset into the round's draws, draws taken)
   alignas(16) float best[4];   // leader: best model of the label being searched
   alignas(16) float dbest[4];  // every CTA: best model of the label whose inlier passes are pending
   unsigned bestloss;          // kNoLoss until a hypothesis has been accepted
@@ -77,7 +75,7 @@ struct RefShared {
   int prod_gp0;               // leader: stream position the round being prepared starts at
   int max_inlier_pix;
   float4 stage[kRefWarps][32];
-  uint32_t tape[kProdWarps][kTape];  // per producer warp: tempered generator outputs of a group of 32 hypotheses, in draw order
+  uint32_t tape[KSUB][kTape];  // per producer warp: tempered generator outputs of a group of 32 hypotheses, in draw order
   int rowstart[kMaxRows + 1]; // per label: index of the first of its cells in each cell row (cells are sorted)
   int32_t cells[kCellCache];  // per label, every CTA: a copy of the label's sorted cell list when it fits
 };
@@ -130,9 +128,10 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
 // first real draw is t = 624) is word t % 624 of block t / 624.  Blocks gen_hi - 2 .. gen_hi are in the ring; a block
 // ahead is generated on demand, a block that has left the ring is regenerated from the seed (never in practice: a round
 // would have to take several hundred draws more than its 384).  `gen_hi` lives in a register of every lane of warp 0.
-__device__ __forceinline__ void gen_cover(RefShared& s, const uint32_t* mt_init, int lane, int& gen_hi, int t_lo, int t_hi) {
+template <class S>
+__device__ __forceinline__ void gen_cover(S& s, const uint32_t* mt_init, int lane, int& gen_hi, int t_lo, int t_hi) {
   const int b_lo = t_lo / kMtN, b_hi = t_hi / kMtN;
-  if (b_lo < gen_hi - 2) {
+  if (b_lo < gen_hi - (S::kRing - 1)) {
     for (int i = lane; i < kMtN; i += 32) s.mtb[0][i] = mt_init[i];
     __syncwarp();
     gen_hi = 0;
@@ -141,16 +140,17 @@ __device__ __forceinline__ void gen_cover(RefShared& s, const uint32_t* mt_init,
 #endif
   }
   while (gen_hi < b_hi) {
-    mt_next_block_warp(s.mtb[(gen_hi + 1) % 3], s.mtb[gen_hi % 3], lane);
+    mt_next_block_warp(s.mtb[(gen_hi + 1) % S::kRing], s.mtb[gen_hi % S::kRing], lane);
     ++gen_hi;
 #ifdef DPX_REFINE_PROBE
     if (threadIdx.x == 0 && blockIdx.x == 0) g_refine_probe_cnt[0] += 1;
 #endif
   }
 }
-__device__ __forceinline__ uint32_t gen_word(const RefShared& s, int t) {
+template <class S>
+__device__ __forceinline__ uint32_t gen_word(const S& s, int t) {
   const int b = t / kMtN;
-  return mt_temper(s.mtb[b % 3][t - b * kMtN]);
+  return mt_temper(s.mtb[b % S::kRing][t - b * kMtN]);
 }
 // The same for the next 624 draws from a fixed position on, without a division per word: the position's block and the
 // one after it.
@@ -159,12 +159,13 @@ struct GenWindow {
   const uint32_t* next;  // the block after, offset so that next[j] is draw t0 + j for j >= left
   int left;              // draws left in the first block
 };
-__device__ __forceinline__ GenWindow gen_window(const RefShared& s, int t0) {
-  const int b = t0 / kMtN, off = t0 - b * kMtN, slot = b % 3;
+template <class S>
+__device__ __forceinline__ GenWindow gen_window(const S& s, int t0) {
+  const int b = t0 / kMtN, off = t0 - b * kMtN, slot = b % S::kRing;
   GenWindow w;
   w.left = kMtN - off;
   w.cur = s.mtb[slot] + off;
-  w.next = s.mtb[slot == 2 ? 0 : slot + 1] - w.left;
+  w.next = s.mtb[slot == S::kRing - 1 ? 0 : slot + 1] - w.left;
   return w;
 }
 __device__ __forceinline__ uint32_t gen_word(const GenWindow& w, int j) { return mt_temper(j < w.left ? w.cur[j] : w.next[j]); }
@@ -198,11 +199,12 @@ __device__ __forceinline__ bool accept_draw(const UniformMap& m, uint32_t u, int
   return static_cast<uint32_t>(product) >= m.threshold;  // (low < n && low < threshold) rejects; threshold < n always
 }
 // one value of the distribution, drawn word by word from position t on (t is advanced past the words used)
-__device__ __forceinline__ int uniform_below_warp(RefShared& s, const uint32_t* mt_init, int lane, int& gen_hi, int& t, const UniformMap& m) {
+template <class S>
+__device__ __forceinline__ int uniform_below_warp(S& s, const uint32_t* mt_init, int lane, int& gen_hi, int& t, const UniformMap& m) {
   int value;
   uint32_t u;
   do {
-    if (t / kMtN > gen_hi || t / kMtN < gen_hi - 2) gen_cover(s, mt_init, lane, gen_hi, t, t);
+    if (t / kMtN > gen_hi || t / kMtN < gen_hi - (S::kRing - 1)) gen_cover(s, mt_init, lane, gen_hi, t, t);
     u = gen_word(s, t);
     ++t;
   } while (!accept_draw(m, u, value));
@@ -287,7 +289,7 @@ __device__ __forceinline__ float plane_error(const float (&m)[4], float x, float
 
 #ifdef DPX_REFINE_PROBE
 // probe builds only (make NVFLAGS_EXTRA=-DDPX_REFINE_PROBE, tools/refine_probe.py): cycles of the leader's thread 0 per phase
-__device__ long long g_refine_probe[24];  // [0, 12): the leader's thread 0 (a producer); [12, 24): its first scoring thread
+__device__ long long g_refine_probe[24];  // [0, 12): the leader's thread 0 (a producer); [12, 24): thread 0 of CTA 1 (a scorer)
 // (accumulated in registers and written once at the end: a global read-modify-write per probe would cost more than most phases)
 #define REF_PROBE(slot) do { const long long t__ = clock64(); rp_acc[slot] += t__ - rp_t; rp_t = t__; } while (0)
 #else
@@ -297,14 +299,17 @@ __device__ long long g_refine_probe[24];  // [0, 12): the leader's thread 0 (a p
 // MINB = CTAs per SM the register budget is set for: 1 (~125 registers, nothing spilled) when the launch has no more CTAs
 // than the GPU has SMs -- the latency case -- and 2 (64 registers) for batches, where a second resident cluster per SM
 // fills the first one's barriers and serial phases.
-template <int LAYOUT, int MINB, int CL>
+template <int LAYOUT, int MINB, int CL, int KSUB>
 __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineArgs args) {
   constexpr int kRefCluster = CL;  // CTAs of this frame's cluster
-  __shared__ RefShared s;
+  constexpr int kSub = KSUB, kHyp = 32 * KSUB, kProdWarps = KSUB;  // one producer warp per group of 32 hypotheses
+  using Shared = RefShared<KSUB>;
+  extern __shared__ __align__(16) unsigned char ref_smem[];
+  Shared& s = *reinterpret_cast<Shared*>(ref_smem);
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned crank = cluster.block_rank();
   const bool leader = crank == 0;
-  RefShared* lead = cluster.map_shared_rank(&s, 0);  // the leader CTA's copy (distributed shared memory)
+  Shared* lead = cluster.map_shared_rank(&s, 0);  // the leader CTA's copy (distributed shared memory)
   const Geometry& g = args.geom;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int frame = blockIdx.x / kRefCluster;
@@ -334,7 +339,9 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
   const int gwarp = static_cast<int>(crank) * kRefWarps + warp;
   // during the search the leader's producer warps do not score: the other warps of the cluster share the points
   const bool producer = leader && warp < kProdWarps;
-  constexpr int kLeaderIdle = DPX_LEADER_IDLE;  // leader warps [0, kLeaderIdle) do not score
+  // leader warps [0, kLeaderIdle) do not score: the producers, and in a 16-CTA cluster the whole leader (its scoring warps
+  // are a twentieth of the cluster's and slow the producers down, which is the longer leg there)
+  constexpr int kLeaderIdle = CL > 8 ? kRefWarps : kProdWarps;
   constexpr int kScoreWarps = kRefCluster * kRefWarps - kLeaderIdle;
   const int swarp = gwarp - kLeaderIdle;
 
@@ -794,17 +801,23 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
         REF_PROBE(3);
         if (leader && warp == 0) {
           // The reference's sequential loop over these hypotheses (RANSAC.hpp:33-46), evaluated by one warp: lane l owns
-          // hypotheses 4l .. 4l+3.  The best-so-far loss before a hypothesis is a prefix minimum; the loop runs while
+          // hypotheses kSub * l .. kSub * l + kSub - 1.  The best-so-far loss before a hypothesis is a prefix minimum; the loop runs while
           // IsContinued holds, which is monotone (the best loss only falls, the iteration count only grows), so the number
           // of iterations really run is the number of hypotheses whose check passes.  Losses are counts: the reference's
           // doubles hold the same integers, HUGE_VAL is kNoLoss here.
           const unsigned best0 = s.bestloss;
           const int iter0 = s.iteration;
-          const uint4 v4 = *reinterpret_cast<const uint4*>(&s.loss[4 * lane]);
-          *reinterpret_cast<uint4*>(&s.loss[4 * lane]) = make_uint4(0, 0, 0, 0);  // for the next round
-          const unsigned mine[4] = {v4.x, v4.y, v4.z, v4.w};
-          const unsigned p0 = mine[0], p1 = min(p0, mine[1]), p2m = min(p1, mine[2]), p3 = min(p2m, mine[3]);
-          unsigned incl = p3;
+          unsigned mine[kSub], pre[kSub];  // this lane's losses; their running minimum
+#pragma unroll
+          for (int q4 = 0; q4 < kSub / 4; ++q4) {
+            const uint4 v4 = *reinterpret_cast<const uint4*>(&s.loss[kSub * lane + 4 * q4]);
+            *reinterpret_cast<uint4*>(&s.loss[kSub * lane + 4 * q4]) = make_uint4(0, 0, 0, 0);  // for the next round
+            mine[4 * q4] = v4.x; mine[4 * q4 + 1] = v4.y; mine[4 * q4 + 2] = v4.z; mine[4 * q4 + 3] = v4.w;
+          }
+          pre[0] = mine[0];
+#pragma unroll
+          for (int j = 1; j < kSub; ++j) pre[j] = min(pre[j - 1], mine[j]);
+          unsigned incl = pre[kSub - 1];
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) {
             const unsigned t = __shfl_up_sync(kFullMask, incl, o);
@@ -813,28 +826,28 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
           unsigned ex = __shfl_up_sync(kFullMask, incl, 1);
           if (lane == 0) ex = kNoLoss;
           ex = min(ex, best0);
-          const unsigned before[4] = {ex, min(ex, p0), min(ex, p1), min(ex, p2m)};
           const double target = ratio * n;
           int consumed = 0;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < kSub; ++j) {
             // IsContinued(iteration, N - best loss, N); int(N - HUGE_VAL) is INT_MIN on x86-64
-            const int inl = before[j] == kNoLoss ? INT_MIN : n - static_cast<int>(before[j]);
-            const bool go_h = (iter0 + 4 * lane + j < args.max_iterations) && (static_cast<double>(inl) < target);
+            const unsigned before = j ? min(ex, pre[j - 1]) : ex;
+            const int inl = before == kNoLoss ? INT_MIN : n - static_cast<int>(before);
+            const bool go_h = (iter0 + kSub * lane + j < args.max_iterations) && (static_cast<double>(inl) < target);
             consumed += __popc(__ballot_sync(kFullMask, go_h));
           }
           // best loss over the iterations really run, and the first of them that reaches it (strict '<' updates)
           unsigned cand = kNoLoss;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (4 * lane + j < consumed) cand = min(cand, mine[j]);
+          for (int j = 0; j < kSub; ++j)
+            if (kSub * lane + j < consumed) cand = min(cand, mine[j]);
           const unsigned best = __reduce_min_sync(kFullMask, cand);
           unsigned bl = best0;
           if (best < best0) {
             unsigned first = kNoLoss;
 #pragma unroll
-            for (int j = 3; j >= 0; --j)
-              if (4 * lane + j < consumed && mine[j] == best) first = 4 * lane + j;
+            for (int j = kSub - 1; j >= 0; --j)
+              if (kSub * lane + j < consumed && mine[j] == best) first = kSub * lane + j;
             const unsigned winner = __reduce_min_sync(kFullMask, first);
             if (lane < 4) s.best[lane] = s.model[buf][winner][lane];
             bl = best;
@@ -891,8 +904,8 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
   }
   cluster.sync();  // no CTA leaves while another may still touch its shared memory
 #ifdef DPX_REFINE_PROBE
-  if (leader && (tid == 0 || tid == kProdWarps * 32) && blockIdx.x < kRefCluster)
-    for (int i = 0; i < 12; ++i) g_refine_probe[(tid ? 12 : 0) + i] += rp_acc[i];
+  if (tid == 0 && blockIdx.x < 2)  // frame 0: the leader's thread 0 (a producer) and thread 0 of the next CTA (a scorer)
+    for (int i = 0; i < 12; ++i) g_refine_probe[(blockIdx.x ? 12 : 0) + i] += rp_acc[i];
 #endif
 }
 
@@ -924,10 +937,16 @@ void mt19937_default_state(uint32_t out[kMtN]) {
 
 template <int LAYOUT, int MINB, int CL>
 cudaError_t launch_refine_as(const RefineArgs& args, cudaStream_t stream, bool probe_only) {
+  // 256-hypothesis rounds (KSUB = 8) were measured with 16-CTA clusters: 5 % faster on the TUM frame, 40 % slower on the ICL
+  // frame (many small labels: more rounds that do not settle at once, twice the work thrown away at the end of each label)
+  constexpr int KSUB = 4;
+  static const cudaError_t smem_ok = cudaFuncSetAttribute(refine_kernel<LAYOUT, MINB, CL, KSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                          static_cast<int>(sizeof(RefShared<KSUB>)));
+  if (smem_ok != cudaSuccess) return smem_ok;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(args.n_frames) * CL, 1, 1);
   cfg.blockDim = dim3(kRefThreads, 1, 1);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = sizeof(RefShared<KSUB>);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -937,17 +956,17 @@ cudaError_t launch_refine_as(const RefineArgs& args, cudaStream_t stream, bool p
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (CL > 8) {
-    static const cudaError_t allowed = cudaFuncSetAttribute(refine_kernel<LAYOUT, MINB, CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    static const cudaError_t allowed = cudaFuncSetAttribute(refine_kernel<LAYOUT, MINB, CL, KSUB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (allowed != cudaSuccess) return allowed;
   }
   if (probe_only) {
     // can this device place the clusters of the launch side by side at all?
     int n_clusters = 0;
-    const cudaError_t e = cudaOccupancyMaxActiveClusters(&n_clusters, refine_kernel<LAYOUT, MINB, CL>, &cfg);
+    const cudaError_t e = cudaOccupancyMaxActiveClusters(&n_clusters, refine_kernel<LAYOUT, MINB, CL, KSUB>, &cfg);
     if (e != cudaSuccess) return e;
     return n_clusters >= args.n_frames ? cudaSuccess : cudaErrorInvalidConfiguration;
   }
-  return cudaLaunchKernelEx(&cfg, refine_kernel<LAYOUT, MINB, CL>, args);
+  return cudaLaunchKernelEx(&cfg, refine_kernel<LAYOUT, MINB, CL, KSUB>, args);
 }
 
 cudaError_t launch_refine(const RefineArgs& args, cudaStream_t stream) {
