@@ -285,8 +285,8 @@ def latency_mode(dev, calls, cpu_base):
         labelled = int((d_lab != 0).sum().item())
         rrec = {"refine_ms": racc["refine"], "device_resident_us": sum(racc.values()) * 1e3,
                 "labelled_pixels_after": labelled,
-                "note": "stage 4 is latency-bound (hundreds of rounds of 32 hypotheses, three cluster barriers each), not "
-                        "bandwidth-bound: each round re-reads the label's points (12 B each) from L2"}
+                "note": "stage 4 is latency-bound (rounds of 128 hypotheses, prepared one round ahead by producer warps, two "
+                        "cluster barriers each), not bandwidth-bound: each round re-reads the label's points (12 B each) from L2"}
         if cpu_base:
             v, dt, kind = cpu_path(h, w, oracle_config_like(rcfg), cloud[None], 1, 1, passes=30)
             rrec["cpu_baseline"] = {"value": v, "unit": UNIT, "us_per_frame": 1e6 / v, "cores": 1, "kind": kind,

@@ -40,6 +40,10 @@
 
 #include "exact_math.cuh"
 
+#if defined(DPX_DEBUG_CHECKS) && !defined(DPX_REFINE_FORCE_RESEED)
+#define DPX_REFINE_FORCE_RESEED  // the debug build also walks the generator's regeneration path (never taken otherwise)
+#endif
+
 namespace dpx {
 namespace {
 
@@ -81,7 +85,7 @@ struct RefShared {
 };
 
 #ifdef DPX_REFINE_PROBE
-__device__ long long g_refine_probe_cnt[2];  // twists, reseeds (frame 0)
+__device__ long long g_refine_probe_cnt[4];  // frame 0: generator blocks made, reseeds, rounds sampled draw by draw / in more than one pass
 #endif
 // ---- std::mt19937, executed by warp 0 of the leader (all lanes compute the same values) -----------------------
 // The next block of 624 words from the current one, out of place:
@@ -131,7 +135,11 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
 template <class S>
 __device__ __forceinline__ void gen_cover(S& s, const uint32_t* mt_init, int lane, int& gen_hi, int t_lo, int t_hi) {
   const int b_lo = t_lo / kMtN, b_hi = t_hi / kMtN;
+#ifdef DPX_REFINE_FORCE_RESEED  // test builds: take the regeneration path on every step back (tools/gpu_debug_checks.sh)
+  if (b_lo < gen_hi) {
+#else
   if (b_lo < gen_hi - (S::kRing - 1)) {
+#endif
     for (int i = lane; i < kMtN; i += 32) s.mtb[0][i] = mt_init[i];
     __syncwarp();
     gen_hi = 0;
@@ -633,7 +641,13 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
       int start = 96 * warp, used = 0, a = -1, b = -1, c = -1, cum = 0;
       int grp_start = -1, used_own = 0;  // the offset this warp's current result was computed at, the draws it took
       bool settled = false, serial = false;
+#ifdef DPX_REFINE_PROBE
+      bool grp_multi = false;
+#endif
       for (int it = 0; it < kSub && !settled; ++it) {
+#ifdef DPX_REFINE_PROBE
+        grp_multi = it > 0;
+#endif
         if (it == 0 || grp_start != start) {
           used_own = sample_group(gp0 + start, a, b, c, cum);
           grp_start = start;
@@ -655,6 +669,10 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
         start = mine_start;
         used = sum;  // total of the round (final once settled)
       }
+#ifdef DPX_REFINE_PROBE
+      if (tid == 0 && blockIdx.x == 0 && grp_multi) g_refine_probe_cnt[3] += 1;
+      if (tid == 0 && blockIdx.x == 0 && (serial || !settled)) g_refine_probe_cnt[2] += 1;
+#endif
       if (serial || !settled) {
         // exact path: warp 0 walks the groups in order, a group that does not settle draw by draw
         if (warp == 0) {
@@ -917,9 +935,9 @@ extern "C" __attribute__((visibility("default"))) int dpx_debug_refine_probe(lon
   cudaDeviceSynchronize();
   if (out) cudaMemcpyFromSymbol(out, dpx::g_refine_probe, sizeof(long long) * 24);
   {
-    long long cnt[2];
+    long long cnt[4];
     cudaMemcpyFromSymbol(cnt, dpx::g_refine_probe_cnt, sizeof(cnt));
-    fprintf(stderr, "[refine probe] twists %lld reseeds %lld (since load)\n", cnt[0], cnt[1]);
+    fprintf(stderr, "[refine probe] since load, frame 0: generator blocks %lld, reseeds %lld, rounds sampled draw by draw %lld, in several passes %lld\n", cnt[0], cnt[1], cnt[2], cnt[3]);
   }
   if (reset) {
     long long zero[24] = {};

@@ -41,6 +41,22 @@ def test_refinement_parameters_and_batches(oracle_mod, threshold, ratio, iters):
         assert np.array_equal(labels[f], ref), f"frame {f}: {(labels[f] != ref).sum()} pixels differ"
 
 
+@pytest.mark.parametrize("frames", [12, 20])
+def test_refinement_batch_sizes_reach_every_kernel_variant(oracle_mod, frames):
+    """The launcher picks the cluster size and register budget by batch size (refine.cu launch_refine): up to 9 frames
+    get 16-CTA clusters (the tests above), up to 18 get 8-CTA clusters with the full register budget, larger batches
+    8-CTA clusters at two CTAs per SM.  Same labels from all of them."""
+    from deplex_b200 import Config, PlaneExtractor, synth, LAYOUT_ROWMAJOR
+    h, w = 480, 640
+    cfg = Config(ransac_refinement=1, ransac_threshold=3.0, ransac_inliers_ratio=0.5, ransac_max_iterations=200)
+    batch = synth.make_batch(h, w, 9090 + frames, frames, "rowmajor")
+    labels = PlaneExtractor(h, w, cfg, max_batch=frames).process_batch_host(batch, LAYOUT_ROWMAJOR)
+    ocfg = to_oracle_cfg(oracle_mod, cfg)
+    for f in range(frames):
+        ref = oracle_mod.process(h, w, ocfg, batch[f])
+        assert np.array_equal(labels[f], ref), f"frame {f} of {frames}: {(labels[f] != ref).sum()} pixels differ"
+
+
 def test_refinement_mse_not_worse():
     """cpp/tests/test_refinement.cpp:43-75 on the GPU path: the MSE of the points labelled 1 does not grow."""
     from deplex_b200 import Config, PlaneExtractor
@@ -64,6 +80,31 @@ def test_refinement_fine_grid_and_fhd(oracle_mod):
         labels = PlaneExtractor(h, w, cfg).process(xyz)
         ref = oracle_mod.process(h, w, to_oracle_cfg(oracle_mod, cfg), xyz)
         assert np.array_equal(labels, ref), f"{h}x{w}/p{patch}: {(labels != ref).sum()} pixels differ ({time.time() - t0:.1f}s)"
+
+
+def test_refinement_many_tiny_labels(oracle_mod):
+    """Hundreds of labels of one to a few 4x4 cells (n = 16, 32, ... points): sampling three distinct ranks out of 16
+    repeats all the time, so the groups of 32 hypotheses take extra draws, settle over several passes or fall back to
+    the draw-by-draw path, and the generator is rewound in every label; more labels than the shared-memory label sort
+    holds.  Both uniform_int mappings."""
+    from deplex_b200 import Config, PlaneExtractor, synth
+    h, w = 480, 640
+    for seed, iters in ((5, 300), (77, 130)):
+        cfg = Config(patch_size=4, min_region_growing_candidate_size=1, min_region_growing_cells_activated=1,
+                     ransac_refinement=1, ransac_threshold=2.0, ransac_inliers_ratio=0.95, ransac_max_iterations=iters)
+        xyz = synth.make_cloud(h, w, seed)
+        ocfg = to_oracle_cfg(oracle_mod, cfg)
+        ex = PlaneExtractor(h, w, cfg)
+        for variant in ("libstdc++11", "libstdc++10"):
+            ex.set_rng_compat(variant)
+            oracle_mod.set_uniform_int_variant(0 if variant == "libstdc++11" else 1)
+            try:
+                ref = oracle_mod.process(h, w, ocfg, xyz)
+            finally:
+                oracle_mod.set_uniform_int_variant(0)
+            labels = ex.process(xyz)
+            assert labels.max() > 256
+            assert np.array_equal(labels, ref), f"seed {seed}, mapping {variant}: {(labels != ref).sum()} pixels differ"
 
 
 def test_refinement_with_pre_gcc11_uniform_int_mapping(oracle_mod):
