@@ -8,7 +8,8 @@
 //   std::mt19937 (default seed 5489, one generator per process() call, shared across the labels) and
 //   libstdc++'s std::uniform_int_distribution<int> (GCC >= 11: Lemire's multiply-shift with rejection)
 //
-// One thread-block cluster (8 CTAs of 512 threads, distributed shared memory) per frame; CTA 0 of the cluster leads.
+// One thread-block cluster (8 CTAs of 512 threads, 16 when the launch is a few frames; distributed shared memory) per
+// frame; CTA 0 of the cluster leads.
 // The reference's loop is sequential twice over -- labels share one random stream, and each label's iterations stop as
 // soon as a hypothesis reaches the target inlier ratio -- so the cluster walks the labels in order and evaluates the
 // next kHyp = 128 hypotheses of the current label speculatively and at once.  A round is a two-stage pipeline: while

@@ -161,6 +161,25 @@ def test_synthetic_scenes_match_oracle(oracle_mod, hw, patch, layout):
     assert mismatched == 0, f"{mismatched} of {total} pixels differ"
 
 
+def test_axis_aligned_normal_on_the_histogram_wrap(oracle_mod):
+    """A frame found by tools/soak_refine.py: one cell's normal is (6e-16, -0.894, -0.447), so its azimuth is pi - 7e-16,
+    the upper edge of the last histogram bin.  glibc rounds that angle correctly; CUDA's atan2 (two ulp allowed) put the
+    cell one bin lower, which swapped the order of two seeds.  cell_walk.cuh atan2_for_bins / acos_for_bins."""
+    import torch
+    from deplex_b200 import Config, PlaneExtractor, synth, LAYOUT_ROWMAJOR
+    h, w = 720, 1280
+    cfg = Config(patch_size=4)
+    xyz = synth.make_batch(h, w, 844057 + 8, 1, "rowmajor")[0]
+    ex = PlaneExtractor(h, w, cfg)
+    labels = ex.process_batch_device(torch.from_numpy(xyz[None]).cuda(), LAYOUT_ROWMAJOR).cpu().numpy()[0]
+    ref, dbg = oracle_mod.process(h, w, to_oracle_cfg(oracle_mod, cfg), xyz, debug=True)
+    cells = ex.cells(0)
+    assert np.array_equal(cells["bin"], dbg["cell_bin"])
+    assert dbg["cell_bin"][11244] == 386          # yq = 19: the wrap
+    assert np.array_equal(cells["seg_label"], dbg["cell_seglabel"])
+    assert np.array_equal(labels, ref)
+
+
 def test_batch_equals_single_and_is_idempotent(oracle_mod):
     """Size-independent properties at BASELINE's batch size: a 256-frame batch gives the same labels as frame-by-frame
     calls, twice in a row, on the device-resident and the host path, in either layout."""
