@@ -138,6 +138,7 @@ size_t carve_tables(const Geometry& g, int max_batch, bool bins_in_smem, char* b
   tb->segs = reinterpret_cast<float*>(take(F * P * kSegFloats * sizeof(float)));
   tb->merge = reinterpret_cast<int32_t*>(take(F * P * sizeof(int32_t)));
   tb->n_planes = reinterpret_cast<int32_t*>(take(F * sizeof(int32_t)));
+  tb->axis_work = reinterpret_cast<int32_t*>(take((1 + kAxisWorkCap) * sizeof(int32_t)));
   return off;
 }
 
@@ -200,7 +201,7 @@ dpx_status run_stages(dpx_extractor* ex, const float* d_xyz, int n_frames, int l
     ra.labels = ex->fuse_labeling ? d_labels : nullptr;
     ra.labels_vec_ok = labels_vec_ok(ex->geom, d_labels) ? 1 : 0;
     DPX_CUDA(ex, launch_region_grow(ra, st, &labels_painted));
-    ex->launches += region_grow_mode(ex->geom, ex->thr) >= 1 ? 3 : 2;  // edge masks (+ seed sort) + region growing
+    ex->launches += region_grow_mode(ex->geom, ex->thr) >= 1 ? 4 : 3;  // edge masks + axis repair (+ seed sort) + region growing
   }
   if (prof) DPX_CUDA(ex, cudaEventRecord(ex->e_stage[2], st));
   {
@@ -433,6 +434,8 @@ dpx_status dpx_create(int32_t height, int32_t width, const dpx_config* cfg_in, i
     cudaError_t e = cudaMalloc(&ex->scratch, ex->scratch_bytes);
     if (e != cudaSuccess) { delete ex; return cuda_fail(nullptr, e, "cudaMalloc(scratch tables)"); }
     carve_tables(g, max_batch, ex->plan.bins_smem != 0, static_cast<char*>(ex->scratch), &ex->tb);
+    e = cudaMemset(ex->tb.axis_work, 0, sizeof(int32_t));
+    if (e != cudaSuccess) { dpx_destroy(ex); return cuda_fail(nullptr, e, "cudaMemset(axis work list)"); }
   }
   if (cfg.ransac_refinement) {
     uint32_t mt[kMtN];

@@ -7,6 +7,7 @@
 #pragma once
 #include "common.cuh"
 #include "plane_fit.cuh"
+#include "normal_bins.cuh"
 
 namespace dpx {
 
@@ -276,41 +277,6 @@ __device__ void walk_cell_runtime(const float* tile, int tw, int p, int t, float
   out.valid_cnt = valid; out.hcnt = hcnt; out.vcnt = vcnt;
 }
 
-// acos / atan2 for the histogram bin (normals_histogram.cpp:33-45).  The bin is trunc((B - 1) * angle / range), so an angle
-// one ulp off flips the bin only when it sits on a bin boundary -- which generic normals never do (probability ~1e-14) and
-// axis-aligned ones do all the time: a plane whose normal lies in the y-z plane comes out of the fp64 eigen-solver with
-// nx ~ 1e-16, ny < 0, and its azimuth pi - 7e-16 is the last bin's upper edge.  glibc rounds such angles correctly, CUDA's
-// libm is allowed two ulp (a 720p frame in tools/soak_refine.py got a different seed order from one such cell).  Next to
-// the axes the angle is (a multiple of pi/2) - (a tiny arctangent / arcsine), and adding the tiny term to the constant's
-// low word first gives the correctly rounded sum; everywhere else CUDA's function is used.
-__device__ __forceinline__ double small_atan(double t) {  // |t| < 2^-20: t - t^3/3, error far below 2^-53 * |t|
-  return __dsub_rn(t, __ddiv_rn(__dmul_rn(__dmul_rn(t, t), t), 3.0));
-}
-__device__ __forceinline__ double atan2_for_bins(double s, double c) {
-  constexpr double kNear = 9.5367431640625e-07;  // 2^-20
-  constexpr double kPiHi = 3.141592653589793116, kPiLo = 1.2246467991473532e-16;
-  constexpr double kPio2Hi = 1.5707963267948966, kPio2Lo = 6.123233995736766e-17;
-  const double as = ::fabs(s), ac = ::fabs(c);
-  if (c < 0.0 && as < __dmul_rn(kNear, ac)) {  // +-(pi - eps)
-    const double r = __dadd_rn(kPiHi, __dsub_rn(kPiLo, small_atan(__ddiv_rn(as, ac))));
-    return ::signbit(s) ? -r : r;
-  }
-  if (as > 0.0 && ac < __dmul_rn(kNear, as)) {  // +-(pi/2 - eps), eps of either sign
-    const double r = __dadd_rn(kPio2Hi, __dsub_rn(kPio2Lo, small_atan(__ddiv_rn(c, as))));
-    return s < 0.0 ? -r : r;
-  }
-  return ::atan2(s, c);
-}
-__device__ __forceinline__ double acos_for_bins(double x) {
-  constexpr double kNear = 9.5367431640625e-07;
-  constexpr double kPio2Hi = 1.5707963267948966, kPio2Lo = 6.123233995736766e-17;
-  if (::fabs(x) < kNear) {  // pi/2 - asin(x), asin(x) = x + x^3/6
-    const double a = __dadd_rn(x, __ddiv_rn(__dmul_rn(__dmul_rn(x, x), x), 6.0));
-    return __dadd_rn(kPio2Hi, __dsub_rn(kPio2Lo, a));
-  }
-  return ::acos(x);
-}
-
 // Everything after the moments: validity, plane fit, planarity, merge tolerance, histogram bin.
 __device__ __forceinline__ void finish_cell(const CellRaw& raw, const Thresholds& th, const Tables& tb, long long cell) {
   const bool valid = static_cast<unsigned long long>(raw.valid_cnt) >= th.valid_pts_threshold &&
@@ -340,26 +306,12 @@ __device__ __forceinline__ void finish_cell(const CellRaw& raw, const Thresholds
     const float tol = __fmul_rn(tr, tr);
 
     if (planar) {
-      // normals_histogram.cpp:33-45 (isZero() precision 1e-5; fp64 trigonometry)
-      const float nx = fit.normal[0], ny = fit.normal[1], nz = fit.normal[2];
-      if (!(fabsf(nx) <= 1e-5f && fabsf(ny) <= 1e-5f && fabsf(nz) <= 1e-5f)) {
-        const int B = th.histogram_bins_per_coord;
-        const f64 dnx = static_cast<double>(nx), dny = static_cast<double>(ny);
-        const f64 proj = sqrt(dnx * dnx + dny * dny);
-        const double polar = acos_for_bins(static_cast<double>(-nz));
-        const double azimuth = atan2_for_bins((dnx / proj).v, (dny / proj).v);
-        const double kPi = 3.14159265358979323846;
-        const int xq = __double2int_rz(((f64(static_cast<double>(B - 1)) * (f64(polar) - f64(0.0))) / f64(kPi)).v);
-        int yq = 0;
-        if (xq > 0)
-          yq = __double2int_rz(
-              ((f64(static_cast<double>(B - 1)) * (f64(azimuth) - f64(-kPi))) / (f64(kPi) - f64(-kPi))).v);
-        const int b = yq * B + xq;
-        // outside [0, B*B) the reference writes out of bounds; such a cell is dropped here
-        if (b >= 0 && b < B * B) {
-          bin = b;
-          flags |= kFlagPlanar;
-        }
+      // (CUDA's acos / atan2 here; the few normals next to an axis, where their last ulp can decide the bin, are worked out
+      // again by the next kernel: region_grow.cu edge_mask_kernel / repair_axis_cell)
+      const int b = histogram_bin<false>(fit.normal[0], fit.normal[1], fit.normal[2], th.histogram_bins_per_coord);
+      if (b >= 0) {
+        bin = b;
+        flags |= kFlagPlanar;
       }
     }
     tb.rec_a[2 * cell] = make_float4(fit.normal[0], fit.normal[1], fit.normal[2], fit.d);

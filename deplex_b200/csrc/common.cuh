@@ -88,6 +88,8 @@ struct Tables {
   float* segs;
   int32_t* merge;
   int32_t* n_planes;
+  int32_t* axis_work;  // [1 + kAxisWorkCap] per batch: count, then the cells whose bin needs the careful path (region_grow.cu)
 };
+constexpr int kAxisWorkCap = 65535;
 
 }  // namespace dpx

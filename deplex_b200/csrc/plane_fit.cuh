@@ -11,6 +11,7 @@
 // Everything lives in registers: the QL iteration is unrolled over its (at most three) static
 // index patterns so that no array is dynamically indexed.
 #pragma once
+#include "cr_math.cuh"
 #include "exact_math.cuh"
 
 namespace dpx {
@@ -26,6 +27,8 @@ struct Eig3 {
 };
 
 // Cardano's closed form (dsyevc3.c:46-77).  Order of the results: w[0] >= w[2] >= w[1].
+// EXACT: atan2 / sin / cos correctly rounded (cr_math.cuh) instead of CUDA's, for the cells where the last ulp shows.
+template <bool EXACT>
 __device__ __forceinline__ void eig3_values(const Sym3& A, f64 (&w)[3]) {
   const f64 de = A.a01 * A.a12;
   const f64 dd = sq(A.a01);
@@ -40,10 +43,18 @@ __device__ __forceinline__ void eig3_values(const Sym3& A, f64 (&w)[3]) {
   const f64 sqrt_p = sqrt(abs(p));
 
   f64 phi = f64(27.0) * (f64(0.25) * sq(c1) * (p - c1) + c0 * (q + f64(6.75) * c0));
-  phi = f64(1.0 / 3.0) * f64(::atan2(sqrt(abs(phi)).v, q.v));
+  {
+    const double ay = sqrt(abs(phi)).v;
+    double at = ::atan2(ay, q.v);
+    if (EXACT && ay == ay && q.v == q.v && !(ay == 0.0 && q.v == 0.0)) at = crm::atan2_cr(ay, q.v, at);
+    phi = f64(1.0 / 3.0) * f64(at);
+  }
 
   double sn, cs;
-  ::sincos(phi.v, &sn, &cs);
+  if (EXACT && phi.v >= 0.0 && phi.v <= 3.2)
+    crm::sincos_cr(phi.v, sn, cs);
+  else
+    ::sincos(phi.v, &sn, &cs);
   const f64 c = sqrt_p * f64(cs);
   const f64 s = f64(1.0 / 1.73205080756887729352744634151) * sqrt_p * f64(sn);
 
@@ -178,9 +189,10 @@ static __device__ __noinline__ void eig3_ql(const Sym3& A, Eig3& out) {
 }
 
 // dsyevh3.c:64-133.
+template <bool EXACT = false>
 __device__ __forceinline__ void eig3_hybrid(const Sym3& A, Eig3& out) {
   f64(&w)[3] = out.w;
-  eig3_values(A, w);
+  eig3_values<EXACT>(A, w);
 
   f64 t = abs(w[0]);
   f64 u = abs(w[1]);
@@ -240,6 +252,7 @@ struct PlaneFit {
 };
 
 // CellSegmentStat::fitPlane (cell_segment_stat.cpp:55-81) with mean = coord_sum_/nr_pts_ (:33,41).
+template <bool EXACT = false>
 __device__ __forceinline__ void fit_plane(const Moments& m, PlaneFit& out) {
   const float fn = static_cast<float>(m.n);
   // cov(i,j) = V(i,j) - (S_i*S_j)/n, each operation rounded to fp32 (cell_segment_stat.cpp:56)
@@ -252,7 +265,7 @@ __device__ __forceinline__ void fit_plane(const Moments& m, PlaneFit& out) {
   A.a22 = static_cast<double>(__fsub_rn(m.v[5], __fdiv_rn(__fmul_rn(m.s[2], m.s[2]), fn)));
 
   Eig3 eg;
-  eig3_hybrid(A, eg);
+  eig3_hybrid<EXACT>(A, eg);
 
   // std::min_element / std::max_element: first of equal elements (cell_segment_stat.cpp:67-68)
   int imin = 0, imax = 0;

@@ -29,6 +29,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "normal_bins.cuh"
 #include "plane_fit.cuh"
 #include "seed_sort.cuh"
 
@@ -83,6 +84,51 @@ __device__ __forceinline__ void store_seg(float* rec, const Moments& m, const Pl
 // never BFS state, so all 4*C tests of a frame are evaluated up front, fully in parallel over the batch;
 // the sequential BFS then only consults one byte per popped cell.  Bit s of edge[u] = "u may activate its
 // neighbour in slot s" (slots in the reference's push order: up, down, left, right).
+// A planar cell whose normal is next to an axis of the histogram (normal_bins.cuh bin_needs_care).  There the last ulp of
+// acos / atan2 can decide the bin -- the azimuth of (6e-16, -0.89, -0.45) is pi - 7e-16, the upper edge of the last bin --
+// so the bin is worked out again with the axis-aware functions; and when the x component is zero or rounding noise with
+// y < 0, its sign decides between the first and the last azimuth bin and hangs on the last ulp of the solver's sin / cos:
+// that cell is first fitted again with correctly rounded trigonometry (cr_math.cuh).
+// The moments come back from rec_b; the point count is the whole cell.  Out of line and rare: axis-aligned planes of
+// rendered or synthetic depth (167 of the ICL frame's 19 200 cells, none of the TUM frame's).
+__device__ __noinline__ void repair_axis_cell(const Tables& tb, int patch, int bins_per_coord, long long cell, float4 na) {
+  if (normal_on_wrap(na.x, na.y)) {
+    const float4 r0 = tb.rec_b[3 * cell], r1 = tb.rec_b[3 * cell + 1], r2 = tb.rec_b[3 * cell + 2];
+    Moments m;
+    m.n = patch * patch;
+    m.s[0] = r0.x; m.s[1] = r0.y; m.s[2] = r0.z;
+    m.v[0] = r0.w; m.v[1] = r1.x; m.v[2] = r1.y; m.v[3] = r1.z; m.v[4] = r1.w; m.v[5] = r2.x;
+    PlaneFit fit;
+    fit_plane<true>(m, fit);
+    na = make_float4(fit.normal[0], fit.normal[1], fit.normal[2], fit.d);
+    tb.rec_a[2 * cell] = na;
+  }
+  const int b = histogram_bin<true>(na.x, na.y, na.z, bins_per_coord);
+  if (b >= 0) tb.bin[cell] = static_cast<int16_t>(b);  // (always: the components that are not zero do not move)
+}
+
+// The cells edge_mask_kernel listed, a few threads for a short list (a frame of sensor data lists none: this kernel is one
+// word read).  The bins are first read after it (seed sort, region growing).  A list that overflowed is replaced by a scan.
+__global__ void __launch_bounds__(128) axis_repair_kernel(const RegionArgs args) {
+  const int count = args.tables.axis_work[0];
+  if (count == 0) return;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+  const Tables& tb = args.tables;
+  if (count <= kAxisWorkCap) {
+    for (int i = gtid; i < count; i += gsize) {
+      const long long cell = tb.axis_work[1 + i];
+      repair_axis_cell(tb, args.geom.patch, args.thr.histogram_bins_per_coord, cell, tb.rec_a[2 * cell]);
+    }
+  } else {
+    const long long total = static_cast<long long>(args.n_frames) * args.geom.n_cells;
+    for (long long cell = gtid; cell < total; cell += gsize) {
+      if (tb.bin[cell] < 0) continue;
+      const float4 na = tb.rec_a[2 * cell];
+      if (bin_needs_care(na.x, na.y, na.z)) repair_axis_cell(tb, args.geom.patch, args.thr.histogram_bins_per_coord, cell, na);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) edge_mask_kernel(const RegionArgs args) {
   const Geometry& g = args.geom;
   const long long total = static_cast<long long>(args.n_frames) * g.n_cells;
@@ -99,6 +145,12 @@ __global__ void __launch_bounds__(256) edge_mask_kernel(const RegionArgs args) {
   unsigned mask = 0;
   if (args.tables.bin[idx] >= 0) {
     const float4 nu = __ldg(args.tables.rec_a + 2 * idx);
+    // a normal next to an axis of the histogram: its bin is worked out again by axis_repair_kernel (a call in here costs this
+    // kernel half its occupancy and a stack frame; an entry in a list costs nothing)
+    if (bin_needs_care(nu.x, nu.y, nu.z)) {
+      const int pos = atomicAdd(args.tables.axis_work, 1);
+      if (pos < kAxisWorkCap) args.tables.axis_work[1 + pos] = static_cast<int>(idx);
+    }
     const double min_cos = static_cast<double>(args.thr.min_cos_angle_merge);
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
@@ -134,6 +186,7 @@ __global__ void __launch_bounds__(32) region_grow_kernel(const RegionArgs args) 
   const Thresholds& th = args.thr;
   const int lane = threadIdx.x;
   const int frame = blockIdx.x;
+  if (blockIdx.x == 0 && threadIdx.x == 0) args.tables.axis_work[0] = 0;  // the list of this batch has been worked off
   const int C = g.n_cells, nh = g.nh, nv = g.nv;
   const int B2 = th.histogram_bins_per_coord * th.histogram_bins_per_coord;
   const long long fc = static_cast<long long>(frame) * C;
@@ -646,6 +699,9 @@ cudaError_t launch_region_grow(const RegionArgs& args, cudaStream_t stream, bool
   const long long cells = static_cast<long long>(args.n_frames) * args.geom.n_cells;
   edge_mask_kernel<<<static_cast<unsigned>((cells + 255) / 256), 256, 0, stream>>>(args);
   cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  axis_repair_kernel<<<16, 128, 0, stream>>>(args);
+  e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   CtaPlan cta{};
   const int mode = cta_mode(args.geom, args.thr, &cta);
