@@ -283,8 +283,16 @@ def latency_mode(dev, calls, cpu_base):
                 racc[kk] = racc.get(kk, 0.0) + v / n_ref
         rex.set_profiling(False)
         labelled = int((d_lab != 0).sum().item())
+        point_passes, rounds = rex.refine_work(0)
+        rbytes = 12 * point_passes
         rrec = {"refine_ms": racc["refine"], "device_resident_us": sum(racc.values()) * 1e3,
                 "labelled_pixels_after": labelled,
+                "roofline": {"bound": "issue rate of the scoring loop / latency of the round pipeline (not HBM)",
+                             "rounds": rounds, "point_passes": point_passes, "algorithmic_bytes": rbytes,
+                             "gbs": rbytes / (racc["refine"] * 1e-3) / 1e9 if racc["refine"] > 0 else None,
+                             "hypothesis_evaluations_per_s": 128 * point_passes / (racc["refine"] * 1e-3) if racc["refine"] > 0 else None,
+                             "what": "12 B x (points of a label) x (rounds of 128 hypotheses scored on it), summed over the "
+                                     "frame's labels (dpx_get_refine_work); the points come from L2 after the first round"},
                 "note": "stage 4 is latency-bound (rounds of 128 hypotheses, prepared one round ahead by producer warps, two "
                         "cluster barriers each), not bandwidth-bound: each round re-reads the label's points (12 B each) from L2"}
         if cpu_base:

@@ -16,7 +16,7 @@ STAGE_NAMES = ("cell_stats", "region_grow", "labeling", "refine")
 EXPORTS = (
     "dpx_config_default", "dpx_config_load_ini", "dpx_create", "dpx_destroy", "dpx_last_error", "dpx_get_info",
     "dpx_process_host", "dpx_process_batch_host", "dpx_process_batch_device", "dpx_process_depth_batch_host",
-    "dpx_process_depth_batch_device", "dpx_get_cells", "dpx_get_planes", "dpx_get_seed_order",
+    "dpx_process_depth_batch_device", "dpx_get_cells", "dpx_get_planes", "dpx_get_seed_order", "dpx_get_refine_work",
     "dpx_set_profiling", "dpx_get_stage_ms", "dpx_get_region_profile", "dpx_kernel_launches", "dpx_host_alloc", "dpx_host_free", "dpx_version",
     "dpx_set_label_transport", "dpx_set_rng_compat", "dpx_process_batch_host_u16", "dpx_process_depth_batch_host_u16",
     "dpx_pipeline_create", "dpx_pipeline_destroy", "dpx_pipeline_last_error", "dpx_pipeline_lanes", "dpx_pipeline_lane",
@@ -96,6 +96,7 @@ def load():
         "dpx_get_cells": (C.c_int, [vp, i32, C.POINTER(dpx_cell), i32]),
         "dpx_get_planes": (C.c_int, [vp, i32, C.POINTER(dpx_plane), i32, C.POINTER(i32)]),
         "dpx_get_seed_order": (C.c_int, [vp, i32, vp, i32]),
+        "dpx_get_refine_work": (C.c_int, [vp, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
         "dpx_set_profiling": (C.c_int, [vp, i32]),
         "dpx_get_stage_ms": (C.c_int, [vp, C.POINTER(C.c_float * N_STAGES)]),
         "dpx_get_region_profile": (C.c_int, [vp, i32, C.POINTER(C.c_int64 * 12)]),

@@ -49,6 +49,7 @@ struct dpx_extractor {
   int fuse_labeling = 1;      // env DPX_FUSE_LABELING=0: keep stage 3 as its own kernel (A/B measurement)
   RegionPlan plan{};
   uint32_t* mt_init = nullptr;       // std::mt19937 default state for the refinement stage
+  unsigned long long* refine_work = nullptr;  // [max_batch][2] point passes, rounds (dpx_get_refine_work)
   long long* region_prof = nullptr;  // [max_batch][kRegionProfSlots], written while profiling is on
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
@@ -226,6 +227,7 @@ dpx_status run_stages(dpx_extractor* ex, const float* d_xyz, int n_frames, int l
     fa.threshold = ex->cfg.ransac_threshold;
     fa.inliers_ratio = ex->cfg.ransac_inliers_ratio;
     fa.mt_init = ex->mt_init;
+    fa.work = ex->refine_work;
     fa.uniform_variant = ex->uniform_variant;
     fa.geom = ex->geom;
     fa.tables = ex->tb;
@@ -442,6 +444,8 @@ dpx_status dpx_create(int32_t height, int32_t width, const dpx_config* cfg_in, i
     mt19937_default_state(mt);
     cudaError_t e = cudaMalloc(&ex->mt_init, sizeof(mt));
     if (e == cudaSuccess) e = cudaMemcpy(ex->mt_init, mt, sizeof(mt), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&ex->refine_work, static_cast<size_t>(max_batch) * 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(ex->refine_work, 0, static_cast<size_t>(max_batch) * 2 * sizeof(unsigned long long));
     if (e != cudaSuccess) { dpx_destroy(ex); return cuda_fail(nullptr, e, "cudaMalloc(mt19937 state)"); }
   }
   {
@@ -479,6 +483,7 @@ void dpx_destroy(dpx_extractor* ex) {
   if (ex->scratch) cudaFree(ex->scratch);
   if (ex->region_prof) cudaFree(ex->region_prof);
   if (ex->mt_init) cudaFree(ex->mt_init);
+  if (ex->refine_work) cudaFree(ex->refine_work);
   if (ex->d_conv) cudaFree(ex->d_conv);
   delete ex;
 }
@@ -774,6 +779,20 @@ dpx_status dpx_get_seed_order(dpx_extractor* ex, int32_t frame, uint64_t* out, i
   DeviceGuard guard(ex->device);
   DPX_CUDA(ex, cudaDeviceSynchronize());
   DPX_CUDA(ex, cudaMemcpy(out, ex->tb.skeys + static_cast<size_t>(frame) * C, static_cast<size_t>(C) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return DPX_OK;
+}
+
+dpx_status dpx_get_refine_work(dpx_extractor* ex, int32_t frame, uint64_t* point_passes, uint64_t* rounds) {
+  if (!ex || !point_passes || !rounds) return DPX_ERR_ARGUMENT;
+  *point_passes = *rounds = 0;
+  if (!ex->refine_work) return fail(ex, DPX_ERR_UNSUPPORTED, "dpx_get_refine_work: the handle was created with ransacRefinement = 0");
+  if (dpx_status rs = resident_frame(ex, frame, &frame); rs != DPX_OK) return rs;
+  DeviceGuard guard(ex->device);
+  DPX_CUDA(ex, cudaDeviceSynchronize());
+  unsigned long long w[2] = {0, 0};
+  DPX_CUDA(ex, cudaMemcpy(w, ex->refine_work + 2 * static_cast<size_t>(frame), sizeof(w), cudaMemcpyDeviceToHost));
+  *point_passes = w[0];
+  *rounds = w[1];
   return DPX_OK;
 }
 

@@ -333,7 +333,10 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
   im.p = p; im.p2 = p2; im.nh = nh; im.width = g.width;
   im.narrow = g.width < (1 << 24);
   const int nseg = args.tables.n_planes[frame];
-  if (nseg <= 0) return;  // no plane: nothing is labelled (plane_extractor.cpp:230-232); the whole cluster leaves
+  if (nseg <= 0) {  // no plane: nothing is labelled (plane_extractor.cpp:230-232); the whole cluster leaves
+    if (leader && tid == 0 && args.work) args.work[2 * frame] = args.work[2 * frame + 1] = 0;
+    return;
+  }
 
   const int32_t* cell_label = args.tables.cell_label + fc;
   int32_t* lab_cells = args.tables.queue + fc;                               // [C] cells sorted by (label, cell id)
@@ -356,6 +359,7 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
 
   // the generator (warp 0 of the leader): position of the next draw in the stream, newest block in the ring
   int gp = kMtN, gen_hi = 0;
+  unsigned long long work_points = 0, work_rounds = 0;  // (leader, thread 0) what the frame's search scored
   if (tid < kHyp) s.loss_cta[tid] = 0;
   __syncthreads();
   if (leader) {
@@ -824,6 +828,8 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
           // IsContinued holds, which is monotone (the best loss only falls, the iteration count only grows), so the number
           // of iterations really run is the number of hypotheses whose check passes.  Losses are counts: the reference's
           // doubles hold the same integers, HUGE_VAL is kNoLoss here.
+          work_points += static_cast<unsigned long long>(n);
+          work_rounds += 1;
           const unsigned best0 = s.bestloss;
           const int iter0 = s.iteration;
           unsigned mine[kSub], pre[kSub];  // this lane's losses; their running minimum
@@ -922,6 +928,10 @@ __global__ void __launch_bounds__(kRefThreads, MINB) refine_kernel(const RefineA
     inlier_pass(1, last_inlier());
   }
   cluster.sync();  // no CTA leaves while another may still touch its shared memory
+  if (leader && tid == 0 && args.work) {
+    args.work[2 * frame] = work_points;
+    args.work[2 * frame + 1] = work_rounds;
+  }
 #ifdef DPX_REFINE_PROBE
   if (tid == 0 && blockIdx.x < 2)  // frame 0: the leader's thread 0 (a producer) and thread 0 of the next CTA (a scorer)
     for (int i = 0; i < 12; ++i) g_refine_probe[(blockIdx.x ? 12 : 0) + i] += rp_acc[i];

@@ -16,6 +16,7 @@ struct RefineArgs {
   Geometry geom;
   Tables tables;       // reads cell_label / n_planes; uses queue and pairs as scratch
   int32_t* labels;     // [F][H*W], updated in place
+  unsigned long long* work;  // [F][2] out (may be null): point passes and rounds of the frame (dpx_get_refine_work)
 };
 
 constexpr int kMtN = 624;

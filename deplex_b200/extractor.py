@@ -261,6 +261,13 @@ class PlaneExtractor:
         self._check(self._lib.dpx_get_seed_order(self._h, frame, out.ctypes.data, n))
         return out[:n]
 
+    def refine_work(self, frame=0):
+        """(point_passes, rounds) of the refinement stage on one frame of the last batch (dpx_get_refine_work): every point
+        pass reads 12 bytes and scores 128 hypotheses."""
+        pp, rr = C.c_uint64(0), C.c_uint64(0)
+        self._check(self._lib.dpx_get_refine_work(self._h, frame, C.byref(pp), C.byref(rr)))
+        return int(pp.value), int(rr.value)
+
     # ---- measurement ----------------------------------------------------------------------------------
     def set_profiling(self, enabled):
         self._check(self._lib.dpx_set_profiling(self._h, 1 if enabled else 0))

@@ -163,6 +163,12 @@ DPX_API dpx_status dpx_get_planes(dpx_extractor* ex, int32_t frame, dpx_plane* o
  * bin (first strict-minimum MSE, plane_extractor.cpp:309-316) is the first entry of the bin's run that is still unassigned. */
 DPX_API dpx_status dpx_get_seed_order(dpx_extractor* ex, int32_t frame, uint64_t* out, int32_t capacity);
 
+/* Work of the refinement stage (ransacRefinement=1) on one frame of the last batch: point_passes = sum over the frame's
+ * labels of (points of the label) x (rounds of 128 hypotheses scored on them) -- each point pass reads 12 bytes and evaluates
+ * 128 hypotheses; rounds = the rounds themselves.  Replaces nothing in the reference (plane_extractor.cpp:472-509 does not
+ * count); it is what bench.py's roofline of the stage is computed from. */
+DPX_API dpx_status dpx_get_refine_work(dpx_extractor* ex, int32_t frame, uint64_t* point_passes, uint64_t* rounds);
+
 /* ---- measurement: CUDA-event time of each stage of the last dpx_process_batch_device call ---- */
 DPX_API dpx_status dpx_set_profiling(dpx_extractor* ex, int32_t enabled);
 DPX_API dpx_status dpx_get_stage_ms(dpx_extractor* ex, float ms[DPX_N_STAGES]);

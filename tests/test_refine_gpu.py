@@ -57,6 +57,23 @@ def test_refinement_batch_sizes_reach_every_kernel_variant(oracle_mod, frames):
         assert np.array_equal(labels[f], ref), f"frame {f} of {frames}: {(labels[f] != ref).sum()} pixels differ"
 
 
+def test_refine_work_counter(oracle_mod):
+    """dpx_get_refine_work: rounds of 128 hypotheses and point passes of one frame.  ransacMaxIterations = 300 with a ratio
+    no hypothesis reaches means every label runs ceil(300 / 128) = 3 rounds over all of its points."""
+    from deplex_b200 import Config, PlaneExtractor, UnsupportedError
+    xyz, ini = frame_cloud("tum")
+    cfg = Config(ini, ransac_refinement=1, ransac_inliers_ratio=2.0, ransac_max_iterations=300)
+    ex = PlaneExtractor(480, 640, cfg)
+    labels_before = PlaneExtractor(480, 640, Config(ini)).process(xyz)
+    ex.process(xyz)
+    point_passes, rounds = ex.refine_work(0)
+    n_labels = len(np.unique(labels_before[labels_before > 0]))
+    assert rounds == 3 * n_labels
+    assert point_passes == 3 * int((labels_before > 0).sum())
+    with pytest.raises(UnsupportedError):
+        PlaneExtractor(480, 640, Config(ini)).refine_work(0)
+
+
 def test_refinement_mse_not_worse():
     """cpp/tests/test_refinement.cpp:43-75 on the GPU path: the MSE of the points labelled 1 does not grow."""
     from deplex_b200 import Config, PlaneExtractor
