@@ -36,6 +36,7 @@
 #include "refine.cuh"
 
 #include <cstdio>
+#include <mutex>
 
 #include <cooperative_groups.h>
 
@@ -969,9 +970,11 @@ cudaError_t launch_refine_as(const RefineArgs& args, cudaStream_t stream, bool p
   // 256-hypothesis rounds (KSUB = 8) were measured with 16-CTA clusters: 5 % faster on the TUM frame, 40 % slower on the ICL
   // frame (many small labels: more rounds that do not settle at once, twice the work thrown away at the end of each label)
   constexpr int KSUB = 4;
-  static const cudaError_t smem_ok = cudaFuncSetAttribute(refine_kernel<LAYOUT, MINB, CL, KSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                          static_cast<int>(sizeof(RefShared<KSUB>)));
-  if (smem_ok != cudaSuccess) return smem_ok;
+  // (function attributes belong to the current device: set on every launch, like the other stages do -- one process may
+  // drive several GPUs, dpx_sequence)
+  cudaError_t e = cudaFuncSetAttribute(refine_kernel<LAYOUT, MINB, CL, KSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(sizeof(RefShared<KSUB>)));
+  if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(args.n_frames) * CL, 1, 1);
   cfg.blockDim = dim3(kRefThreads, 1, 1);
@@ -985,13 +988,13 @@ cudaError_t launch_refine_as(const RefineArgs& args, cudaStream_t stream, bool p
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (CL > 8) {
-    static const cudaError_t allowed = cudaFuncSetAttribute(refine_kernel<LAYOUT, MINB, CL, KSUB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (allowed != cudaSuccess) return allowed;
+    e = cudaFuncSetAttribute(refine_kernel<LAYOUT, MINB, CL, KSUB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
   }
   if (probe_only) {
     // can this device place the clusters of the launch side by side at all?
     int n_clusters = 0;
-    const cudaError_t e = cudaOccupancyMaxActiveClusters(&n_clusters, refine_kernel<LAYOUT, MINB, CL, KSUB>, &cfg);
+    e = cudaOccupancyMaxActiveClusters(&n_clusters, refine_kernel<LAYOUT, MINB, CL, KSUB>, &cfg);
     if (e != cudaSuccess) return e;
     return n_clusters >= args.n_frames ? cudaSuccess : cudaErrorInvalidConfiguration;
   }
@@ -1000,28 +1003,39 @@ cudaError_t launch_refine_as(const RefineArgs& args, cudaStream_t stream, bool p
 
 cudaError_t launch_refine(const RefineArgs& args, cudaStream_t stream) {
   if (args.n_frames == 0 || args.geom.n_cells == 0) return cudaSuccess;
-  static const int n_sm = [] {
-    int dev = 0, v = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v;
-  }();
+  // per device (one process may drive several): SM count, and whether n 16-CTA clusters can be resident side by side
+  struct DeviceFacts {
+    int n_sm = 0;
+    signed char wide_ok[2][16] = {};  // [layout][frames]: 0 unknown, 1 yes, -1 no
+  };
+  static DeviceFacts facts[64];
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
   const bool row = args.layout == kLayoutRowMajor;
-  // A handful of frames: 16 CTAs per frame halve the scoring time of a round (the clusters must all be resident at once
-  // for that to be a gain; asked of the occupancy calculator once per frame count).
-  if (args.n_frames * kRefClusterWide <= n_sm) {
-    static int wide_ok[16] = {};  // per frame count: 0 unknown, 1 yes, -1 no
-    int& ok = wide_ok[args.n_frames & 15];
-    if (ok == 0) {
-      const cudaError_t e = row ? launch_refine_as<kLayoutRowMajor, 1, kRefClusterWide>(args, stream, true)
-                                : launch_refine_as<kLayoutColMajor, 1, kRefClusterWide>(args, stream, true);
-      ok = e == cudaSuccess ? 1 : -1;
-      (void)cudaGetLastError();
+  bool wide = false;
+  int n_sm = 0;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    DeviceFacts& f = facts[dev & 63];
+    if (f.n_sm == 0) cudaDeviceGetAttribute(&f.n_sm, cudaDevAttrMultiProcessorCount, dev);
+    n_sm = f.n_sm;
+    // A handful of frames: 16 CTAs per frame halve the scoring time of a round (the clusters must all be resident at once
+    // for that to be a gain; asked of the occupancy calculator once per device and frame count).
+    if (args.n_frames * kRefClusterWide <= n_sm && args.n_frames < 16) {
+      signed char& ok = f.wide_ok[row ? 0 : 1][args.n_frames];
+      if (ok == 0) {
+        const cudaError_t e = row ? launch_refine_as<kLayoutRowMajor, 1, kRefClusterWide>(args, stream, true)
+                                  : launch_refine_as<kLayoutColMajor, 1, kRefClusterWide>(args, stream, true);
+        ok = e == cudaSuccess ? 1 : -1;
+        (void)cudaGetLastError();
+      }
+      wide = ok > 0;
     }
-    if (ok > 0)
-      return row ? launch_refine_as<kLayoutRowMajor, 1, kRefClusterWide>(args, stream, false)
-                 : launch_refine_as<kLayoutColMajor, 1, kRefClusterWide>(args, stream, false);
   }
+  if (wide)
+    return row ? launch_refine_as<kLayoutRowMajor, 1, kRefClusterWide>(args, stream, false)
+               : launch_refine_as<kLayoutColMajor, 1, kRefClusterWide>(args, stream, false);
   if (args.n_frames * kRefCluster <= n_sm)
     return row ? launch_refine_as<kLayoutRowMajor, 1, kRefCluster>(args, stream, false) : launch_refine_as<kLayoutColMajor, 1, kRefCluster>(args, stream, false);
   return row ? launch_refine_as<kLayoutRowMajor, 2, kRefCluster>(args, stream, false) : launch_refine_as<kLayoutColMajor, 2, kRefCluster>(args, stream, false);

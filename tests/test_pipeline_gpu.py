@@ -148,6 +148,22 @@ def test_sequence_extractor_matches_frame_by_frame(oracle_mod):
     seq.close()
 
 
+def test_sequence_with_refinement_on_every_gpu(oracle_mod):
+    """The refinement kernel's launch variants (16-CTA clusters need a per-device function attribute) through the sequence
+    API: one worker thread per GPU in one process, chunks of 4, 2 and 1 frames.  With one GPU visible the same device is
+    listed twice (two handles, two threads)."""
+    import torch
+    from deplex_b200 import Config, SequenceExtractor, LAYOUT_ROWMAJOR
+    h, w, n = 480, 640, 7
+    _, clouds, _ = _batch(h, w, 6600, n)
+    cfg = Config(ransac_refinement=1, ransac_threshold=3.0, ransac_inliers_ratio=0.5, ransac_max_iterations=200)
+    ref = oracle_mod.process_batch(h, w, to_oracle_cfg(oracle_mod, cfg), clouds, 1, os.cpu_count() or 1)
+    devices = list(range(torch.cuda.device_count())) if torch.cuda.device_count() > 1 else [0, 0]
+    seq = SequenceExtractor(h, w, cfg, devices=devices, max_batch=4)
+    assert np.array_equal(seq.process_host(clouds, LAYOUT_ROWMAJOR), ref)
+    seq.close()
+
+
 def test_sequence_device_resident_capi(oracle_mod):
     """dpx_sequence_process_device: every device runs its resident frames through a lanes-deep pipeline."""
     import torch
