@@ -14,25 +14,32 @@
 // soon as a hypothesis reaches the target inlier ratio -- so the cluster walks the labels in order and evaluates the
 // next kHyp = 128 hypotheses of the current label speculatively and at once.  A round is a two-stage pipeline: while
 // the cluster scores round r, four producer warps of the leader prepare round r + 1 as if round r ran to its end.
-//   producers  (leader, warps 0-3).  Warp 0 draws the sample ranks, 32 hypotheses at a time: the next generator outputs
-//              are tempered in parallel into a tape and lane h takes outputs from 3h on; rejections of the distribution
-//              and repeated samples shift the lanes behind them (a prefix sum, iterated to a fixed point), and a group
-//              that does not settle takes the exact draw-by-draw path.  The draws each hypothesis took are remembered.
-//              The generator's blocks of 624 words live in a ring of three, each twisted out of place from the one
-//              before, so any position of the last ~1200 draws can be returned to by resetting a counter.
-//              Then 128 threads turn (hypothesis, sample) ranks into pixels -- the k-th pixel of a label in image
-//              order follows from the label's cells sorted by cell id (cells are painted whole), no per-pixel index
-//              lists -- build the plane models (fp32, the reference's expression order) and push them into every
-//              CTA's shared memory;
-//   scorers    (every other warp of the 8 CTAs).  A warp stages 32 points in shared memory, then lane g scores
-//              hypotheses g, g + 32, g + 64, g + 96 on each of them (the loss is a count, so the order of the points
-//              is free); per-warp counts are summed per CTA and go to the leader with one distributed-shared-memory
-//              atomic per hypothesis;
+//   producers  (leader, warps 0-3), one warp per group of 32 hypotheses.  Sampling: in the common case each hypothesis'
+//              three generator outputs are accepted by the distribution and distinct, read straight from the generator's
+//              block (96 draws per group); otherwise the group's next 128 outputs go to a tape, lane h takes outputs from
+//              3h on, and rejections and repeated samples shift the lanes behind them (a prefix sum, iterated to a fixed
+//              point).  Group w starts as if the groups before it took 96 draws each; a small table and one named barrier
+//              per pass tell the warps whether that held, and the groups behind one with extra draws go again.  A round
+//              that does not settle takes the exact path (warp 0, group by group, draw by draw where it must).  The draws
+//              each hypothesis took are remembered.
+//              The generator's blocks of 624 words live in a ring of three, each made out of place from the one before,
+//              so any position of the last ~1200 draws can be returned to by resetting a counter.
+//              Then thread h turns its three ranks into pixels -- the k-th pixel of a label in image order follows from
+//              the label's cells sorted by cell id (cells are painted whole), no per-pixel index lists; the divisions
+//              are multiply-shifts -- builds the plane model (fp32, the reference's expression order) and pushes it into
+//              every CTA's shared memory;
+//   scorers    (every other warp of the cluster; in a 16-CTA cluster the leader does not score).  An equal share of the
+//              label's points per warp; a warp stages 32 points in shared memory, then lane g scores hypotheses g,
+//              g + 32, g + 64, g + 96 on each of them (the loss is a count, so the order of the points is free); per-warp
+//              counts are summed per CTA and go to the leader with one distributed-shared-memory atomic per hypothesis;
 //   warp 0     replays the reference's sequential loop over the 128 losses as a prefix minimum (best-so-far,
 //              IsContinued), finds how many hypotheses were really run, and leaves the generator just after the last
-//              of them when the search stops (the round prepared ahead is dropped).
-// FindInliers + the relabelling loop (which stops at the last inlier, plane_extractor.cpp:500-507) become two
-// passes: the largest inlier pixel index, then "non-inlier before it -> 0".
+//              of them when the search stops (the round prepared ahead is dropped); it pushes the continue flag and,
+//              at the end of a label, the label's model to every CTA.
+// FindInliers + the relabelling loop (which stops at the last inlier, plane_extractor.cpp:500-507) become two passes --
+// the largest inlier pixel index, then "non-inlier before it -> 0" -- run one label late by the scoring warps, behind the
+// producers' preparation of the next label's first round.  launch_refine (end of file) picks cluster size and register
+// budget by batch size.
 #include "refine.cuh"
 
 #include <cstdio>
@@ -54,7 +61,7 @@ constexpr int kRefWarps = kRefThreads / 32;
 // groups of 32 hypotheses per round: KSUB, a template parameter; 4 -> 128 hypotheses per cluster-wide pass over the label's points
 constexpr int kRefCluster = 8;   // CTAs per frame (portable cluster size limit) ...
 constexpr int kRefClusterWide = 16;  // ... or 16 (non-portable, opt-in) when the launch is a few frames only
-constexpr int kTape = 128;      // generator outputs prepared per round (32 hypotheses x 3 draws + slack)
+constexpr int kTape = 128;      // generator outputs prepared per group of 32 hypotheses (3 draws each + slack)
 constexpr int kMaxRows = 1023;  // cell rows the per-label row table can hold
 constexpr int kSortLabels = 256;  // labels the shared-memory label sort handles (kRefWarps * kSortLabels <= kCellCache)
 constexpr int kCellCache = 4096;  // cells of one label cached in shared memory (larger labels read the global list)
