@@ -10,6 +10,7 @@
 //   merge int32[F][Pcap], n_planes int32[F]
 // rec_a / rec_b are only written for valid cells; nothing reads them for the others.
 #pragma once
+#include <cstdlib>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -91,5 +92,39 @@ struct Tables {
   int32_t* axis_work;  // [1 + kAxisWorkCap] per batch: count, then the cells whose bin needs the careful path (region_grow.cu)
 };
 constexpr int kAxisWorkCap = 65535;
+
+// ---- programmatic dependent launch --------------------------------------------------------------------------------
+// The stages of a batch are short kernels that depend on each other; between two of them the GPU drains one grid and
+// dispatches the next, a few microseconds each time.  A kernel launched with the programmatic-serialization attribute is
+// dispatched while its predecessor in the stream is still running and waits, at `pdl_wait()` (its first instruction
+// here), until that grid has completed and its memory is visible -- the ordering is the same, the dispatch is off the
+// critical path.  DPX_PDL=0 / 1 overrides the default.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+constexpr bool kPdlDefault = true;
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("DPX_PDL");
+    return (e && *e) ? std::atoi(e) != 0 : kPdlDefault;
+  }();
+  return on;
+}
+#ifdef __CUDACC__
+template <class... KArgs, class... Args>
+inline cudaError_t launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 }  // namespace dpx

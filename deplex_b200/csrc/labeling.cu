@@ -20,6 +20,7 @@ constexpr int kLabelThreads = 128;
 
 // grid: x = column groups, y = cell row, z = frame
 __global__ void __launch_bounds__(kLabelThreads) labeling_kernel(const LabelArgs args) {
+  pdl_wait();
   const Geometry& g = args.geom;
   const int p = g.patch;
   const int col = (blockIdx.x * kLabelThreads + threadIdx.x) * 4;
@@ -94,7 +95,7 @@ cudaError_t launch_labeling(const LabelArgs& args, cudaStream_t stream) {
     return cudaMemsetAsync(args.labels, 0, sizeof(int32_t) * g.n_points * args.n_frames, stream);
   const int groups = (g.width + 3) / 4;
   dim3 grid((groups + kLabelThreads - 1) / kLabelThreads, g.nv, args.todo ? labeling_deferred_frames(args.n_frames) : args.n_frames);
-  labeling_kernel<<<grid, kLabelThreads, 0, stream>>>(args);
+  if (const cudaError_t e = launch_dependent(labeling_kernel, dim3(grid), dim3(kLabelThreads), 0, stream, args); e != cudaSuccess) return e;
   return cudaGetLastError();
 }
 

@@ -110,6 +110,7 @@ __device__ __noinline__ void repair_axis_cell(const Tables& tb, int patch, int b
 // The cells edge_mask_kernel listed, a few threads for a short list (a frame of sensor data lists none: this kernel is one
 // word read).  The bins are first read after it (seed sort, region growing).  A list that overflowed is replaced by a scan.
 __global__ void __launch_bounds__(128) axis_repair_kernel(const RegionArgs args) {
+  pdl_wait();
   const int count = args.tables.axis_work[0];
   if (count == 0) return;
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(128) axis_repair_kernel(const RegionArgs args)
 }
 
 __global__ void __launch_bounds__(256) edge_mask_kernel(const RegionArgs args) {
+  pdl_wait();
   const Geometry& g = args.geom;
   const long long total = static_cast<long long>(args.n_frames) * g.n_cells;
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -685,8 +687,7 @@ int cta_mode(const Geometry& g, const Thresholds& th, CtaPlan* plan) {
 template <int MODE>
 cudaError_t launch_cta(const RegionArgs& args, const CtaPlan& plan, cudaStream_t stream) {
   cudaFuncSetAttribute(region_grow_cta_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.bytes));
-  region_grow_cta_kernel<MODE><<<args.n_frames, kCtaThreads, plan.bytes, stream>>>(args, plan);
-  return cudaGetLastError();
+  return launch_dependent(region_grow_cta_kernel<MODE>, dim3(args.n_frames), dim3(kCtaThreads), plan.bytes, stream, args, plan);
 }
 }  // namespace
 
@@ -697,11 +698,9 @@ cudaError_t launch_region_grow(const RegionArgs& args, cudaStream_t stream, bool
   if (painted) *painted = false;
   if (args.n_frames == 0) return cudaSuccess;
   const long long cells = static_cast<long long>(args.n_frames) * args.geom.n_cells;
-  edge_mask_kernel<<<static_cast<unsigned>((cells + 255) / 256), 256, 0, stream>>>(args);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_dependent(edge_mask_kernel, dim3(static_cast<unsigned>((cells + 255) / 256)), dim3(256), 0, stream, args);
   if (e != cudaSuccess) return e;
-  axis_repair_kernel<<<16, 128, 0, stream>>>(args);
-  e = cudaGetLastError();
+  e = launch_dependent(axis_repair_kernel, dim3(16), dim3(128), 0, stream, args);
   if (e != cudaSuccess) return e;
   CtaPlan cta{};
   const int mode = cta_mode(args.geom, args.thr, &cta);

@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(kCtaThreads) region_grow_cta_kernel(const Regi
   const Geometry& g = args.geom;
   const Thresholds& th = args.thr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_wait();
   const int frame = blockIdx.x;
   if (blockIdx.x == 0 && threadIdx.x == 0) args.tables.axis_work[0] = 0;  // the list of this batch has been worked off
   const int C = g.n_cells, nh = g.nh, nv = g.nv;
